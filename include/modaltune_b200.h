@@ -1,0 +1,136 @@
+/*
+ * modaltune_b200 -- C ABI of the B200 (sm_100a) kernels for the ModalTune-GigaPath fine-tuning hot path.
+ *
+ * The reference (martellab-sri/ModalTune) is pure Python: it has no FFI layer.  Its only native boundary on this path
+ * is `flash_attn_func(q, k, v, dropout, bias, softmax_scale, is_causal) -> (out, lse)`
+ * (models/prov_gigapath/gigapath/torchscale/component/flash_attention.py:11-28), everything else is ATen ops reached
+ * through nn.Module.forward.  Each entry point below therefore names the reference Python function it replaces; the
+ * Python side (modaltune_b200/_lib.py, ops.py) binds them with ctypes and wraps them in torch.autograd.Functions, and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers to DEVICE memory, sizes as int64_t, no torch types;  `stream` is a cudaStream_t passed as void*.
+ *   - dtype codes: MT_F32 = 0 (float), MT_BF16 = 1 (__nv_bfloat16).  Statistics (mean, rstd, lse, delta) are float.
+ *   - the caller owns every buffer (outputs and workspaces are pre-allocated by the caller); kernels never allocate.
+ *   - return value: 0 on success, otherwise a cudaError_t / negative MT_E* code; mt_last_error() gives the message.
+ *   - single host thread per process, one process per GPU.  No CPU fallback exists behind any entry point.
+ */
+#ifndef MODALTUNE_B200_H
+#define MODALTUNE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MT_F32 0
+#define MT_BF16 1
+
+#define MT_E_BADARG (-1)
+#define MT_E_UNSUPPORTED (-2)
+
+#define MT_MAX_BRANCHES 8
+
+/* Geometry of LongNet dilated attention for one sequence (torchscale/component/dilated_attention.py:82-144).
+ * Branch b uses segment length seg_len[b] (already clamped: g = min(sl, n_tokens)) and dilation ratio[b];
+ * head h keeps in-segment offsets floor(h*ratio/n_heads) + j*ratio. */
+typedef struct {
+  int32_t n_tokens;   /* N, cls included                      */
+  int32_t n_heads;    /* 16                                   */
+  int32_t head_dim;   /* 48                                   */
+  int32_t n_branches; /* <= MT_MAX_BRANCHES                   */
+  int32_t seg_len[MT_MAX_BRANCHES];
+  int32_t ratio[MT_MAX_BRANCHES];
+} mt_dilated_geometry;
+
+const char* mt_last_error(void);
+int mt_version(void);
+/* 1 when the running device is sm_100 (tcgen05 / TMA kernels usable), 0 otherwise, <0 on error */
+int mt_device_is_sm100(void);
+
+/* ---- A0: PatchEmbed epilogue + positional embedding + cls row -----------------------------------------------------
+ * replaces: PatchEmbed.forward bias add (slide_encoder.py:52-56), `x + pos_embed[:, pos]`, cls concat
+ * (longvit_adapter.py:232-246) and coords_to_pos (slide_encoder.py:198-211).
+ * proj [L, E] = feats @ W^T (GEMM result, dtype `proj_dtype`), bias [E] f32, coords [L,2] f32 (pixels),
+ * table [ngrids, E/2] f32 = 1-D sincos factor, cls [E] f32  ->  x [L+1, E] f32 (row 0 = cls). */
+int mt_embed_assemble(const void* proj, int proj_dtype, const float* bias, const float* coords, const float* table,
+                      const float* cls, float* x, int64_t n_tiles, int64_t embed, int64_t ngrids, float tile_size,
+                      void* stream);
+
+/* ---- A1: LayerNorm ------------------------------------------------------------------------------------------------
+ * replaces: nn.LayerNorm calls in EncoderLayer.forward (torchscale/architecture/encoder.py:137-166) and in
+ * CrossAttentionLayer.forward_pre (models/vitadapter/adapter_modules.py:217-218).
+ * fwd: y = (x - mean) * rstd * gamma + beta [+ add[row % add_rows]].  x [rows, cols] x_dtype, y y_dtype. */
+int mt_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, const void* add, int add_dtype,
+                     int64_t add_rows, void* y, int y_dtype, float* mean, float* rstd, int64_t rows, int64_t cols,
+                     float eps, void* stream);
+/* bwd: dx = LN'(dy) [+ residual];  optional dgamma/dbeta [cols] f32 (accumulated with atomics into zeroed buffers). */
+int mt_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma, const float* mean,
+                     const float* rstd, const void* residual, int res_dtype, void* dx, int dx_dtype, float* dgamma,
+                     float* dbeta, int64_t rows, int64_t cols, void* stream);
+
+/* ---- A6: GELU(fp32) + LayerNorm(3072) between fc1 and fc2 ---------------------------------------------------------
+ * replaces: `activation_fn(x.float()).type_as(x)` + ffn_layernorm (torchscale/component/feedforward_network.py:135-140)
+ * h [rows, cols] = fc1 output (bias included).  y = LN(gelu_erf(h)). */
+int mt_gelu_ln_fwd(const void* h, int h_dtype, const float* gamma, const float* beta, void* y, int y_dtype,
+                   float* mean, float* rstd, int64_t rows, int64_t cols, float eps, void* stream);
+/* dh = gelu'(h) * LN'(dy) with u = gelu(h) recomputed. */
+int mt_gelu_ln_bwd(const void* dy, int dy_dtype, const void* h, int h_dtype, const float* gamma, const float* mean,
+                   const float* rstd, void* dh, int dh_dtype, int64_t rows, int64_t cols, void* stream);
+
+/* ---- A3/A4: dilated attention, all branches, per-branch outputs ---------------------------------------------------
+ * replaces: DilatedAttention.gathering x3 + attention_ops -> flash_attn_func, 5 times per layer
+ * (torchscale/component/dilated_attention.py:82-111,216-252; multihead_attention.py:109-119; flash_attention.py:11-28).
+ * qkv [n_alloc, 3*E] (q | k | v, head-major inside each), row stride `qkv_ld` elements, rows >= n_tokens must be zero
+ * and n_alloc a multiple of 16 (sm100 path reads them through TMA).
+ * o_br : compact per-branch outputs, branch b at element offset sum_{b'<b} N*E/r_b', layout [N][E/r_b]: row p holds the
+ *        16/r_b heads that own position p (heads (p%r)*16/r ..), each head_dim wide.           (dtype)
+ * lse_br: same compaction, [N][H/r_b] float, natural-log LSE including the zero-slot keys.
+ * impl: 0 = SIMT fp32 math (any dtype), 1 = tcgen05/TMA (bf16 only). */
+int mt_dilated_attn_fwd(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc, int dtype,
+                        void* o_br, float* lse_br, int impl, void* stream);
+
+/* ---- A5 (+ inner_attn_ln of A2): LSE merge of the branches fused with LayerNorm -----------------------------------
+ * replaces: DilatedAttention.scattering (dilated_attention.py:113-144) + inner_attn_ln (:257-258).
+ * attn [N,E] (dtype) = sum_b softmax_b(lse_b) o_b, lse [N,H] f32 = log sum_b exp(lse_b); y = LN(attn). */
+int mt_dilated_merge_ln_fwd(const mt_dilated_geometry* geom, const void* o_br, const float* lse_br, int dtype,
+                            void* attn, float* lse, const float* gamma, const float* beta, float eps, void* y,
+                            float* mean, float* rstd, void* stream);
+/* backward of LN then of the (detached-weight) merge.  attn is recomputed from o_br / lse_br (never stored):
+ * dattn [N,E] (dtype) = LN'(dy);  delta_br (lse_br compaction, f32) = dattn[p,h,:] . o_b[p,h,:]. */
+int mt_dilated_merge_ln_bwd(const mt_dilated_geometry* geom, const void* dy, const void* o_br, const float* lse_br,
+                            const float* gamma, const float* mean, const float* rstd, int dtype, void* dattn,
+                            float* delta_br, void* stream);
+
+/* ---- backward of A3/A4/A5 -----------------------------------------------------------------------------------------
+ * replaces: autograd of the five flash_attn_func calls + gather/scatter (no reference source; flash-attn bwd).
+ * dS_b = exp(S - LSE) * (dO V^T - delta_b);  dqkv_f32 [N, 3E] float is ZEROED by the call and accumulated with
+ * reductions over branches. */
+int mt_dilated_attn_bwd(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,
+                        const void* dattn, const float* lse, const float* delta_br, int dtype, float* dqkv_f32,
+                        int impl, void* stream);
+
+/* ---- A7/A8: Injector / Extractor cross-attention core (12 heads x 16) ---------------------------------------------
+ * replaces: the softmax(QK^T/4)V inside nn.MultiheadAttention called from CrossAttentionLayer.forward_pre
+ * (models/vitadapter/adapter_modules.py:225-229); the projections around it stay GEMMs.
+ * q [Lq, E'] , k,v [Lk, E'] (E' = heads*head_dim = 192), o [Lq, E'], lse [Lq, heads] f32.  Any Lq/Lk: few-query/many-key
+ * (Extractor) runs split-K over Lk with an LSE combine, many-query/few-key (Injector) keeps K/V in shared memory. */
+int mt_cross_attn_fwd(const void* q, const void* k, const void* v, int dtype, void* o, float* lse, int64_t lq,
+                      int64_t lk, int heads, int head_dim, float* workspace, int64_t workspace_floats, void* stream);
+int mt_cross_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                      int dtype, float* dq_f32, float* dk_f32, float* dv_f32, int64_t lq, int64_t lk, int heads,
+                      int head_dim, void* stream);
+int64_t mt_cross_attn_workspace_floats(int64_t lq, int64_t lk, int heads, int head_dim);
+
+/* ---- small fused element-wise pieces ------------------------------------------------------------------------------
+ * y[r, c] = a[r, c] + gate[c] * (a[r, c] + b[r, c])      Injector tail `query + gamma * attn` (adapter_modules.py:362)
+ *           with attn = a + b already containing the inner residual (:231).  gate may be NULL (=1).  f32 a, dtype b. */
+int mt_gated_residual(const float* a, const void* b, int b_dtype, const float* gate, float* y, int64_t rows,
+                      int64_t cols, void* stream);
+int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MODALTUNE_B200_H */

@@ -1,0 +1,350 @@
+// Injector / Extractor cross-attention core: softmax(q k^T / sqrt(16)) v with 12 heads x 16 in the 192-d compressed
+// space (models/vitadapter/adapter_modules.py:225-229 -> nn.MultiheadAttention).  The reference materialises the
+// [12, Lq, Lk] probabilities (and their head average, which it discards); here nothing of that size is ever written.
+//
+//   Injector  (Lq = tiles ~1e4, Lk = modal tokens ~66): one thread per query, K/V tiles broadcast from shared memory.
+//   Extractor (Lq ~66, Lk = tiles ~1e4): split-K over the keys (grid.z), partial (m, l, acc) per split, LSE combine.
+// Backward is two kernels, each accumulating in registers along its own loop and flushing with fp32 atomics:
+//   dq-kernel (thread per query, loop over keys) and dkv-kernel (thread per key, loop over queries).
+#include "mt_common.cuh"
+
+namespace mt {
+
+static constexpr int HD = 16;
+static constexpr int XT = 128;  // threads per CTA = rows (queries or keys) per CTA
+static constexpr int XC = 64;   // staged rows per chunk
+
+template <typename T>
+__device__ __forceinline__ void load16(const T* p, float (&v)[HD]) {
+  float a[8], b[8];
+  load8(p, a);
+  load8(p + 8, b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[j] = a[j];
+    v[8 + j] = b[j];
+  }
+}
+
+// stage rows [r0, r0+XC) of a [L, heads*HD] matrix (head h) into smem [XC][HD] (fp32); rows >= lim zero-filled
+template <typename T>
+__device__ __forceinline__ void stage16(float* dst, const T* __restrict__ src, int64_t ld, int h, int64_t r0,
+                                        int64_t lim) {
+  // XC rows x 2 chunks of 8 = 128 chunk loads = one per thread
+  const int row = threadIdx.x >> 1, ch = threadIdx.x & 1;
+  float v[8];
+  if (r0 + row < lim) {
+    load8(src + (r0 + row) * ld + h * HD + ch * 8, v);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dst[row * HD + ch * 8 + j] = v[j];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(XT) cross_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k,
+                                                       const T* __restrict__ v, T* __restrict__ o,
+                                                       float* __restrict__ lse, float* __restrict__ ws, int64_t lq,
+                                                       int64_t lk, int heads, int64_t keys_per_split) {
+  __shared__ float Ks[XC * HD], Vs[XC * HD];
+  const int h = blockIdx.y, split = blockIdx.z, nsplit = gridDim.z;
+  const int64_t qi = (int64_t)blockIdx.x * XT + threadIdx.x;
+  const int64_t ld = (int64_t)heads * HD;
+  const bool live = qi < lq;
+  float qv[HD];
+  if (live) load16(q + qi * ld + h * HD, qv);
+  else
+#pragma unroll
+    for (int j = 0; j < HD; ++j) qv[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < HD; ++j) qv[j] *= 0.25f;  // 1/sqrt(16)
+  float m = -INFINITY, l = 0.f, acc[HD];
+#pragma unroll
+  for (int j = 0; j < HD; ++j) acc[j] = 0.f;
+  const int64_t kbeg = split * keys_per_split, kend = min(lk, kbeg + keys_per_split);
+  for (int64_t k0 = kbeg; k0 < kend; k0 += XC) {
+    __syncthreads();
+    stage16(Ks, k, ld, h, k0, kend);
+    stage16(Vs, v, ld, h, k0, kend);
+    __syncthreads();
+    const int cnt = (int)min((int64_t)XC, kend - k0);
+    for (int j0 = 0; j0 < cnt; j0 += 8) {
+      float s[8], mx = m;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        float d = 0.f;
+#pragma unroll
+        for (int e = 0; e < HD; ++e) d = fmaf(qv[e], Ks[(j0 + jj) * HD + e], d);
+        s[jj] = (j0 + jj < cnt) ? d : -INFINITY;
+        mx = fmaxf(mx, s[jj]);
+      }
+      const float alpha = expf(m - mx);
+      l *= alpha;
+#pragma unroll
+      for (int e = 0; e < HD; ++e) acc[e] *= alpha;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float p = expf(s[jj] - mx);
+        l += p;
+#pragma unroll
+        for (int e = 0; e < HD; ++e) acc[e] = fmaf(p, Vs[(j0 + jj) * HD + e], acc[e]);
+      }
+      m = mx;
+    }
+  }
+  if (!live) return;
+  if (nsplit == 1) {
+    const float inv = 1.f / l;
+    float out[HD];
+#pragma unroll
+    for (int e = 0; e < HD; ++e) out[e] = acc[e] * inv;
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] = out[j];
+      b[j] = out[8 + j];
+    }
+    store8(o + qi * ld + h * HD, a);
+    store8(o + qi * ld + h * HD + 8, b);
+    lse[qi * heads + h] = m + logf(l);
+  } else {
+    float* w = ws + (((int64_t)split * lq + qi) * heads + h) * (HD + 2);
+    w[0] = m;
+    w[1] = l;
+#pragma unroll
+    for (int e = 0; e < HD; ++e) w[2 + e] = acc[e];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) cross_combine_kernel(const float* __restrict__ ws, T* __restrict__ o,
+                                                            float* __restrict__ lse, int64_t lq, int heads,
+                                                            int nsplit) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= lq * heads) return;
+  float m = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) m = fmaxf(m, ws[((int64_t)s * lq * heads + idx) * (HD + 2)]);
+  float l = 0.f, acc[HD];
+#pragma unroll
+  for (int e = 0; e < HD; ++e) acc[e] = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const float* w = ws + ((int64_t)s * lq * heads + idx) * (HD + 2);
+    const float f = (w[0] == -INFINITY) ? 0.f : expf(w[0] - m);
+    l = fmaf(f, w[1], l);
+#pragma unroll
+    for (int e = 0; e < HD; ++e) acc[e] = fmaf(f, w[2 + e], acc[e]);
+  }
+  const float inv = 1.f / l;
+  const int64_t qi = idx / heads;
+  const int h = (int)(idx % heads);
+#pragma unroll
+  for (int e = 0; e < HD; ++e) o[qi * heads * HD + h * HD + e] = from_float<T>(acc[e] * inv);
+  lse[idx] = m + logf(l);
+}
+
+// dq[qi] += sum_k exp(s - lse) * (dO.v_k - delta) * k_k / 4
+template <typename T>
+__global__ void __launch_bounds__(XT) cross_bwd_dq_kernel(const T* __restrict__ q, const T* __restrict__ k,
+                                                          const T* __restrict__ v, const T* __restrict__ o,
+                                                          const T* __restrict__ d_o, const float* __restrict__ lse,
+                                                          float* __restrict__ dq, int64_t lq, int64_t lk, int heads,
+                                                          int64_t keys_per_split) {
+  __shared__ float Ks[XC * HD], Vs[XC * HD];
+  const int h = blockIdx.y, split = blockIdx.z;
+  const int64_t qi = (int64_t)blockIdx.x * XT + threadIdx.x;
+  const int64_t ld = (int64_t)heads * HD;
+  const bool live = qi < lq;
+  float qv[HD], gv[HD], acc[HD], delta = 0.f, L = INFINITY;
+#pragma unroll
+  for (int j = 0; j < HD; ++j) qv[j] = gv[j] = acc[j] = 0.f;
+  if (live) {
+    float ov[HD];
+    load16(q + qi * ld + h * HD, qv);
+    load16(d_o + qi * ld + h * HD, gv);
+    load16(o + qi * ld + h * HD, ov);
+#pragma unroll
+    for (int j = 0; j < HD; ++j) delta = fmaf(gv[j], ov[j], delta);
+    L = lse[qi * heads + h];
+  }
+#pragma unroll
+  for (int j = 0; j < HD; ++j) qv[j] *= 0.25f;
+  const int64_t kbeg = split * keys_per_split, kend = min(lk, kbeg + keys_per_split);
+  for (int64_t k0 = kbeg; k0 < kend; k0 += XC) {
+    __syncthreads();
+    stage16(Ks, k, ld, h, k0, kend);
+    stage16(Vs, v, ld, h, k0, kend);
+    __syncthreads();
+    const int cnt = (int)min((int64_t)XC, kend - k0);
+    for (int j = 0; j < cnt; ++j) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int e = 0; e < HD; ++e) {
+        s = fmaf(qv[e], Ks[j * HD + e], s);
+        dp = fmaf(gv[e], Vs[j * HD + e], dp);
+      }
+      const float ds = expf(s - L) * (dp - delta) * 0.25f;
+#pragma unroll
+      for (int e = 0; e < HD; ++e) acc[e] = fmaf(ds, Ks[j * HD + e], acc[e]);
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int e = 0; e < HD; ++e) atomicAdd(dq + qi * ld + h * HD + e, acc[e]);
+  }
+}
+
+// thread per key: dv[k] += sum_q p dO_q ; dk[k] += sum_q p (dO_q.v_k - delta_q) q_q / 4
+template <typename T>
+__global__ void __launch_bounds__(XT) cross_bwd_dkv_kernel(const T* __restrict__ q, const T* __restrict__ k,
+                                                           const T* __restrict__ v, const T* __restrict__ o,
+                                                           const T* __restrict__ d_o, const float* __restrict__ lse,
+                                                           float* __restrict__ dk, float* __restrict__ dv, int64_t lq,
+                                                           int64_t lk, int heads, int64_t q_per_split) {
+  __shared__ float Qs[XC * HD], Gs[XC * HD], Ls[XC], Ds[XC];
+  const int h = blockIdx.y, split = blockIdx.z;
+  const int64_t ki = (int64_t)blockIdx.x * XT + threadIdx.x;
+  const int64_t ld = (int64_t)heads * HD;
+  const bool live = ki < lk;
+  float kv[HD], vv[HD], dka[HD], dva[HD];
+#pragma unroll
+  for (int j = 0; j < HD; ++j) kv[j] = vv[j] = dka[j] = dva[j] = 0.f;
+  if (live) {
+    load16(k + ki * ld + h * HD, kv);
+    load16(v + ki * ld + h * HD, vv);
+  }
+  const int64_t qbeg = split * q_per_split, qend = min(lq, qbeg + q_per_split);
+  for (int64_t q0 = qbeg; q0 < qend; q0 += XC) {
+    __syncthreads();
+    if (threadIdx.x < XC) {
+      const int64_t qi = q0 + threadIdx.x;
+      float a[HD], g[HD], ov[HD], de = 0.f;
+      if (qi < qend) {
+        load16(q + qi * ld + h * HD, a);
+        load16(d_o + qi * ld + h * HD, g);
+        load16(o + qi * ld + h * HD, ov);
+#pragma unroll
+        for (int e = 0; e < HD; ++e) de = fmaf(g[e], ov[e], de);
+        Ls[threadIdx.x] = lse[qi * heads + h];
+      } else {
+#pragma unroll
+        for (int e = 0; e < HD; ++e) a[e] = g[e] = 0.f;
+        Ls[threadIdx.x] = INFINITY;
+      }
+      Ds[threadIdx.x] = de;
+#pragma unroll
+      for (int e = 0; e < HD; ++e) {
+        Qs[threadIdx.x * HD + e] = a[e] * 0.25f;
+        Gs[threadIdx.x * HD + e] = g[e];
+      }
+    }
+    __syncthreads();
+    const int cnt = (int)min((int64_t)XC, qend - q0);
+    for (int j = 0; j < cnt; ++j) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int e = 0; e < HD; ++e) {
+        s = fmaf(Qs[j * HD + e], kv[e], s);
+        dp = fmaf(Gs[j * HD + e], vv[e], dp);
+      }
+      const float p = expf(s - Ls[j]);
+      const float ds = p * (dp - Ds[j]);
+#pragma unroll
+      for (int e = 0; e < HD; ++e) {
+        dva[e] = fmaf(p, Gs[j * HD + e], dva[e]);
+        dka[e] = fmaf(ds, Qs[j * HD + e], dka[e]);  // Qs already carries the 1/4
+      }
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int e = 0; e < HD; ++e) {
+      atomicAdd(dk + ki * ld + h * HD + e, dka[e]);
+      atomicAdd(dv + ki * ld + h * HD + e, dva[e]);
+    }
+  }
+}
+
+static int pick_splits(int64_t rows_parallel, int64_t loop_len, int heads) {
+  const int64_t ctas = ((rows_parallel + XT - 1) / XT) * heads;
+  if (ctas >= 2 * kNumSMs) return 1;
+  int64_t want = (4 * kNumSMs + ctas - 1) / ctas;
+  int64_t maxs = (loop_len + 2 * XC - 1) / (2 * XC);
+  if (want > maxs) want = maxs;
+  if (want > 64) want = 64;
+  return (int)(want < 1 ? 1 : want);
+}
+
+}  // namespace mt
+
+using namespace mt;
+
+extern "C" int64_t mt_cross_attn_workspace_floats(int64_t lq, int64_t lk, int heads, int head_dim) {
+  (void)head_dim;
+  const int ns = pick_splits(lq, lk, heads);
+  return ns == 1 ? 0 : (int64_t)ns * lq * heads * (HD + 2);
+}
+
+extern "C" int mt_cross_attn_fwd(const void* q, const void* k, const void* v, int dtype, void* o, float* lse,
+                                 int64_t lq, int64_t lk, int heads, int head_dim, float* workspace,
+                                 int64_t workspace_floats, void* stream) {
+  MT_REQUIRE(head_dim == HD, "cross_attn: head_dim must be 16 (got %d)", head_dim);
+  MT_REQUIRE(lq > 0 && lk > 0 && heads > 0 && heads <= 65535, "cross_attn: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ns = pick_splits(lq, lk, heads);
+  MT_REQUIRE(ns == 1 || (workspace != nullptr && workspace_floats >= (int64_t)ns * lq * heads * (HD + 2)),
+             "cross_attn: workspace too small");
+  const int64_t kps = ((lk + ns - 1) / ns + XC - 1) / XC * XC;
+  dim3 grid((unsigned)((lq + XT - 1) / XT), (unsigned)heads, (unsigned)ns);
+  if (dtype == MT_F32) {
+    cross_fwd_kernel<float><<<grid, XT, 0, st>>>((const float*)q, (const float*)k, (const float*)v, (float*)o, lse,
+                                                 workspace, lq, lk, heads, kps);
+    if (ns > 1)
+      cross_combine_kernel<float><<<(unsigned)((lq * heads + 127) / 128), 128, 0, st>>>(workspace, (float*)o, lse, lq, heads, ns);
+  } else if (dtype == MT_BF16) {
+    using bf = __nv_bfloat16;
+    cross_fwd_kernel<bf><<<grid, XT, 0, st>>>((const bf*)q, (const bf*)k, (const bf*)v, (bf*)o, lse, workspace, lq, lk,
+                                              heads, kps);
+    if (ns > 1)
+      cross_combine_kernel<bf><<<(unsigned)((lq * heads + 127) / 128), 128, 0, st>>>(workspace, (bf*)o, lse, lq, heads, ns);
+  } else {
+    set_error("cross_attn: bad dtype %d", dtype);
+    return MT_E_BADARG;
+  }
+  return check_launch("cross_fwd_kernel");
+}
+
+extern "C" int mt_cross_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                                 const float* lse, int dtype, float* dq_f32, float* dk_f32, float* dv_f32, int64_t lq,
+                                 int64_t lk, int heads, int head_dim, void* stream) {
+  MT_REQUIRE(head_dim == HD, "cross_attn: head_dim must be 16 (got %d)", head_dim);
+  MT_REQUIRE(lq > 0 && lk > 0 && heads > 0 && heads <= 65535, "cross_attn: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t ld = (size_t)heads * HD;
+  MT_CUDA(cudaMemsetAsync(dq_f32, 0, sizeof(float) * lq * ld, st));
+  MT_CUDA(cudaMemsetAsync(dk_f32, 0, sizeof(float) * lk * ld, st));
+  MT_CUDA(cudaMemsetAsync(dv_f32, 0, sizeof(float) * lk * ld, st));
+  const int nsk = pick_splits(lq, lk, heads), nsq = pick_splits(lk, lq, heads);
+  const int64_t kps = ((lk + nsk - 1) / nsk + XC - 1) / XC * XC;
+  const int64_t qps = ((lq + nsq - 1) / nsq + XC - 1) / XC * XC;
+  dim3 gq((unsigned)((lq + XT - 1) / XT), (unsigned)heads, (unsigned)nsk);
+  dim3 gk((unsigned)((lk + XT - 1) / XT), (unsigned)heads, (unsigned)nsq);
+  if (dtype == MT_F32) {
+    using f = float;
+    cross_bwd_dq_kernel<f><<<gq, XT, 0, st>>>((const f*)q, (const f*)k, (const f*)v, (const f*)o, (const f*)d_o, lse,
+                                              dq_f32, lq, lk, heads, kps);
+    cross_bwd_dkv_kernel<f><<<gk, XT, 0, st>>>((const f*)q, (const f*)k, (const f*)v, (const f*)o, (const f*)d_o, lse,
+                                               dk_f32, dv_f32, lq, lk, heads, qps);
+  } else if (dtype == MT_BF16) {
+    using f = __nv_bfloat16;
+    cross_bwd_dq_kernel<f><<<gq, XT, 0, st>>>((const f*)q, (const f*)k, (const f*)v, (const f*)o, (const f*)d_o, lse,
+                                              dq_f32, lq, lk, heads, kps);
+    cross_bwd_dkv_kernel<f><<<gk, XT, 0, st>>>((const f*)q, (const f*)k, (const f*)v, (const f*)o, (const f*)d_o, lse,
+                                               dk_f32, dv_f32, lq, lk, heads, qps);
+  } else {
+    set_error("cross_attn: bad dtype %d", dtype);
+    return MT_E_BADARG;
+  }
+  return check_launch("cross_bwd kernels");
+}

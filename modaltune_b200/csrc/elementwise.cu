@@ -1,0 +1,438 @@
+// HBM-bound fused kernels of the path: embedding assembly (A0), LayerNorm fwd/bwd (A1), GELU+LayerNorm(3072) fwd/bwd
+// (A6), gated residual (A7 tail), casts.  All accesses are 128-bit vectorised; one row is owned by COLS/24 threads and
+// every thread keeps its 24 elements in registers between the statistics pass and the write (single HBM pass).
+#include "mt_common.cuh"
+
+namespace mt {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// row reductions: TPR threads per row (32 -> one warp, 128 -> four warps through shared memory)
+// ---------------------------------------------------------------------------------------------------------------------
+template <int TPR>
+__device__ __forceinline__ float row_sum(float v, float* red, int row_in_block, int t) {
+  v = warp_sum(v);
+  if constexpr (TPR == 32) {
+    return v;
+  } else {
+    constexpr int W = TPR / 32;
+    __syncthreads();
+    if ((t & 31) == 0) red[row_in_block * W + (t >> 5)] = v;
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < W; ++i) s += red[row_in_block * W + i];
+    return s;
+  }
+}
+
+template <int COLS> struct RowCfg {
+  static constexpr int TPR = COLS / 24;          // threads per row, 3 chunks of 8 elements each
+  static constexpr int THREADS = 256;
+  static constexpr int RPB = THREADS / TPR;      // rows per block iteration
+  static_assert(COLS % 24 == 0 && (TPR == 32 || TPR == 128), "supported widths: 768, 3072");
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// y = LN(f(x)) * gamma + beta (+ add[row % add_rows]);  f = identity or GELU
+template <int COLS, typename TX, typename TY, typename TA, bool GELU>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, const TA* __restrict__ add,
+                                                     int64_t add_rows, TY* __restrict__ y, float* __restrict__ mean,
+                                                     float* __restrict__ rstd, int64_t rows, float eps) {
+  using C = RowCfg<COLS>;
+  __shared__ float red[C::RPB * (C::TPR / 32) + 1];
+  const int t = threadIdx.x % C::TPR, rib = threadIdx.x / C::TPR;
+  for (int64_t row0 = (int64_t)blockIdx.x * C::RPB; row0 < rows; row0 += (int64_t)gridDim.x * C::RPB) {
+    const int64_t row = row0 + rib;
+    const bool live = row < rows;
+    float v[3][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (live) {
+        load8(x + row * COLS + (i * C::TPR + t) * 8, v[i]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (GELU) v[i][j] = gelu_erf(v[i][j]);
+        s += v[i][j];
+      }
+    }
+    const float mu = row_sum<C::TPR>(s, red, rib, t) * (1.f / COLS);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float d = v[i][j] - mu;
+        q += d * d;
+      }
+    const float var = row_sum<C::TPR>(q, red, rib, t) * (1.f / COLS);
+    const float rs = rsqrtf(var + eps);
+    if (live) {
+      if (t == 0) {
+        if (mean) mean[row] = mu;
+        if (rstd) rstd[row] = rs;
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int c = (i * C::TPR + t) * 8;
+        float g[8], b[8], o[8];
+        load8(gamma + c, g);
+        load8(beta + c, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * g[j] + b[j];
+        if (add != nullptr) {
+          float a[8];
+          load8(add + (row % add_rows) * COLS + c, a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += a[j];
+        }
+        store8(y + row * COLS + c, o);
+      }
+    }
+  }
+}
+
+// dx = [gelu'(x)] * rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ residual), g = dy * gamma, xhat = (f(x) - mean) * rstd
+template <int COLS, typename TDY, typename TX, typename TR, typename TDX, bool GELU, bool WGRAD>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
+                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, const TR* __restrict__ residual,
+                                                     TDX* __restrict__ dx, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, int64_t rows) {
+  using C = RowCfg<COLS>;
+  __shared__ float red[C::RPB * (C::TPR / 32) + 1];
+  const int t = threadIdx.x % C::TPR, rib = threadIdx.x / C::TPR;
+  float gam[3][8];
+  float dg_acc[WGRAD ? 3 : 1][8], db_acc[WGRAD ? 3 : 1][8];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    load8(gamma + (i * C::TPR + t) * 8, gam[i]);
+    if constexpr (WGRAD) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dg_acc[i][j] = db_acc[i][j] = 0.f;
+    }
+  }
+  for (int64_t row0 = (int64_t)blockIdx.x * C::RPB; row0 < rows; row0 += (int64_t)gridDim.x * C::RPB) {
+    const int64_t row = row0 + rib;
+    const bool live = row < rows;
+    float xh[3][8], g[3][8], raw[3][8];
+    const float mu = live ? mean[row] : 0.f, rs = live ? rstd[row] : 0.f;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int c = (i * C::TPR + t) * 8;
+      float d[8];
+      if (live) {
+        load8(x + row * COLS + c, raw[i]);
+        load8(dy + row * COLS + c, d);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) raw[i][j] = d[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float u = GELU ? gelu_erf(raw[i][j]) : raw[i][j];
+        xh[i][j] = (u - mu) * rs;
+        g[i][j] = d[j] * gam[i][j];
+        s1 += g[i][j];
+        s2 += g[i][j] * xh[i][j];
+        if constexpr (WGRAD) {
+          dg_acc[i][j] += d[j] * xh[i][j];
+          db_acc[i][j] += d[j];
+        }
+      }
+    }
+    const float m1 = row_sum<C::TPR>(s1, red, rib, t) * (1.f / COLS);
+    const float m2 = row_sum<C::TPR>(s2, red, rib, t) * (1.f / COLS);
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int c = (i * C::TPR + t) * 8;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = rs * (g[i][j] - m1 - xh[i][j] * m2);
+          if (GELU) o[j] *= gelu_erf_grad(raw[i][j]);
+        }
+        if (residual != nullptr) {
+          float r[8];
+          load8(residual + row * COLS + c, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        }
+        store8(dx + row * COLS + c, o);
+      }
+    }
+  }
+  if constexpr (WGRAD) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = (i * C::TPR + t) * 8 + j;
+        atomicAdd(dgamma + c, dg_acc[i][j]);
+        atomicAdd(dbeta + c, db_acc[i][j]);
+      }
+  }
+}
+
+template <typename TP>
+__global__ void __launch_bounds__(256) embed_assemble_kernel(const TP* __restrict__ proj, const float* __restrict__ bias,
+                                                             const float* __restrict__ coords,
+                                                             const float* __restrict__ table,
+                                                             const float* __restrict__ cls, float* __restrict__ x,
+                                                             int64_t n_tiles, int embed, int ngrids, float inv_tile) {
+  const int chunks = embed / 8;
+  const int64_t total = (n_tiles + 1) * chunks;
+  const int half = embed / 2;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = idx / chunks;
+    const int c = (int)(idx % chunks) * 8;
+    float o[8];
+    if (row == 0) {
+      load8(cls + c, o);  // cls_token + pos_embed[0], and pos_embed[0] == 0
+    } else {
+      const int64_t i = row - 1;
+      float p[8], b[8], e[8];
+      load8(proj + i * embed + c, p);
+      load8(bias + c, b);
+      // pos = floor(c0/256) * G + floor(c1/256) + 1 ;  pos_embed[pos] = [T[j] | T[i]]
+      int gi = (int)floorf(coords[2 * i] * inv_tile), gj = (int)floorf(coords[2 * i + 1] * inv_tile);
+      gi = min(max(gi, 0), ngrids - 1);
+      gj = min(max(gj, 0), ngrids - 1);
+      if (c < half) load8(table + (int64_t)gj * half + c, e);
+      else load8(table + (int64_t)gi * half + (c - half), e);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = p[j] + b[j] + e[j];
+    }
+    store8(x + row * embed + c, o);
+  }
+}
+
+template <typename TB>
+__global__ void __launch_bounds__(256) gated_residual_kernel(const float* __restrict__ a, const TB* __restrict__ b,
+                                                             const float* __restrict__ gate, float* __restrict__ y,
+                                                             int64_t rows, int cols) {
+  const int chunks = cols / 8;
+  const int64_t total = rows * chunks;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % chunks) * 8;
+    float av[8], bv[8], gv[8], o[8];
+    load8(a + idx * 8, av);
+    load8(b + idx * 8, bv);
+    if (gate) load8(gate + c, gv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = av[j] + (gate ? gv[j] : 1.f) * (av[j] + bv[j]);
+    store8(y + idx * 8, o);
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n8, int64_t n) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n8; idx += (int64_t)gridDim.x * blockDim.x) {
+    float v[8];
+    load8(s + idx * 8, v);
+    store8(d + idx * 8, v);
+  }
+  if (blockIdx.x == 0) {
+    for (int64_t i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) d[i] = from_float<TD>(to_float(s[i]));
+  }
+}
+
+static inline int grid_for(int64_t work_items, int per_block) {
+  int64_t blocks = (work_items + per_block - 1) / per_block;
+  int64_t cap = (int64_t)kNumSMs * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---- dispatch helpers ------------------------------------------------------------------------------------------------
+template <int COLS, bool GELU, typename TX, typename TY>
+static int launch_ln_fwd(const void* x, const float* gamma, const float* beta, const void* add, int add_dtype,
+                         int64_t add_rows, void* y, float* mean, float* rstd, int64_t rows, float eps, cudaStream_t st) {
+  using C = RowCfg<COLS>;
+  const int grid = grid_for(rows, C::RPB);
+  if (add == nullptr || add_dtype == MT_F32)
+    ln_fwd_kernel<COLS, TX, TY, float, GELU><<<grid, 256, 0, st>>>((const TX*)x, gamma, beta, (const float*)add,
+                                                                   add_rows > 0 ? add_rows : 1, (TY*)y, mean, rstd,
+                                                                   rows, eps);
+  else
+    ln_fwd_kernel<COLS, TX, TY, __nv_bfloat16, GELU><<<grid, 256, 0, st>>>(
+        (const TX*)x, gamma, beta, (const __nv_bfloat16*)add, add_rows > 0 ? add_rows : 1, (TY*)y, mean, rstd, rows, eps);
+  return check_launch("ln_fwd_kernel");
+}
+
+template <int COLS, bool GELU>
+static int dispatch_ln_fwd(const void* x, int xd, const float* gamma, const float* beta, const void* add, int ad,
+                           int64_t add_rows, void* y, int yd, float* mean, float* rstd, int64_t rows, float eps,
+                           cudaStream_t st) {
+  if (xd == MT_F32 && yd == MT_F32)
+    return launch_ln_fwd<COLS, GELU, float, float>(x, gamma, beta, add, ad, add_rows, y, mean, rstd, rows, eps, st);
+  if (xd == MT_F32 && yd == MT_BF16)
+    return launch_ln_fwd<COLS, GELU, float, __nv_bfloat16>(x, gamma, beta, add, ad, add_rows, y, mean, rstd, rows, eps, st);
+  if (xd == MT_BF16 && yd == MT_BF16)
+    return launch_ln_fwd<COLS, GELU, __nv_bfloat16, __nv_bfloat16>(x, gamma, beta, add, ad, add_rows, y, mean, rstd, rows, eps, st);
+  if (xd == MT_BF16 && yd == MT_F32)
+    return launch_ln_fwd<COLS, GELU, __nv_bfloat16, float>(x, gamma, beta, add, ad, add_rows, y, mean, rstd, rows, eps, st);
+  set_error("layernorm: unsupported dtype combination");
+  return MT_E_UNSUPPORTED;
+}
+
+template <int COLS, bool GELU, typename TDY, typename TX, typename TDX>
+static int launch_ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                         const void* residual, int rd, void* dx, float* dgamma, float* dbeta, int64_t rows,
+                         cudaStream_t st) {
+  using C = RowCfg<COLS>;
+  int grid = grid_for(rows, C::RPB);
+  if (dgamma != nullptr && grid > kNumSMs * 2) grid = kNumSMs * 2;  // bound the number of atomic flushes
+  if (dgamma != nullptr) {
+    if constexpr (!GELU) {
+      if (residual != nullptr && rd != MT_F32) {
+        set_error("layernorm bwd with weight grads: residual must be f32");
+        return MT_E_UNSUPPORTED;
+      }
+      ln_bwd_kernel<COLS, TDY, TX, float, TDX, GELU, true><<<grid, 256, 0, st>>>(
+          (const TDY*)dy, (const TX*)x, gamma, mean, rstd, (const float*)residual, (TDX*)dx, dgamma, dbeta, rows);
+    }
+  } else if (residual == nullptr || rd == MT_F32)
+    ln_bwd_kernel<COLS, TDY, TX, float, TDX, GELU, false><<<grid, 256, 0, st>>>(
+        (const TDY*)dy, (const TX*)x, gamma, mean, rstd, (const float*)residual, (TDX*)dx, dgamma, dbeta, rows);
+  else
+    ln_bwd_kernel<COLS, TDY, TX, __nv_bfloat16, TDX, GELU, false><<<grid, 256, 0, st>>>(
+        (const TDY*)dy, (const TX*)x, gamma, mean, rstd, (const __nv_bfloat16*)residual, (TDX*)dx, dgamma, dbeta, rows);
+  return check_launch("ln_bwd_kernel");
+}
+
+template <int COLS, bool GELU>
+static int dispatch_ln_bwd(const void* dy, int dyd, const void* x, int xd, const float* gamma, const float* mean,
+                           const float* rstd, const void* residual, int rd, void* dx, int dxd, float* dgamma,
+                           float* dbeta, int64_t rows, cudaStream_t st) {
+#define MT_LNB(TDY, TX, TDX) \
+  return launch_ln_bwd<COLS, GELU, TDY, TX, TDX>(dy, x, gamma, mean, rstd, residual, rd, dx, dgamma, dbeta, rows, st)
+  using bf = __nv_bfloat16;
+  if (dyd == MT_F32 && xd == MT_F32 && dxd == MT_F32) MT_LNB(float, float, float);
+  if (dyd == MT_BF16 && xd == MT_F32 && dxd == MT_F32) MT_LNB(bf, float, float);
+  if (dyd == MT_BF16 && xd == MT_BF16 && dxd == MT_BF16) MT_LNB(bf, bf, bf);
+  if (dyd == MT_F32 && xd == MT_BF16 && dxd == MT_BF16) MT_LNB(float, bf, bf);
+  if (dyd == MT_BF16 && xd == MT_BF16 && dxd == MT_F32) MT_LNB(bf, bf, float);
+  if (dyd == MT_F32 && xd == MT_BF16 && dxd == MT_F32) MT_LNB(float, bf, float);
+  if (dyd == MT_BF16 && xd == MT_F32 && dxd == MT_BF16) MT_LNB(bf, float, bf);
+  if (dyd == MT_F32 && xd == MT_F32 && dxd == MT_BF16) MT_LNB(float, float, bf);
+#undef MT_LNB
+  set_error("layernorm bwd: unsupported dtype combination");
+  return MT_E_UNSUPPORTED;
+}
+
+}  // namespace mt
+
+using namespace mt;
+
+extern "C" int mt_embed_assemble(const void* proj, int proj_dtype, const float* bias, const float* coords,
+                                 const float* table, const float* cls, float* x, int64_t n_tiles, int64_t embed,
+                                 int64_t ngrids, float tile_size, void* stream) {
+  MT_REQUIRE(embed % 16 == 0 && n_tiles >= 0, "embed_assemble: embed must be a multiple of 16");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for((n_tiles + 1) * (embed / 8), 256);
+  if (proj_dtype == MT_F32)
+    embed_assemble_kernel<float><<<grid, 256, 0, st>>>((const float*)proj, bias, coords, table, cls, x, n_tiles,
+                                                       (int)embed, (int)ngrids, 1.f / tile_size);
+  else
+    embed_assemble_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)proj, bias, coords, table, cls, x,
+                                                               n_tiles, (int)embed, (int)ngrids, 1.f / tile_size);
+  return check_launch("embed_assemble_kernel");
+}
+
+extern "C" int mt_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, const void* add,
+                                int add_dtype, int64_t add_rows, void* y, int y_dtype, float* mean, float* rstd,
+                                int64_t rows, int64_t cols, float eps, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows == 0) return 0;
+  if (cols == 768)
+    return dispatch_ln_fwd<768, false>(x, x_dtype, gamma, beta, add, add_dtype, add_rows, y, y_dtype, mean, rstd, rows, eps, st);
+  if (cols == 3072)
+    return dispatch_ln_fwd<3072, false>(x, x_dtype, gamma, beta, add, add_dtype, add_rows, y, y_dtype, mean, rstd, rows, eps, st);
+  set_error("layernorm: width %lld not supported (768, 3072)", (long long)cols);
+  return MT_E_UNSUPPORTED;
+}
+
+extern "C" int mt_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
+                                const float* mean, const float* rstd, const void* residual, int res_dtype, void* dx,
+                                int dx_dtype, float* dgamma, float* dbeta, int64_t rows, int64_t cols, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows == 0) return 0;
+  MT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm bwd: dgamma and dbeta go together");
+  if (cols == 768)
+    return dispatch_ln_bwd<768, false>(dy, dy_dtype, x, x_dtype, gamma, mean, rstd, residual, res_dtype, dx, dx_dtype, dgamma, dbeta, rows, st);
+  if (cols == 3072)
+    return dispatch_ln_bwd<3072, false>(dy, dy_dtype, x, x_dtype, gamma, mean, rstd, residual, res_dtype, dx, dx_dtype, dgamma, dbeta, rows, st);
+  set_error("layernorm bwd: width %lld not supported (768, 3072)", (long long)cols);
+  return MT_E_UNSUPPORTED;
+}
+
+extern "C" int mt_gelu_ln_fwd(const void* h, int h_dtype, const float* gamma, const float* beta, void* y, int y_dtype,
+                              float* mean, float* rstd, int64_t rows, int64_t cols, float eps, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows == 0) return 0;
+  if (cols == 3072)
+    return dispatch_ln_fwd<3072, true>(h, h_dtype, gamma, beta, nullptr, 0, 1, y, y_dtype, mean, rstd, rows, eps, st);
+  if (cols == 768)
+    return dispatch_ln_fwd<768, true>(h, h_dtype, gamma, beta, nullptr, 0, 1, y, y_dtype, mean, rstd, rows, eps, st);
+  set_error("gelu_ln: width %lld not supported (768, 3072)", (long long)cols);
+  return MT_E_UNSUPPORTED;
+}
+
+extern "C" int mt_gelu_ln_bwd(const void* dy, int dy_dtype, const void* h, int h_dtype, const float* gamma,
+                              const float* mean, const float* rstd, void* dh, int dh_dtype, int64_t rows, int64_t cols,
+                              void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows == 0) return 0;
+  if (cols == 3072)
+    return dispatch_ln_bwd<3072, true>(dy, dy_dtype, h, h_dtype, gamma, mean, rstd, nullptr, 0, dh, dh_dtype, nullptr, nullptr, rows, st);
+  if (cols == 768)
+    return dispatch_ln_bwd<768, true>(dy, dy_dtype, h, h_dtype, gamma, mean, rstd, nullptr, 0, dh, dh_dtype, nullptr, nullptr, rows, st);
+  set_error("gelu_ln bwd: width %lld not supported (768, 3072)", (long long)cols);
+  return MT_E_UNSUPPORTED;
+}
+
+extern "C" int mt_gated_residual(const float* a, const void* b, int b_dtype, const float* gate, float* y, int64_t rows,
+                                 int64_t cols, void* stream) {
+  MT_REQUIRE(cols % 8 == 0, "gated_residual: cols must be a multiple of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows == 0) return 0;
+  const int grid = grid_for(rows * (cols / 8), 256);
+  if (b_dtype == MT_F32)
+    gated_residual_kernel<float><<<grid, 256, 0, st>>>(a, (const float*)b, gate, y, rows, (int)cols);
+  else
+    gated_residual_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, (const __nv_bfloat16*)b, gate, y, rows, (int)cols);
+  return check_launch("gated_residual_kernel");
+}
+
+extern "C" int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) return 0;
+  const int64_t n8 = n / 8;
+  const int grid = grid_for(n8 > 0 ? n8 : 1, 256);
+  if (src_dtype == MT_F32 && dst_dtype == MT_BF16)
+    cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n8, n);
+  else if (src_dtype == MT_BF16 && dst_dtype == MT_F32)
+    cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n8, n);
+  else if (src_dtype == MT_F32 && dst_dtype == MT_F32)
+    cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, n8, n);
+  else
+    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n8, n);
+  return check_launch("cast_kernel");
+}
