@@ -70,6 +70,12 @@ int mt_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, c
                      const float* rstd, const void* residual, int res_dtype, void* dx, int dx_dtype, float* dgamma,
                      float* dbeta, int64_t rows, int64_t cols, void* stream);
 
+/* residual add fused with the next pre-LN (torchscale/architecture/encoder.py:152-166):
+ * x_out = x + a (f32 residual stream, a in a_dtype), y = LN(x_out).  cols = 768. */
+int mt_add_layernorm_fwd(const float* x, const void* a, int a_dtype, const float* gamma, const float* beta,
+                         float* x_out, void* y, int y_dtype, float* mean, float* rstd, int64_t rows, int64_t cols,
+                         float eps, void* stream);
+
 /* ---- A6: GELU(fp32) + LayerNorm(3072) between fc1 and fc2 ---------------------------------------------------------
  * replaces: `activation_fn(x.float()).type_as(x)` + ffn_layernorm (torchscale/component/feedforward_network.py:135-140)
  * h [rows, cols] = fc1 output (bias included).  y = LN(gelu_erf(h)). */
@@ -128,6 +134,10 @@ int64_t mt_cross_attn_workspace_floats(int64_t lq, int64_t lk, int heads, int he
  *           with attn = a + b already containing the inner residual (:231).  gate may be NULL (=1).  f32 a, dtype b. */
 int mt_gated_residual(const float* a, const void* b, int b_dtype, const float* gate, float* y, int64_t rows,
                       int64_t cols, void* stream);
+/* backward of mt_gated_residual: da = dy * (1 + gate), db = dy * gate (dtype of b), dgate[c] = sum_r dy * (a + b)
+ * (dgate is zeroed by the call and accumulated with atomics). */
+int mt_gated_residual_bwd(const float* dy, const float* a, const void* b, int b_dtype, const float* gate, float* da,
+                          void* db, int db_dtype, float* dgate, int64_t rows, int64_t cols, void* stream);
 int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
 
 #ifdef __cplusplus

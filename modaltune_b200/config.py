@@ -1,0 +1,66 @@
+"""Run-time switches of the compute path.
+
+``mode``
+    ``"bf16"`` -- fp32 residual stream, LayerNorm / softmax / GELU statistics in fp32, bf16 GEMM and attention operands
+    with fp32 accumulation (the same structure the reference has under ``autocast``);
+    ``"fp32"`` -- everything in fp32 (cuBLAS fp32 GEMMs without TF32, fp32 SIMT attention); the 1e-4 parity mode.
+``attn_impl``
+    ``"auto"`` -- tcgen05/TMA dilated-attention kernels in bf16 mode, SIMT kernels in fp32 mode;
+    ``"simt"`` -- force the SIMT kernels (any mode);  ``"sm100"`` -- force the tcgen05 kernels (bf16 only).
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+
+import torch
+
+_state = {
+    "mode": os.environ.get("MODALTUNE_B200_MODE", "bf16"),
+    "attn_impl": os.environ.get("MODALTUNE_B200_ATTN", "auto"),
+}
+
+
+def set_mode(mode: str) -> None:
+    assert mode in ("bf16", "fp32")
+    _state["mode"] = mode
+
+
+def set_attn_impl(impl: str) -> None:
+    assert impl in ("auto", "simt", "sm100")
+    _state["attn_impl"] = impl
+
+
+def mode() -> str:
+    return _state["mode"]
+
+
+def compute_dtype() -> torch.dtype:
+    return torch.bfloat16 if _state["mode"] == "bf16" else torch.float32
+
+
+# what "auto" resolves to in bf16 mode, per direction (flipped to 1 as the tcgen05 kernels are validated on B200)
+AUTO_IMPL = {"fwd": 0, "bwd": 0}
+
+
+def attn_impl(direction: str = "fwd") -> int:
+    """0 = SIMT, 1 = tcgen05 (the ``impl`` argument of mt_dilated_attn_{fwd,bwd})."""
+    impl = _state["attn_impl"]
+    if impl == "simt" or _state["mode"] == "fp32":
+        if impl == "sm100":
+            raise RuntimeError("the tcgen05 dilated-attention kernels compute in bf16; fp32 mode needs attn_impl simt/auto")
+        return 0
+    return 1 if impl == "sm100" else AUTO_IMPL[direction]
+
+
+@contextlib.contextmanager
+def using(mode: str | None = None, attn_impl: str | None = None):
+    old = dict(_state)
+    try:
+        if mode is not None:
+            set_mode(mode)
+        if attn_impl is not None:
+            set_attn_impl(attn_impl)
+        yield
+    finally:
+        _state.update(old)

@@ -240,6 +240,103 @@ __global__ void __launch_bounds__(256) gated_residual_kernel(const float* __rest
   }
 }
 
+// x_out = x + a (fp32 residual stream), y = LN(x_out) * gamma + beta: the residual add after the attention / FFN branch
+// fused with the next block's pre-LN (encoder.py:152-166), one pass over HBM.
+template <int COLS, typename TA, typename TY>
+__global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict__ x, const TA* __restrict__ a,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float* __restrict__ x_out,
+                                                         TY* __restrict__ y, float* __restrict__ mean,
+                                                         float* __restrict__ rstd, int64_t rows, float eps) {
+  using C = RowCfg<COLS>;
+  __shared__ float red[C::RPB * (C::TPR / 32) + 1];
+  const int t = threadIdx.x % C::TPR, rib = threadIdx.x / C::TPR;
+  for (int64_t row0 = (int64_t)blockIdx.x * C::RPB; row0 < rows; row0 += (int64_t)gridDim.x * C::RPB) {
+    const int64_t row = row0 + rib;
+    const bool live = row < rows;
+    float v[3][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (live) {
+        float av[8];
+        load8(x + row * COLS + (i * C::TPR + t) * 8, v[i]);
+        load8(a + row * COLS + (i * C::TPR + t) * 8, av);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] += av[j];
+        store8(x_out + row * COLS + (i * C::TPR + t) * 8, v[i]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+    const float mu = row_sum<C::TPR>(s, red, rib, t) * (1.f / COLS);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float d = v[i][j] - mu;
+        q += d * d;
+      }
+    const float var = row_sum<C::TPR>(q, red, rib, t) * (1.f / COLS);
+    const float rs = rsqrtf(var + eps);
+    if (live) {
+      if (t == 0) {
+        mean[row] = mu;
+        rstd[row] = rs;
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int c = (i * C::TPR + t) * 8;
+        float g[8], b[8], o[8];
+        load8(gamma + c, g);
+        load8(beta + c, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * g[j] + b[j];
+        store8(y + row * COLS + c, o);
+      }
+    }
+  }
+}
+
+// backward of y = a + gate * (a + b):  da = dy * (1 + gate), db = dy * gate, dgate[c] += sum_r dy * (a + b)
+template <typename TB>
+__global__ void __launch_bounds__(256) gated_residual_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a,
+                                                                 const TB* __restrict__ b,
+                                                                 const float* __restrict__ gate, float* __restrict__ da,
+                                                                 TB* __restrict__ db, float* __restrict__ dgate,
+                                                                 int64_t rows, int cols) {
+  // thread t owns column chunk (t % chunks) for rows (blockIdx.x * rpb + t / chunks) + k * gridDim.x * rpb
+  const int chunks = cols / 8;
+  const int rpb = blockDim.x / chunks;
+  const int ch = threadIdx.x % chunks, rib = threadIdx.x / chunks;
+  if (rib >= rpb) return;
+  float gv[8], acc[8];
+  load8(gate + ch * 8, gv);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * rpb + rib; row < rows; row += (int64_t)gridDim.x * rpb) {
+    const int64_t off = row * cols + ch * 8;
+    float d[8], av[8], bv[8], oa[8], ob[8];
+    load8(dy + off, d);
+    load8(a + off, av);
+    load8(b + off, bv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      oa[j] = d[j] * (1.f + gv[j]);
+      ob[j] = d[j] * gv[j];
+      acc[j] = fmaf(d[j], av[j] + bv[j], acc[j]);
+    }
+    store8(da + off, oa);
+    store8(db + off, ob);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(dgate + ch * 8 + j, acc[j]);
+}
+
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256) cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n8, int64_t n) {
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n8; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -419,6 +516,45 @@ extern "C" int mt_gated_residual(const float* a, const void* b, int b_dtype, con
   else
     gated_residual_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, (const __nv_bfloat16*)b, gate, y, rows, (int)cols);
   return check_launch("gated_residual_kernel");
+}
+
+extern "C" int mt_add_layernorm_fwd(const float* x, const void* a, int a_dtype, const float* gamma, const float* beta,
+                                    float* x_out, void* y, int y_dtype, float* mean, float* rstd, int64_t rows,
+                                    int64_t cols, float eps, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows == 0) return 0;
+  MT_REQUIRE(cols == 768, "add_layernorm: width %lld not supported (768)", (long long)cols);
+  using C = RowCfg<768>;
+  using bf = __nv_bfloat16;
+  const int grid = grid_for(rows, C::RPB);
+  if (a_dtype == MT_F32 && y_dtype == MT_F32)
+    add_ln_fwd_kernel<768, float, float><<<grid, 256, 0, st>>>(x, (const float*)a, gamma, beta, x_out, (float*)y, mean, rstd, rows, eps);
+  else if (a_dtype == MT_BF16 && y_dtype == MT_BF16)
+    add_ln_fwd_kernel<768, bf, bf><<<grid, 256, 0, st>>>(x, (const bf*)a, gamma, beta, x_out, (bf*)y, mean, rstd, rows, eps);
+  else if (a_dtype == MT_F32 && y_dtype == MT_BF16)
+    add_ln_fwd_kernel<768, float, bf><<<grid, 256, 0, st>>>(x, (const float*)a, gamma, beta, x_out, (bf*)y, mean, rstd, rows, eps);
+  else
+    add_ln_fwd_kernel<768, bf, float><<<grid, 256, 0, st>>>(x, (const bf*)a, gamma, beta, x_out, (float*)y, mean, rstd, rows, eps);
+  return check_launch("add_ln_fwd_kernel");
+}
+
+extern "C" int mt_gated_residual_bwd(const float* dy, const float* a, const void* b, int b_dtype, const float* gate,
+                                     float* da, void* db, int db_dtype, float* dgate, int64_t rows, int64_t cols,
+                                     void* stream) {
+  MT_REQUIRE(cols % 8 == 0 && cols / 8 <= 256, "gated_residual_bwd: cols must be a multiple of 8, at most 2048");
+  MT_REQUIRE(b_dtype == db_dtype, "gated_residual_bwd: db must have the dtype of b");
+  MT_REQUIRE(gate != nullptr && dgate != nullptr, "gated_residual_bwd: gate and dgate are required");
+  cudaStream_t st = (cudaStream_t)stream;
+  MT_CUDA(cudaMemsetAsync(dgate, 0, sizeof(float) * (size_t)cols, st));
+  if (rows == 0) return 0;
+  const int rpb = 256 / (int)(cols / 8);
+  int grid = grid_for(rows, rpb);
+  if (grid > kNumSMs * 4) grid = kNumSMs * 4;  // bound the number of atomic flushes
+  if (b_dtype == MT_F32)
+    gated_residual_bwd_kernel<float><<<grid, 256, 0, st>>>(dy, a, (const float*)b, gate, da, (float*)db, dgate, rows, (int)cols);
+  else
+    gated_residual_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dy, a, (const __nv_bfloat16*)b, gate, da, (__nv_bfloat16*)db, dgate, rows, (int)cols);
+  return check_launch("gated_residual_bwd_kernel");
 }
 
 extern "C" int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream) {

@@ -1,0 +1,475 @@
+"""Thin Python side of the C ABI: tensor -> pointer marshalling and the ``torch.autograd.Function``s of the hot path.
+
+Every function here launches hand-written sm_100a kernels from ``libmodaltune_b200.so`` on the current CUDA stream;
+dense projections between them are plain cuBLAS GEMMs (``torch.nn.functional.linear`` / ``torch.matmul``).  Nothing in
+this module has a CPU implementation: tensors must live on a CUDA device.
+
+Reference functions replaced (paths relative to the reference root, ``TS/`` =
+``models/prov_gigapath/gigapath/torchscale/``): ``TS/architecture/encoder.py:121-175`` (EncoderLayer.forward),
+``TS/component/dilated_attention.py:82-262``, ``TS/component/multihead_attention.py:109-119``,
+``TS/component/feedforward_network.py:132-143``, ``models/vitadapter/adapter_modules.py:210-234, 321-369``.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import MT_BF16, MT_F32, DilatedGeometry
+
+HEADS = 16
+HEAD_DIM = 48
+EMBED = 768
+LN_EPS = 1e-5
+
+# kernel-launch counter (bench.py reports it as `gpu_launches`); incremented once per C-ABI launch call
+launch_count = 0
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return MT_F32
+    if t.dtype == torch.bfloat16:
+        return MT_BF16
+    raise TypeError(f"unsupported dtype {t.dtype} (float32 / bfloat16 only)")
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    assert t.is_cuda, "modaltune_b200 kernels need CUDA tensors (there is no CPU path)"
+    assert t.is_contiguous(), "modaltune_b200 kernels need contiguous tensors"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check(rc: int, what: str, launches: int = 1) -> None:
+    global launch_count
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {_lib.last_error()}")
+    launch_count += launches
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t if t.dtype == torch.float32 else t.float()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# dilated-attention geometry
+# ---------------------------------------------------------------------------------------------------------------------
+class Geometry:
+    """Host mirror of ``mt_dilated_geometry`` + the compact per-branch buffer sizes (include/modaltune_b200.h)."""
+
+    _cache: Dict[tuple, "Geometry"] = {}
+
+    def __init__(self, n_tokens: int, segment_lengths: Sequence[int], ratios: Sequence[int], heads: int = HEADS,
+                 head_dim: int = HEAD_DIM):
+        assert len(segment_lengths) == len(ratios) <= _lib.MT_MAX_BRANCHES
+        self.n_tokens, self.heads, self.head_dim = int(n_tokens), heads, head_dim
+        self.segment_lengths = [int(s) for s in segment_lengths]
+        self.ratios = [int(r) for r in ratios]
+        g = DilatedGeometry()
+        g.n_tokens, g.n_heads, g.head_dim, g.n_branches = self.n_tokens, heads, head_dim, len(ratios)
+        self.o_elems = 0
+        self.lse_elems = 0
+        self.flops_fwd = 0.0  # algorithmic: 4 * d * sum c^2 over real positions only
+        for b, (sl, r) in enumerate(zip(self.segment_lengths, self.ratios)):
+            g.seg_len[b] = min(sl, 2**31 - 1)
+            g.ratio[b] = r
+            assert heads % r == 0, "dilation must divide the head count"
+            self.o_elems += self.n_tokens * (heads // r) * head_dim
+            self.lse_elems += self.n_tokens * (heads // r)
+            gl = min(sl, self.n_tokens)
+            n_seg = -(-self.n_tokens // gl)
+            for s in range(n_seg):
+                lo, hi = s * gl, min(self.n_tokens, (s + 1) * gl)
+                for h in range(heads):
+                    off = (h * r) // heads
+                    c = max(0, -(-(hi - lo - off) // r))
+                    self.flops_fwd += 4.0 * head_dim * c * c
+        self.c_struct = g
+        self.n_alloc = -(-self.n_tokens // 128) * 128  # qkv rows incl. the zero tail the TMA path reads
+
+    @classmethod
+    def get(cls, n_tokens: int, segment_lengths: Sequence[int], ratios: Sequence[int]) -> "Geometry":
+        key = (int(n_tokens), tuple(int(s) for s in segment_lengths), tuple(int(r) for r in ratios))
+        if key not in cls._cache:
+            cls._cache[key] = Geometry(*key)
+        return cls._cache[key]
+
+    def ref(self):
+        return ctypes.byref(self.c_struct)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# raw kernel wrappers (no autograd)
+# ---------------------------------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, out_dtype, add=None, eps: float = LN_EPS, want_stats: bool = True):
+    rows, cols = x.shape
+    y = torch.empty((rows, cols), device=x.device, dtype=out_dtype)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
+    add_rows = add.shape[0] if add is not None else 1
+    rc = _lib.load().mt_layernorm_fwd(_p(x), _dt(x), _p(gamma), _p(beta), _p(add), _dt(add) if add is not None else 0,
+                                      add_rows, _p(y), _dt(y), _p(mean), _p(rstd), rows, cols, eps, _stream())
+    _check(rc, "mt_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_dtype, residual=None, want_wgrad: bool = False):
+    rows, cols = x.shape
+    dx = torch.empty((rows, cols), device=x.device, dtype=dx_dtype)
+    dgamma = dbeta = None
+    if want_wgrad:
+        dgamma = torch.zeros(cols, device=x.device, dtype=torch.float32)
+        dbeta = torch.zeros(cols, device=x.device, dtype=torch.float32)
+    rc = _lib.load().mt_layernorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(mean), _p(rstd), _p(residual),
+                                      _dt(residual) if residual is not None else 0, _p(dx), _dt(dx), _p(dgamma),
+                                      _p(dbeta), rows, cols, _stream())
+    _check(rc, "mt_layernorm_bwd")
+    return dx, dgamma, dbeta
+
+
+def add_layernorm_fwd(x, a, gamma, beta, out_dtype, eps: float = LN_EPS):
+    """x_out = x + a (fp32), y = LN(x_out)."""
+    rows, cols = x.shape
+    assert x.dtype == torch.float32
+    x_out = torch.empty_like(x)
+    y = torch.empty((rows, cols), device=x.device, dtype=out_dtype)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rc = _lib.load().mt_add_layernorm_fwd(_p(x), _p(a), _dt(a), _p(gamma), _p(beta), _p(x_out), _p(y), _dt(y), _p(mean),
+                                          _p(rstd), rows, cols, eps, _stream())
+    _check(rc, "mt_add_layernorm_fwd")
+    return x_out, y, mean, rstd
+
+
+def gelu_ln_fwd(h, gamma, beta, out_dtype, eps: float = LN_EPS):
+    rows, cols = h.shape
+    y = torch.empty((rows, cols), device=h.device, dtype=out_dtype)
+    mean = torch.empty(rows, device=h.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=h.device, dtype=torch.float32)
+    rc = _lib.load().mt_gelu_ln_fwd(_p(h), _dt(h), _p(gamma), _p(beta), _p(y), _dt(y), _p(mean), _p(rstd), rows, cols,
+                                    eps, _stream())
+    _check(rc, "mt_gelu_ln_fwd")
+    return y, mean, rstd
+
+
+def gelu_ln_bwd(dy, h, gamma, mean, rstd, out_dtype):
+    rows, cols = h.shape
+    dh = torch.empty((rows, cols), device=h.device, dtype=out_dtype)
+    rc = _lib.load().mt_gelu_ln_bwd(_p(dy), _dt(dy), _p(h), _dt(h), _p(gamma), _p(mean), _p(rstd), _p(dh), _dt(dh),
+                                    rows, cols, _stream())
+    _check(rc, "mt_gelu_ln_bwd")
+    return dh
+
+
+def dilated_attn_fwd(geom: Geometry, qkv: torch.Tensor, impl: int):
+    """qkv [n_alloc, 3E] -> (o_br [o_elems], lse_br [lse_elems]) in the compact per-branch layout."""
+    o_br = torch.empty(geom.o_elems, device=qkv.device, dtype=qkv.dtype)
+    lse_br = torch.empty(geom.lse_elems, device=qkv.device, dtype=torch.float32)
+    rc = _lib.load().mt_dilated_attn_fwd(geom.ref(), _p(qkv), qkv.stride(0), qkv.shape[0], _dt(qkv), _p(o_br),
+                                         _p(lse_br), impl, _stream())
+    _check(rc, "mt_dilated_attn_fwd")
+    return o_br, lse_br
+
+
+def dilated_merge_ln_fwd(geom: Geometry, o_br, lse_br, gamma, beta, eps: float = LN_EPS, want_attn: bool = False):
+    N, E = geom.n_tokens, geom.heads * geom.head_dim
+    y = torch.empty((N, E), device=o_br.device, dtype=o_br.dtype)
+    attn = torch.empty((N, E), device=o_br.device, dtype=o_br.dtype) if want_attn else None
+    lse = torch.empty((N, geom.heads), device=o_br.device, dtype=torch.float32)
+    mean = torch.empty(N, device=o_br.device, dtype=torch.float32)
+    rstd = torch.empty(N, device=o_br.device, dtype=torch.float32)
+    rc = _lib.load().mt_dilated_merge_ln_fwd(geom.ref(), _p(o_br), _p(lse_br), _dt(o_br), _p(attn), _p(lse), _p(gamma),
+                                             _p(beta), eps, _p(y), _p(mean), _p(rstd), _stream())
+    _check(rc, "mt_dilated_merge_ln_fwd")
+    return y, attn, lse, mean, rstd
+
+
+def dilated_merge_ln_bwd(geom: Geometry, dy, o_br, lse_br, gamma, mean, rstd):
+    N, E = geom.n_tokens, geom.heads * geom.head_dim
+    dattn = torch.empty((N, E), device=o_br.device, dtype=o_br.dtype)
+    delta_br = torch.empty(geom.lse_elems, device=o_br.device, dtype=torch.float32)
+    rc = _lib.load().mt_dilated_merge_ln_bwd(geom.ref(), _p(dy), _p(o_br), _p(lse_br), _p(gamma), _p(mean), _p(rstd),
+                                             _dt(o_br), _p(dattn), _p(delta_br), _stream())
+    _check(rc, "mt_dilated_merge_ln_bwd")
+    return dattn, delta_br
+
+
+def dilated_attn_bwd(geom: Geometry, qkv, dattn, lse, delta_br, impl: int):
+    N, E = geom.n_tokens, geom.heads * geom.head_dim
+    dqkv = torch.empty((N, 3 * E), device=qkv.device, dtype=torch.float32)
+    rc = _lib.load().mt_dilated_attn_bwd(geom.ref(), _p(qkv), qkv.stride(0), qkv.shape[0], _p(dattn), _p(lse),
+                                         _p(delta_br), _dt(qkv), _p(dqkv), impl, _stream())
+    _check(rc, "mt_dilated_attn_bwd", 2)
+    return dqkv
+
+
+def cross_attn_fwd(q, k, v, heads: int):
+    lq, e = q.shape
+    lk = k.shape[0]
+    hd = e // heads
+    o = torch.empty_like(q)
+    lse = torch.empty((lq, heads), device=q.device, dtype=torch.float32)
+    lib = _lib.load()
+    nws = lib.mt_cross_attn_workspace_floats(lq, lk, heads, hd)
+    ws = torch.empty(max(int(nws), 1), device=q.device, dtype=torch.float32)
+    rc = lib.mt_cross_attn_fwd(_p(q), _p(k), _p(v), _dt(q), _p(o), _p(lse), lq, lk, heads, hd, _p(ws), int(nws),
+                               _stream())
+    _check(rc, "mt_cross_attn_fwd", 2 if nws else 1)
+    return o, lse
+
+
+def cross_attn_bwd(q, k, v, o, d_o, lse, heads: int):
+    lq, e = q.shape
+    lk = k.shape[0]
+    dq = torch.empty((lq, e), device=q.device, dtype=torch.float32)
+    dk = torch.empty((lk, e), device=q.device, dtype=torch.float32)
+    dv = torch.empty((lk, e), device=q.device, dtype=torch.float32)
+    rc = _lib.load().mt_cross_attn_bwd(_p(q), _p(k), _p(v), _p(o), _p(d_o), _p(lse), _dt(q), _p(dq), _p(dk), _p(dv), lq,
+                                       lk, heads, e // heads, _stream())
+    _check(rc, "mt_cross_attn_bwd", 5)
+    return dq, dk, dv
+
+
+def embed_assemble(proj, bias, coords, table, cls, tile_size: float = 256.0):
+    """proj [L, E] (GEMM output), coords [L, 2] -> x [L+1, E] fp32 with the sincos positions and the cls row."""
+    L, E = proj.shape
+    x = torch.empty((L + 1, E), device=proj.device, dtype=torch.float32)
+    rc = _lib.load().mt_embed_assemble(_p(proj), _dt(proj), _p(bias), _p(coords), _p(table), _p(cls), _p(x), L, E,
+                                       table.shape[0], float(tile_size), _stream())
+    _check(rc, "mt_embed_assemble")
+    return x
+
+
+def cast(src: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    dst = torch.empty(src.shape, device=src.device, dtype=dtype)
+    rc = _lib.load().mt_cast(_p(src), _dt(src), _p(dst), _dt(dst), src.numel(), _stream())
+    _check(rc, "mt_cast")
+    return dst
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# autograd: trainable LayerNorm, cross-attention core, Injector tail
+# ---------------------------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    """y = LN(x) * gamma + beta [+ add]  with x [rows, 768] fp32; y in ``out_dtype``.  Grads for x, gamma, beta, add."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, add, out_dtype):
+        x = x.contiguous()
+        g32, b32 = _f32(gamma).contiguous(), _f32(beta).contiguous()
+        addc = None
+        if add is not None:
+            assert add.shape == x.shape
+            addc = add.contiguous()
+        y, mean, rstd = layernorm_fwd(x, g32, b32, out_dtype, add=addc)
+        ctx.save_for_backward(x, g32, mean, rstd)
+        ctx.has_add = add is not None
+        ctx.add_dtype = add.dtype if add is not None else None
+        ctx.need_w = gamma.requires_grad or beta.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g32, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx, dgamma, dbeta = layernorm_bwd(dy, x, g32, mean, rstd, x.dtype, want_wgrad=ctx.need_w)
+        dadd = dy.to(ctx.add_dtype) if ctx.has_add else None
+        return dx, dgamma, dbeta, dadd, None
+
+
+def layer_norm(x, gamma, beta, add=None, out_dtype=None):
+    return LayerNormFn.apply(x, gamma, beta, add, out_dtype or x.dtype)
+
+
+class CrossAttnFn(torch.autograd.Function):
+    """softmax(q k^T / sqrt(hd)) v over [L, heads*hd] operands; the core of nn.MultiheadAttention in the adapter."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        o, lse = cross_attn_fwd(q, k, v, heads)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.heads = heads
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, k, v, o, lse = ctx.saved_tensors
+        dq, dk, dv = cross_attn_bwd(q, k, v, o, d_o.contiguous().to(q.dtype), lse, ctx.heads)
+        return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None
+
+
+def cross_attention(q, k, v, heads: int):
+    return CrossAttnFn.apply(q, k, v, heads)
+
+
+def gated_residual_fwd(a, b, g32):
+    y = torch.empty_like(a)
+    rows, cols = a.shape
+    rc = _lib.load().mt_gated_residual(_p(a), _p(b), _dt(b), _p(g32), _p(y), rows, cols, _stream())
+    _check(rc, "mt_gated_residual")
+    return y
+
+
+def gated_residual_bwd(dy, a, b, g32):
+    rows, cols = a.shape
+    da = torch.empty_like(a)
+    db = torch.empty_like(b)
+    dgate = torch.empty(cols, device=a.device, dtype=torch.float32)
+    rc = _lib.load().mt_gated_residual_bwd(_p(dy), _p(a), _p(b), _dt(b), _p(g32), _p(da), _p(db), _dt(db), _p(dgate),
+                                           rows, cols, _stream())
+    _check(rc, "mt_gated_residual_bwd")
+    return da, db, dgate
+
+
+class GatedResidualFn(torch.autograd.Function):
+    """y = a + gate * (a + b): the Injector tail ``query + gamma * (query + attn)`` (adapter_modules.py:231,362)."""
+
+    @staticmethod
+    def forward(ctx, a, b, gate):
+        a, b = a.contiguous(), b.contiguous()
+        g32 = _f32(gate).contiguous()
+        y = gated_residual_fwd(a, b, g32)
+        ctx.save_for_backward(a, b, g32)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, b, g32 = ctx.saved_tensors
+        return gated_residual_bwd(dy.contiguous(), a, b, g32)
+
+
+def gated_residual(a, b, gate):
+    return GatedResidualFn.apply(a, b, gate)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the frozen LongNet encoder layer: one autograd node, dX-only backward
+# ---------------------------------------------------------------------------------------------------------------------
+class FrozenLayerWeights:
+    """Derived, read-only copies of one encoder layer's parameters in the layout the kernels want: fused QKV weight
+    [2304, 768], GEMM operands in the compute dtype, LayerNorm scales in fp32.  Rebuilt when a source parameter
+    changes (``load_state_dict`` / in-place edits bump ``_version``) or moves."""
+
+    def __init__(self):
+        self.key = None
+
+    def refresh(self, layer, dtype: torch.dtype):
+        sa, ffn = layer.self_attn, layer.ffn
+        params = [sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight, sa.q_proj.bias, sa.k_proj.bias,
+                  sa.v_proj.bias, sa.out_proj.weight, sa.out_proj.bias, sa.inner_attn_ln.weight,
+                  sa.inner_attn_ln.bias, layer.self_attn_layer_norm.weight, layer.self_attn_layer_norm.bias,
+                  layer.final_layer_norm.weight, layer.final_layer_norm.bias, ffn.fc1.weight, ffn.fc1.bias,
+                  ffn.fc2.weight, ffn.fc2.bias, ffn.ffn_layernorm.weight, ffn.ffn_layernorm.bias]
+        key = (dtype, tuple((p.data_ptr(), p._version) for p in params))
+        if key == self.key:
+            return self
+        with torch.no_grad():
+            d = lambda p: p.detach().to(dtype).contiguous()
+            f = lambda p: p.detach().float().contiguous()
+            self.w_qkv = torch.cat([d(sa.q_proj.weight), d(sa.k_proj.weight), d(sa.v_proj.weight)], 0).contiguous()
+            self.b_qkv = torch.cat([d(sa.q_proj.bias), d(sa.k_proj.bias), d(sa.v_proj.bias)], 0).contiguous()
+            self.w_o, self.b_o = d(sa.out_proj.weight), d(sa.out_proj.bias)
+            self.w_1, self.b_1 = d(ffn.fc1.weight), d(ffn.fc1.bias)
+            self.w_2, self.b_2 = d(ffn.fc2.weight), d(ffn.fc2.bias)
+            self.ln1 = (f(layer.self_attn_layer_norm.weight), f(layer.self_attn_layer_norm.bias))
+            self.ln2 = (f(layer.final_layer_norm.weight), f(layer.final_layer_norm.bias))
+            self.ln_in = (f(sa.inner_attn_ln.weight), f(sa.inner_attn_ln.bias))
+            self.ln_ffn = (f(ffn.ffn_layernorm.weight), f(ffn.ffn_layernorm.bias))
+        self.key = key
+        return self
+
+
+def _linear(x, w, b):
+    return torch.nn.functional.linear(x, w, b)
+
+
+def _qkv_project(h1: torch.Tensor, W: FrozenLayerWeights, geom: Geometry) -> torch.Tensor:
+    """QKV GEMM into a buffer with ``n_alloc`` rows whose tail rows are zero (the TMA gather reads them as the
+    reference's zero padding, dilated_attention.py:82-111)."""
+    N = geom.n_tokens
+    qkv = torch.empty((geom.n_alloc, 3 * EMBED), device=h1.device, dtype=h1.dtype)
+    torch.addmm(W.b_qkv, h1, W.w_qkv.t(), out=qkv[:N])
+    if geom.n_alloc > N:
+        qkv[N:].zero_()
+    return qkv
+
+
+def encoder_layer_forward(x: torch.Tensor, W: FrozenLayerWeights, geom: Geometry, cdt: torch.dtype, impl):
+    """x [N, 768] fp32 -> (y fp32, saved tensors); ``impl`` = (forward, backward) attention kernel selectors.  Eval-mode EncoderLayer (encoder.py:121-175)."""
+    h1, mean1, rstd1 = layernorm_fwd(x, W.ln1[0], W.ln1[1], cdt)
+    qkv = _qkv_project(h1, W, geom)
+    del h1
+    o_br, lse_br = dilated_attn_fwd(geom, qkv, impl[0])
+    a_ln, _, lse, mean_a, rstd_a = dilated_merge_ln_fwd(geom, o_br, lse_br, W.ln_in[0], W.ln_in[1])
+    attn_out = _linear(a_ln, W.w_o, W.b_o)
+    del a_ln
+    x1, h2, mean2, rstd2 = add_layernorm_fwd(x, attn_out, W.ln2[0], W.ln2[1], cdt)
+    del attn_out
+    f1 = _linear(h2, W.w_1, W.b_1)
+    del h2
+    g, mean_f, rstd_f = gelu_ln_fwd(f1, W.ln_ffn[0], W.ln_ffn[1], cdt)
+    f2 = _linear(g, W.w_2, W.b_2)
+    del g
+    y = x1 + f2 if f2.dtype == torch.float32 else torch.add(x1, f2)
+    saved = (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f)
+    return y, saved
+
+
+def encoder_layer_backward(dy: torch.Tensor, saved, W: FrozenLayerWeights, geom: Geometry, cdt: torch.dtype, impl):
+    """dX of the frozen layer (no weight gradients: every parameter of the slide encoder is frozen,
+    longvit_adapter.py:78-80)."""
+    (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f) = saved
+    dy = dy.contiguous()
+    d_f2 = dy if cdt == torch.float32 else cast(dy, cdt)
+    dg = torch.matmul(d_f2, W.w_2)                                   # [N, 3072]
+    d_f1 = gelu_ln_bwd(dg, f1, W.ln_ffn[0], mean_f, rstd_f, cdt)
+    del dg
+    dh2 = torch.matmul(d_f1, W.w_1)                                  # [N, 768]
+    del d_f1
+    dx1, _, _ = layernorm_bwd(dh2, x1, W.ln2[0], mean2, rstd2, torch.float32, residual=dy)
+    del dh2
+    d_out = dx1 if cdt == torch.float32 else cast(dx1, cdt)
+    d_aln = torch.matmul(d_out, W.w_o)
+    dattn, delta_br = dilated_merge_ln_bwd(geom, d_aln, o_br, lse_br, W.ln_in[0], mean_a, rstd_a)
+    del d_aln
+    dqkv = dilated_attn_bwd(geom, qkv, dattn, lse, delta_br, impl[1])   # fp32 [N, 2304]
+    dqkv_c = dqkv if cdt == torch.float32 else cast(dqkv, cdt)
+    dh1 = torch.matmul(dqkv_c, W.w_qkv)
+    dx, _, _ = layernorm_bwd(dh1, x, W.ln1[0], mean1, rstd1, torch.float32, residual=dx1)
+    return dx
+
+
+class FrozenEncoderLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, geom, cdt, impl):
+        y, saved = encoder_layer_forward(x.contiguous(), W, geom, cdt, impl)
+        ctx.save_for_backward(*saved)
+        ctx.W, ctx.geom, ctx.cdt, ctx.impl = W, geom, cdt, impl
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx = encoder_layer_backward(dy, ctx.saved_tensors, ctx.W, ctx.geom, ctx.cdt, ctx.impl)
+        return dx, None, None, None, None
+
+
+def frozen_encoder_layer(x, W, geom, cdt, impl):
+    if torch.is_grad_enabled() and x.requires_grad:
+        return FrozenEncoderLayerFn.apply(x, W, geom, cdt, impl)
+    y, _ = encoder_layer_forward(x.contiguous(), W, geom, cdt, impl)
+    return y
+
+
+def attention_flops(geom: Geometry) -> Tuple[float, float]:
+    """(forward, backward) algorithmic attention FLOPs of one layer."""
+    return geom.flops_fwd, 2.5 * geom.flops_fwd
