@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Benchmark of the ModalTune-GigaPath fine-tuning hot path (BASELINE.json: slides/s fwd+bwd at 10k tiles).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--tiles L] [--mode bf16|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one slide through the reference's training step: 3 task passes forward, the KL-distillation loss, one backward
+(`train_modaltune.py:156-179, 218-235`), plus the data-parallel all-reduce of the trainable gradients when N > 1.  Every
+rank processes its own slides (weak scaling, no data-path collective).  Prints ONE JSON line on rank 0.
+
+* ``value``: device-resident slides/s (inputs already in HBM), CUDA events, max over ranks.
+* ``e2e``: the same step driven from pinned HOST buffers through the module API, H2D copy of the slide and D2H read of
+  loss / logits inside the timed region.
+* ``roofline``: the dilated-attention backward kernel (the dominant kernel), timed live with CUDA events on its stream
+  inside the timed region; algorithmic FLOPs = 2.5 * 4*d*sum c^2 per launch against the measured bf16
+  tensor peak of MEASURED_PEAKS.json.
+* ``cpu_baseline`` / ``--impl reference``: the oracle port of the reference's CPU arithmetic (the reference is pure
+  Python and does not travel to the GPU box) on the host cores, on a bounded sample: ONE encoder-layer forward+backward
+  at the same token count, scaled by the 36 layer passes of a slide step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tiles", type=int, default=10000)
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--attn", default="auto", choices=["auto", "simt", "sm100"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+METRIC = "slides/s fwd+bwd, GigaPath+ModalTune 10k tiles"
+UNIT = "slides/s"
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"ModalTune-GigaPath (LongNet 12L/768d/16h dilated attention + Modal Adapter), synthetic "
+                    f"{args.tiles}-tile slides + 331 pathway tokens + clinical + text-task embeddings, 3 task passes "
+                    f"fwd + KL-distillation loss + bwd per slide (BASELINE.json configs[1])",
+        "tiles": args.tiles, "tokens": args.tiles + 1, "modal_tokens": 66, "task_passes": 3,
+        "slides_per_step_per_gpu": 1, "parallelism": f"slide-sharded dp{world}",
+        "l2": "working set per step (several GB of saved activations) exceeds the 126 MB L2; no explicit flush",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port, one encoder layer fwd+bwd at the bench token count, scaled to a slide step
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_layer_sample(n_tokens: int, reps: int = 1):
+    """Seconds for one frozen-encoder-layer forward+backward (dX) of the oracle at ``n_tokens`` tokens, fp32."""
+    from modaltune_b200 import synthetic
+    from oracle import modaltune_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    shapes = {"self_attn.q_proj": (768, 768), "self_attn.k_proj": (768, 768), "self_attn.v_proj": (768, 768),
+              "self_attn.out_proj": (768, 768), "ffn.fc1": (3072, 768), "ffn.fc2": (768, 3072)}
+    sd = {}
+    for k, shp in shapes.items():
+        sd[f"encoder.layers.0.{k}.weight"] = torch.empty(shp)
+        sd[f"encoder.layers.0.{k}.bias"] = torch.empty(shp[0])
+    for k, n in (("self_attn.inner_attn_ln", 768), ("self_attn_layer_norm", 768), ("final_layer_norm", 768),
+                 ("ffn.ffn_layernorm", 3072)):
+        sd[f"encoder.layers.0.{k}.weight"] = torch.empty(n)
+        sd[f"encoder.layers.0.{k}.bias"] = torch.empty(n)
+    synthetic.seeded_init_(sd.items(), seed=0)
+    g = torch.Generator().manual_seed(0)
+    seg = O.optimal_segment_lengths()
+    times = []
+    for _ in range(reps):
+        x = torch.randn(n_tokens, 768, generator=g).requires_grad_(True)
+        dy = torch.randn(n_tokens, 768, generator=g)
+        t0 = time.perf_counter()
+        y = O.encoder_layer(sd, 0, x, seg, O.DILATED_RATIO)
+        torch.autograd.grad(y, x, dy)
+        times.append(time.perf_counter() - t0)
+    return sorted(times)[len(times) // 2]
+
+
+def cpu_baseline(n_tokens: int):
+    t = cpu_layer_sample(n_tokens, reps=1)
+    return {"value": 1.0 / (36.0 * t), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"oracle (CPU restatement of the reference, fp32, torch {torch.get_num_threads()} threads): one "
+                      f"LongNet encoder layer forward+backward at {n_tokens} tokens = {t:.2f} s, scaled by the 36 layer "
+                      f"passes of a slide step (adapter cross-attention and embedding, ~3% of the FLOPs, excluded)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_tokens = args.tiles + 1
+    for _ in range(min(args.warmup, 1)):
+        cpu_layer_sample(n_tokens)
+    ts = [cpu_layer_sample(n_tokens) for _ in range(args.steps)]
+    t = sum(ts) / len(ts)
+    value = 1.0 / (36.0 * t)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 36.0 * t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"each step = one oracle encoder-layer fwd+bwd at {n_tokens} tokens "
+                                   f"({t:.2f} s mean), scaled x36 layer passes per slide step; the reference is pure "
+                                   f"Python with no CPU attention kernel of its own (flash_attn_func is None on CPU)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def pack_host_slide(slide):
+    """Pinned host staging of one case: the 331 pathway vectors are packed into one buffer (one H2D copy, not 331)."""
+    sizes = [slide["genes"][i].shape[1] for i in range(len(slide["genes"]))]
+    genes = torch.cat([slide["genes"][i].reshape(-1) for i in range(len(sizes))])
+    host = {"x": slide["x"], "coords": slide["coords"], "genes_flat": genes, "clinical": slide["clinical"],
+            "text": slide["text"]}
+    host = {k: v.contiguous().pin_memory() for k, v in host.items()}
+    nbytes = sum(v.numel() * v.element_size() for v in host.values())
+    return host, sizes, nbytes
+
+
+def host_to_device(host, sizes, dev):
+    d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    parts = torch.split(d.pop("genes_flat"), sizes)
+    d["genes"] = {i: p.unsqueeze(0) for i, p in enumerate(parts)}
+    return d
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+
+    from modaltune_b200 import _lib, config, ops, synthetic, train_step
+    from tests import helpers
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path in modaltune_b200)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    config.set_mode(args.mode)
+    config.set_attn_impl(args.attn)
+
+    model = helpers.build_model(None, device=dev)          # full 331-pathway ModalTune-GigaPath, seeded random init
+    proj = helpers.build_projector(0, dev)
+    flat = train_step.FlatGradAllReduce([p for p in model.parameters() if p.requires_grad])
+    n_slides = 2
+    hosts = [pack_host_slide(synthetic.synthetic_slide(args.tiles, seed=1000 + rank * 100 + i)) for i in range(n_slides)]
+    resident = [host_to_device(h, s, dev) for h, s, _ in hosts]
+    h2d_bytes = hosts[0][2]
+    geom = ops.Geometry.get(args.tiles + 1, model.segment_lengths, (1, 2, 4, 8, 16))
+
+    def step(slide):
+        flat.zero()
+        loss, logits = train_step.forward_backward(model, proj, slide)
+        flat.all_reduce()
+        return loss, logits
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(run, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            run(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    # ---- warm-up -------------------------------------------------------------------------------------------------
+    for i in range(max(args.warmup, 3)):
+        step(resident[i % n_slides])
+    torch.cuda.synchronize()
+
+    # ---- device-resident timed region --------------------------------------------------------------------------------
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    ops.kernel_events = {}
+    launches0 = ops.launch_count
+    ms = timed(lambda i: step(resident[i % n_slides]), args.steps)
+    launches = ops.launch_count - launches0
+    events, ops.kernel_events = ops.kernel_events, None
+    value = world * args.steps / (ms / 1e3)
+
+    # ---- end to end: pinned host -> device, step, loss/logits back to the host ---------------------------------------
+    out = {}
+
+    def e2e_step(i):
+        h, s, _ = hosts[i % n_slides]
+        loss, logits = step(host_to_device(h, s, dev))
+        out["loss"], out["logits"] = float(loss), logits.float().cpu()   # D2H reads (synchronising, like loss.item())
+
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    e2e_value = world * args.steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (dilated-attention backward) ------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    else:
+        peak, peak_src = 1590.0, "fallback (B200_PROFILING.md)"
+    f_fwd, f_bwd = ops.attention_flops(geom)
+
+    def avg_ms(name):
+        ev = events.get(name, [])
+        return sum(a.elapsed_time(b) for a, b in ev) / max(len(ev), 1), len(ev)
+
+    t_bwd, n_bwd = avg_ms("dilated_attn_bwd")
+    t_fwd, n_fwd = avg_ms("dilated_attn_fwd")
+    ach_bwd = f_bwd / (t_bwd * 1e-3) / 1e12 if t_bwd > 0 else 0.0
+    ach_fwd = f_fwd / (t_fwd * 1e-3) / 1e12 if t_fwd > 0 else 0.0
+    impl_names = {0: "simt", 1: "tcgen05"}
+    roofline = {
+        "bound": "tensor", "kernel": f"dilated_attn_bwd[{impl_names[config.attn_impl('bwd')]}]", "achieved": ach_bwd,
+        "peak": peak, "peak_source": peak_src, "unit": "TFLOP/s", "frac": ach_bwd / peak, "traffic": None,
+        "launch_ms": t_bwd, "launches_timed": n_bwd, "algorithmic_gflop_per_launch": f_bwd / 1e9,
+        "share_of_step": t_bwd * n_bwd / ms,
+        "fwd": {"kernel": f"dilated_attn_fwd[{impl_names[config.attn_impl('fwd')]}]", "achieved": ach_fwd,
+                "frac": ach_fwd / peak, "launch_ms": t_fwd, "launches_timed": n_fwd,
+                "algorithmic_gflop_per_launch": f_fwd / 1e9, "share_of_step": t_fwd * n_fwd / ms},
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4 + 3 * 256 * 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clk, "roofline": roofline,
+        "attention_tflops": {"fwd": ach_fwd, "bwd": ach_bwd},
+        "loss": out.get("loss"),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.tiles + 1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -27,6 +27,28 @@ LN_EPS = 1e-5
 
 # kernel-launch counter (bench.py reports it as `gpu_launches`); incremented once per C-ABI launch call
 launch_count = 0
+# optional per-kernel CUDA-event timing (bench.py's roofline leg): name -> [(start_event, stop_event), ...]
+kernel_events = None
+
+
+class _timed:
+    """Record CUDA events on the launching stream around one kernel when ``kernel_events`` is a dict."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if kernel_events is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.stop = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if kernel_events is not None:
+            self.stop.record()
+            kernel_events.setdefault(self.name, []).append((self.start, self.stop))
+        return False
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -174,8 +196,9 @@ def dilated_attn_fwd(geom: Geometry, qkv: torch.Tensor, impl: int):
     """qkv [n_alloc, 3E] -> (o_br [o_elems], lse_br [lse_elems]) in the compact per-branch layout."""
     o_br = torch.empty(geom.o_elems, device=qkv.device, dtype=qkv.dtype)
     lse_br = torch.empty(geom.lse_elems, device=qkv.device, dtype=torch.float32)
-    rc = _lib.load().mt_dilated_attn_fwd(geom.ref(), _p(qkv), qkv.stride(0), qkv.shape[0], _dt(qkv), _p(o_br),
-                                         _p(lse_br), impl, _stream())
+    with _timed("dilated_attn_fwd"):
+        rc = _lib.load().mt_dilated_attn_fwd(geom.ref(), _p(qkv), qkv.stride(0), qkv.shape[0], _dt(qkv), _p(o_br),
+                                             _p(lse_br), impl, _stream())
     _check(rc, "mt_dilated_attn_fwd")
     return o_br, lse_br
 
@@ -206,8 +229,9 @@ def dilated_merge_ln_bwd(geom: Geometry, dy, o_br, lse_br, gamma, mean, rstd):
 def dilated_attn_bwd(geom: Geometry, qkv, dattn, lse, delta_br, impl: int):
     N, E = geom.n_tokens, geom.heads * geom.head_dim
     dqkv = torch.empty((N, 3 * E), device=qkv.device, dtype=torch.float32)
-    rc = _lib.load().mt_dilated_attn_bwd(geom.ref(), _p(qkv), qkv.stride(0), qkv.shape[0], _p(dattn), _p(lse),
-                                         _p(delta_br), _dt(qkv), _p(dqkv), impl, _stream())
+    with _timed("dilated_attn_bwd"):
+        rc = _lib.load().mt_dilated_attn_bwd(geom.ref(), _p(qkv), qkv.stride(0), qkv.shape[0], _p(dattn), _p(lse),
+                                             _p(delta_br), _dt(qkv), _p(dqkv), impl, _stream())
     _check(rc, "mt_dilated_attn_bwd", 2)
     return dqkv
 

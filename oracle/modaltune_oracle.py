@@ -107,6 +107,25 @@ def branch_geometry(n_tokens: int, segment_length: int, ratio: int, heads: int =
     return g, n_seg, m, offsets
 
 
+class _ScatterRows(torch.autograd.Function):
+    """Write per-(segment, offset) blocks [hpb, c, d] into the strided rows of a dense [N, H, d] tensor (the reference's
+    sparse_to_dense, dilated_attention.py:39-59) with a cheap strided-slice backward."""
+
+    @staticmethod
+    def forward(ctx, base, r, hpb, where, *blocks):
+        out = base.clone()
+        for (lo, hi, o), blk in zip(where, blocks):
+            out[lo:hi:r, o * hpb:(o + 1) * hpb] = blk.transpose(0, 1)
+        ctx.meta = (r, hpb, where)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        r, hpb, where = ctx.meta
+        return (None, None, None, None) + tuple(grad[lo:hi:r, o * hpb:(o + 1) * hpb].transpose(0, 1)
+                                                for lo, hi, o in where)
+
+
 def dilated_attention_core(q: Tensor, k: Tensor, v: Tensor, segment_lengths: Sequence[int],
                            ratios: Sequence[int], return_branches: bool = False):
     """q, k, v [N, H, d] -> merged attention [N, H*d].
@@ -123,26 +142,48 @@ def dilated_attention_core(q: Tensor, k: Tensor, v: Tensor, segment_lengths: Seq
     outs, lses = [], []
     for sl, r in zip(segment_lengths, ratios):
         g, n_seg, m, offsets = branch_geometry(N, int(sl), int(r), H)
-        o_b = torch.zeros(N, H, d, dtype=dt)
-        lse_b = torch.full((N, H), -1e8, dtype=dt)
+        hpb = H // r  # heads h with floor(h*r/H) == o are the contiguous block [o*hpb, (o+1)*hpb)
+        o_parts = [[None] * r for _ in range(n_seg)]
+        l_parts = [[None] * r for _ in range(n_seg)]
         for s in range(n_seg):
             seg_end = min(N, (s + 1) * g)
-            for h in range(H):
-                idx = s * g + offsets[h] + r * torch.arange(m)
-                real = idx[idx < seg_end]
-                n_zero = m - real.numel()
-                if real.numel() == 0:
+            for o in range(r):
+                lo = s * g + o
+                # slots j = 0..m-1 sit at positions lo + j*r; the real ones are the strided slice below
+                qs = q[lo:seg_end:r, o * hpb:(o + 1) * hpb].transpose(0, 1)   # [hpb, c, d]
+                c = qs.shape[1]
+                if c == 0:
                     continue
-                qs, ks, vs = q[real, h], k[real, h], v[real, h]
-                sc = (qs @ ks.t()) * scale
+                ks = k[lo:seg_end:r, o * hpb:(o + 1) * hpb].transpose(0, 1)
+                vs = v[lo:seg_end:r, o * hpb:(o + 1) * hpb].transpose(0, 1)
+                sc = torch.matmul(qs, ks.transpose(1, 2)) * scale             # [hpb, c, c]
+                n_zero = m - c
+                mx = sc.max(dim=-1, keepdim=True).values.detach()
                 if n_zero > 0:
-                    sc_full = torch.cat([sc, sc.new_zeros(sc.shape[0], n_zero)], dim=1)
-                else:
-                    sc_full = sc
-                lse = torch.logsumexp(sc_full, dim=1)
-                p = torch.exp(sc - lse[:, None])
-                o_b[real, h] = p @ vs
-                lse_b[real, h] = lse.detach()
+                    mx = mx.clamp(min=0.0)
+                e = torch.exp(sc - mx)
+                den = e.sum(-1, keepdim=True)
+                if n_zero > 0:
+                    den = den + n_zero * torch.exp(-mx)                        # zero keys: score 0, value 0
+                o_parts[s][o] = (torch.matmul(e, vs) / den, lo, seg_end)
+                l_parts[s][o] = (mx + torch.log(den)).squeeze(-1).detach()
+        # assemble the dense per-branch tensors (zeros / -1e8 where a head does not own a position, :39-59)
+        o_b = torch.zeros(N, H, d, dtype=dt)
+        lse_b = torch.full((N, H), -1e8, dtype=dt)
+        pieces = []
+        for s in range(n_seg):
+            for o in range(r):
+                if o_parts[s][o] is None:
+                    continue
+                ob, lo, hi = o_parts[s][o]
+                pieces.append((ob, l_parts[s][o], lo, hi, o))
+        if q.requires_grad or k.requires_grad or v.requires_grad:
+            o_b = _ScatterRows.apply(o_b, r, hpb, [(lo, hi, o) for _, _, lo, hi, o in pieces], *[p[0] for p in pieces])
+        else:
+            for ob, _, lo, hi, o in pieces:
+                o_b[lo:hi:r, o * hpb:(o + 1) * hpb] = ob.transpose(0, 1)
+        for _, lb, lo, hi, o in pieces:
+            lse_b[lo:hi:r, o * hpb:(o + 1) * hpb] = lb.transpose(0, 1)
         outs.append(o_b)
         lses.append(lse_b)
     with torch.no_grad():

@@ -1,0 +1,179 @@
+"""Kernel-level parity on the B200: every C-ABI entry point against the oracle-based CPU statement of the same op
+(``tests/cpu_kernels.py``) on identical seeded inputs.  fp32 kernels: tight tolerance; bf16 storage: bf16 rounding.
+"""
+import math
+
+import pytest
+import torch
+
+from modaltune_b200 import _lib, ops
+from modaltune_b200.slide_encoder import DILATED_RATIO, optimal_segment_lengths
+from tests import cpu_kernels as C
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def tol(dtype):
+    return 2e-5 if dtype == torch.float32 else 2e-2
+
+
+def test_library_loads_on_sm100():
+    lib = _lib.load()
+    assert lib.mt_version() >= 100
+    assert lib.mt_device_is_sm100() == 1
+
+
+@pytest.mark.parametrize("cols", [768, 3072])
+@pytest.mark.parametrize("xdt,ydt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                     (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("rows", [1, 66, 1037])
+def test_layernorm_fwd_bwd(rows, cols, xdt, ydt):
+    g = torch.Generator().manual_seed(rows * 7 + cols)
+    x = (torch.randn(rows, cols, generator=g) * 1.7 + 0.3).to(xdt)
+    gamma, beta = 1 + 0.1 * torch.randn(cols, generator=g), 0.1 * torch.randn(cols, generator=g)
+    dy = torch.randn(rows, cols, generator=g).to(ydt)
+    res = torch.randn(rows, cols, generator=g)
+    y_c, m_c, r_c = C.layernorm_fwd(x, gamma, beta, ydt)
+    y, m, r = ops.layernorm_fwd(x.to(DEV), gamma.to(DEV), beta.to(DEV), ydt)
+    assert rel(y, y_c) < tol(ydt) and rel(m, m_c) < 1e-5 and rel(r, r_c) < 1e-4
+    want_w = xdt == torch.float32 and cols == 768
+    dx_c, dg_c, db_c = C.layernorm_bwd(dy, x, gamma, m_c, r_c, torch.float32, residual=res, want_wgrad=want_w)
+    dx, dg, db = ops.layernorm_bwd(dy.to(DEV), x.to(DEV), gamma.to(DEV), m, r, torch.float32, residual=res.to(DEV),
+                                   want_wgrad=want_w)
+    assert rel(dx, dx_c) < 2e-5
+    if want_w:
+        assert rel(dg, dg_c) < 1e-4 and rel(db, db_c) < 1e-4
+
+
+def test_layernorm_fused_add_and_add_layernorm():
+    g = torch.Generator().manual_seed(5)
+    x, a = torch.randn(66, 768, generator=g), torch.randn(66, 768, generator=g)
+    gamma, beta = 1 + 0.1 * torch.randn(768, generator=g), 0.1 * torch.randn(768, generator=g)
+    y_c, _, _ = C.layernorm_fwd(x, gamma, beta, torch.float32, add=a)
+    y, _, _ = ops.layernorm_fwd(x.to(DEV), gamma.to(DEV), beta.to(DEV), torch.float32, add=a.to(DEV))
+    assert rel(y, y_c) < 2e-5
+    for adt in (torch.float32, torch.bfloat16):
+        xo_c, y_c, m_c, r_c = C.add_layernorm_fwd(x, a.to(adt), gamma, beta, adt)
+        xo, y, m, r = ops.add_layernorm_fwd(x.to(DEV), a.to(adt).to(DEV), gamma.to(DEV), beta.to(DEV), adt)
+        assert rel(xo, xo_c) < 1e-6 and rel(y, y_c) < tol(adt) and rel(m, m_c) < 1e-5 and rel(r, r_c) < 1e-4
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_gelu_ln_fwd_bwd(dt):
+    g = torch.Generator().manual_seed(11)
+    h = (torch.randn(513, 3072, generator=g) * 1.5).to(dt)
+    gamma, beta = 1 + 0.1 * torch.randn(3072, generator=g), 0.1 * torch.randn(3072, generator=g)
+    dy = torch.randn(513, 3072, generator=g).to(dt)
+    y_c, m_c, r_c = C.gelu_ln_fwd(h, gamma, beta, dt)
+    y, m, r = ops.gelu_ln_fwd(h.to(DEV), gamma.to(DEV), beta.to(DEV), dt)
+    assert rel(y, y_c) < tol(dt) and rel(m, m_c) < 1e-4 and rel(r, r_c) < 1e-4
+    dh_c = C.gelu_ln_bwd(dy, h, gamma, m_c, r_c, dt)
+    dh = ops.gelu_ln_bwd(dy.to(DEV), h.to(DEV), gamma.to(DEV), m, r, dt)
+    assert rel(dh, dh_c) < tol(dt)
+
+
+def test_embed_assemble_and_cast_and_gated_residual():
+    g = torch.Generator().manual_seed(3)
+    L = 777
+    proj = torch.randn(L, 768, generator=g)
+    bias, cls = torch.randn(768, generator=g), torch.randn(768, generator=g)
+    from modaltune_b200.slide_encoder import sincos_factor
+    table = sincos_factor(1000, 768)
+    cells = torch.randint(0, 999, (L, 2), generator=g).float() * 256.0 + torch.rand(L, 2, generator=g) * 200
+    x_c = C.embed_assemble(proj, bias, cells, table, cls)
+    for dt in (torch.float32, torch.bfloat16):
+        x = ops.embed_assemble(proj.to(dt).to(DEV), bias.to(DEV), cells.to(DEV), table.to(DEV), cls.to(DEV))
+        assert rel(x, C.embed_assemble(proj.to(dt), bias, cells, table, cls)) < 1e-6
+    assert rel(ops.embed_assemble(proj.to(DEV), bias.to(DEV), cells.to(DEV), table.to(DEV), cls.to(DEV)), x_c) < 1e-6
+    v = torch.randn(100003, generator=g)
+    assert torch.equal(ops.cast(v.to(DEV), torch.bfloat16).cpu(), v.to(torch.bfloat16))
+    a, b, gate = torch.randn(301, 768, generator=g), torch.randn(301, 768, generator=g), torch.randn(768, generator=g)
+    dy = torch.randn(301, 768, generator=g)
+    for dt in (torch.float32, torch.bfloat16):
+        y = ops.gated_residual_fwd(a.to(DEV), b.to(dt).to(DEV), gate.to(DEV))
+        assert rel(y, C.gated_residual_fwd(a, b.to(dt), gate)) < 1e-6
+        da, db, dg = ops.gated_residual_bwd(dy.to(DEV), a.to(DEV), b.to(dt).to(DEV), gate.to(DEV))
+        da_c, db_c, dg_c = C.gated_residual_bwd(dy, a, b.to(dt), gate)
+        assert rel(da, da_c) < 1e-6 and rel(db, db_c) < tol(dt) and rel(dg, dg_c) < 1e-4
+
+
+@pytest.mark.parametrize("lq,lk", [(700, 66), (66, 700), (66, 10000), (5000, 13), (1, 1), (129, 65)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_cross_attention_core(lq, lk, dt):
+    g = torch.Generator().manual_seed(lq * 31 + lk)
+    q, k, v = (torch.randn(n, 192, generator=g).to(dt) for n in (lq, lk, lk))
+    d_o = torch.randn(lq, 192, generator=g).to(dt)
+    o_c, lse_c = C.cross_attn_fwd(q, k, v, 12)
+    o, lse = ops.cross_attn_fwd(q.to(DEV), k.to(DEV), v.to(DEV), 12)
+    assert rel(o, o_c) < tol(dt) and rel(lse, lse_c) < 1e-5
+    dq_c, dk_c, dv_c = C.cross_attn_bwd(q, k, v, o_c, d_o, lse_c, 12)
+    dq, dk, dv = ops.cross_attn_bwd(q.to(DEV), k.to(DEV), v.to(DEV), o, d_o.to(DEV), lse, 12)
+    t = 5e-5 if dt == torch.float32 else 3e-2  # bf16: delta = dO.o uses the rounded o
+    assert rel(dq, dq_c) < t and rel(dk, dk_c) < t and rel(dv, dv_c) < t
+
+
+GEOMS = [  # (N, segment lengths) -- the reference's edge geometries: N around segment lengths,
+    # N % r != 0, N < 16, tails that are almost all padding
+    (7, [16, 24, 32, 64, 128]), (75, [16, 24, 32, 64, 128]), (97, [8, 32, 64, 96, 256]),
+    (130, [32, 64, 128, 256, 512]), (1024, None), (1025, None), (1500, None), (2049, [256, 512, 1024, 4096, 8192]),
+]
+
+
+def _qkv(N, n_alloc, g, dt, scale=1.0):
+    qkv = torch.zeros(n_alloc, 2304)
+    qkv[:N] = torch.randn(N, 2304, generator=g) * scale
+    return qkv.to(dt)
+
+
+@pytest.mark.parametrize("N,sl", GEOMS)
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_dilated_attention_simt_vs_oracle(N, sl, dt):
+    sl = sl or optimal_segment_lengths()
+    geom = ops.Geometry.get(N, sl, DILATED_RATIO)
+    g = torch.Generator().manual_seed(N)
+    qkv = _qkv(N, geom.n_alloc, g, dt, 1.5)
+    gamma, beta = 1 + 0.1 * torch.randn(768, generator=g), 0.1 * torch.randn(768, generator=g)
+    dy = torch.randn(N, 768, generator=g).to(dt)
+    o_c, l_c = C.dilated_attn_fwd(geom, qkv, 0)
+    o, l = ops.dilated_attn_fwd(geom, qkv.to(DEV), 0)
+    assert rel(l, l_c) < 1e-5 and rel(o, o_c) < tol(dt)
+    y_c, a_c, lse_c, m_c, r_c = C.dilated_merge_ln_fwd(geom, o_c, l_c, gamma, beta, want_attn=True)
+    y, a, lse, m, r = ops.dilated_merge_ln_fwd(geom, o, l, gamma.to(DEV), beta.to(DEV), want_attn=True)
+    assert rel(a, a_c) < tol(dt) and rel(lse, lse_c) < 1e-5 and rel(y, y_c) < 2 * tol(dt)
+    da_c, de_c = C.dilated_merge_ln_bwd(geom, dy, o_c, l_c, gamma, m_c, r_c)
+    da, de = ops.dilated_merge_ln_bwd(geom, dy.to(DEV), o, l, gamma.to(DEV), m, r)
+    assert rel(da, da_c) < 2 * tol(dt) and rel(de, de_c) < 2 * tol(dt)
+    dq_c = C.dilated_attn_bwd(geom, qkv, da_c, lse_c, de_c, 0)
+    dq = ops.dilated_attn_bwd(geom, qkv.to(DEV), da_c.to(DEV), lse_c.to(DEV), de_c.to(DEV), 0)
+    assert rel(dq, dq_c) < (1e-4 if dt == torch.float32 else 3e-2)
+
+
+def test_dilated_attention_linearity_in_v_at_full_size():
+    """Size-independent property at the bench size (10k tiles): attention is linear in V, and the merged weights sum
+    to one (constant V -> constant output)."""
+    N = 10001
+    geom = ops.Geometry.get(N, optimal_segment_lengths(), DILATED_RATIO)
+    g = torch.Generator().manual_seed(1)
+    qkv = _qkv(N, geom.n_alloc, g, torch.float32).to(DEV)
+    ones = torch.ones(768, device=DEV)
+    zeros = torch.zeros(768, device=DEV)
+
+    def attn(t):
+        o, l = ops.dilated_attn_fwd(geom, t, 0)
+        return ops.dilated_merge_ln_fwd(geom, o, l, ones, zeros, want_attn=True)[1]
+
+    a1 = attn(qkv)
+    q2 = qkv.clone()
+    q2[:N, 1536:] *= -2.5
+    assert rel(attn(q2), -2.5 * a1) < 1e-5
+    q3 = qkv.clone()
+    q3[:N, 1536:] = 0.75
+    # rows whose branches contain zero-padded slots see value 0 there: output <= 0.75, and == 0.75 where no padding
+    a3 = attn(q3)
+    assert float(a3.max()) <= 0.75 + 1e-5 and float(a3.min()) > 0.0
