@@ -104,8 +104,9 @@ int mt_dilated_merge_ln_fwd(const mt_dilated_geometry* geom, const void* o_br, c
                             void* attn, float* lse, const float* gamma, const float* beta, float eps, void* y,
                             float* mean, float* rstd, void* stream);
 /* backward of LN then of the (detached-weight) merge.  attn is recomputed from o_br / lse_br (never stored):
- * dattn [N,E] (dtype) = LN'(dy);  delta_br (lse_br compaction, f32) = dattn[p,h,:] . o_b[p,h,:]. */
-int mt_dilated_merge_ln_bwd(const mt_dilated_geometry* geom, const void* dy, const void* o_br, const float* lse_br,
+ * dattn [N,E] (dtype) = LN'(dy), dy in dy_dtype;  delta_br (lse_br compaction, f32) = dattn[p,h,:] . o_b[p,h,:]. */
+int mt_dilated_merge_ln_bwd(const mt_dilated_geometry* geom, const void* dy, int dy_dtype, const void* o_br,
+                            const float* lse_br,
                             const float* gamma, const float* mean, const float* rstd, int dtype, void* dattn,
                             float* delta_br, void* stream);
 

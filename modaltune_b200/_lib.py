@@ -47,7 +47,7 @@ SIGNATURES = {
     "mt_gelu_ln_bwd": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, c_int, _I64, _I64, _P]),
     "mt_dilated_attn_fwd": (c_int, [_G, _P, _I64, _I64, c_int, _P, _P, c_int, _P]),
     "mt_dilated_merge_ln_fwd": (c_int, [_G, _P, _P, c_int, _P, _P, _P, _P, c_float, _P, _P, _P, _P]),
-    "mt_dilated_merge_ln_bwd": (c_int, [_G, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
+    "mt_dilated_merge_ln_bwd": (c_int, [_G, _P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
     "mt_dilated_attn_bwd": (c_int, [_G, _P, _I64, _I64, _P, _P, _P, c_int, _P, c_int, _P]),
     "mt_cross_attn_fwd": (c_int, [_P, _P, _P, c_int, _P, _P, _I64, _I64, c_int, c_int, _P, _I64, _P]),
     "mt_cross_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _I64, _I64, c_int, c_int, _P]),

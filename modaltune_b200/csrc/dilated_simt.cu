@@ -396,8 +396,8 @@ __global__ void __launch_bounds__(256) merge_ln_fwd_kernel(const DilatedGeom G, 
 }
 
 // dattn = LN'(dy) with attn recomputed from the branch outputs; delta_b[p, h] = dattn[p, h, :] . o_b[p, h, :]
-template <typename T>
-__global__ void __launch_bounds__(256) merge_ln_bwd_kernel(const DilatedGeom G, const T* __restrict__ dy,
+template <typename T, typename TDY>
+__global__ void __launch_bounds__(256) merge_ln_bwd_kernel(const DilatedGeom G, const TDY* __restrict__ dy,
                                                            const T* __restrict__ o_br,
                                                            const float* __restrict__ lse_br,
                                                            const float* __restrict__ gamma,
@@ -564,9 +564,9 @@ extern "C" int mt_dilated_merge_ln_fwd(const mt_dilated_geometry* geom, const vo
   return check_launch("merge_ln_fwd_kernel");
 }
 
-extern "C" int mt_dilated_merge_ln_bwd(const mt_dilated_geometry* geom, const void* dy, const void* o_br,
-                                       const float* lse_br, const float* gamma, const float* mean, const float* rstd,
-                                       int dtype, void* dattn, float* delta_br, void* stream) {
+extern "C" int mt_dilated_merge_ln_bwd(const mt_dilated_geometry* geom, const void* dy, int dy_dtype,
+                                       const void* o_br, const float* lse_br, const float* gamma, const float* mean,
+                                       const float* rstd, int dtype, void* dattn, float* delta_br, void* stream) {
   DilatedGeom G;
   int rc = make_dilated_geom(geom, &G);
   if (rc) return rc;
@@ -574,11 +574,19 @@ extern "C" int mt_dilated_merge_ln_bwd(const mt_dilated_geometry* geom, const vo
   cudaStream_t st = (cudaStream_t)stream;
   int grid = (G.N + 7) / 8;
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-  if (dtype == MT_F32)
-    merge_ln_bwd_kernel<float><<<grid, 256, 0, st>>>(G, (const float*)dy, (const float*)o_br, lse_br, gamma, mean, rstd,
-                                                     (float*)dattn, delta_br);
-  else
-    merge_ln_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(G, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)o_br,
-                                                             lse_br, gamma, mean, rstd, (__nv_bfloat16*)dattn, delta_br);
+  using bf = __nv_bfloat16;
+  if (dtype == MT_F32 && dy_dtype == MT_F32)
+    merge_ln_bwd_kernel<float, float><<<grid, 256, 0, st>>>(G, (const float*)dy, (const float*)o_br, lse_br, gamma, mean,
+                                                            rstd, (float*)dattn, delta_br);
+  else if (dtype == MT_BF16 && dy_dtype == MT_BF16)
+    merge_ln_bwd_kernel<bf, bf><<<grid, 256, 0, st>>>(G, (const bf*)dy, (const bf*)o_br, lse_br, gamma, mean, rstd,
+                                                      (bf*)dattn, delta_br);
+  else if (dtype == MT_BF16 && dy_dtype == MT_F32)
+    merge_ln_bwd_kernel<bf, float><<<grid, 256, 0, st>>>(G, (const float*)dy, (const bf*)o_br, lse_br, gamma, mean, rstd,
+                                                         (bf*)dattn, delta_br);
+  else {
+    set_error("merge_ln_bwd: unsupported dtype combination (%d, dy %d)", dtype, dy_dtype);
+    return MT_E_UNSUPPORTED;
+  }
   return check_launch("merge_ln_bwd_kernel");
 }

@@ -220,8 +220,8 @@ def dilated_merge_ln_bwd(geom: Geometry, dy, o_br, lse_br, gamma, mean, rstd):
     N, E = geom.n_tokens, geom.heads * geom.head_dim
     dattn = torch.empty((N, E), device=o_br.device, dtype=o_br.dtype)
     delta_br = torch.empty(geom.lse_elems, device=o_br.device, dtype=torch.float32)
-    rc = _lib.load().mt_dilated_merge_ln_bwd(geom.ref(), _p(dy), _p(o_br), _p(lse_br), _p(gamma), _p(mean), _p(rstd),
-                                             _dt(o_br), _p(dattn), _p(delta_br), _stream())
+    rc = _lib.load().mt_dilated_merge_ln_bwd(geom.ref(), _p(dy), _dt(dy), _p(o_br), _p(lse_br), _p(gamma), _p(mean),
+                                             _p(rstd), _dt(o_br), _p(dattn), _p(delta_br), _stream())
     _check(rc, "mt_dilated_merge_ln_bwd")
     return dattn, delta_br
 
@@ -355,6 +355,42 @@ def gated_residual_bwd(dy, a, b, g32):
     return da, db, dgate
 
 
+class _tf32:
+    """Scoped TF32 for the adapter's skinny trainable GEMMs in bf16 mode (10-bit mantissa operands, fp32 storage)."""
+
+    def __enter__(self):
+        self.old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.old
+        return False
+
+
+class LinearTF32Fn(torch.autograd.Function):
+    """y = x w^T + b on fp32 tensors with TF32 tensor-core GEMMs in forward AND backward."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.has_b = b is not None
+        with _tf32():
+            return torch.nn.functional.linear(x, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        with _tf32():
+            dx = dy @ w if ctx.needs_input_grad[0] else None
+            dw = dy.t() @ x if ctx.needs_input_grad[1] else None
+        db = dy.sum(0) if ctx.has_b and ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
+def linear_tf32(x, w, b):
+    return LinearTF32Fn.apply(x, w, b)
+
+
 class GatedResidualFn(torch.autograd.Function):
     """y = a + gate * (a + b): the Injector tail ``query + gamma * (query + attn)`` (adapter_modules.py:231,362)."""
 
@@ -402,9 +438,9 @@ class FrozenLayerWeights:
             f = lambda p: p.detach().float().contiguous()
             self.w_qkv = torch.cat([d(sa.q_proj.weight), d(sa.k_proj.weight), d(sa.v_proj.weight)], 0).contiguous()
             self.b_qkv = torch.cat([d(sa.q_proj.bias), d(sa.k_proj.bias), d(sa.v_proj.bias)], 0).contiguous()
-            self.w_o, self.b_o = d(sa.out_proj.weight), d(sa.out_proj.bias)
-            self.w_1, self.b_1 = d(ffn.fc1.weight), d(ffn.fc1.bias)
-            self.w_2, self.b_2 = d(ffn.fc2.weight), d(ffn.fc2.bias)
+            self.w_o, self.b_o = d(sa.out_proj.weight), f(sa.out_proj.bias)
+            self.w_1, self.b_1 = d(ffn.fc1.weight), f(ffn.fc1.bias)
+            self.w_2, self.b_2 = d(ffn.fc2.weight), f(ffn.fc2.bias)
             self.ln1 = (f(layer.self_attn_layer_norm.weight), f(layer.self_attn_layer_norm.bias))
             self.ln2 = (f(layer.final_layer_norm.weight), f(layer.final_layer_norm.bias))
             self.ln_in = (f(sa.inner_attn_ln.weight), f(sa.inner_attn_ln.bias))
@@ -415,6 +451,20 @@ class FrozenLayerWeights:
 
 def _linear(x, w, b):
     return torch.nn.functional.linear(x, w, b)
+
+
+def _linear_f32out(x, w, b32):
+    """x @ w^T + b with 16-bit operands and an fp32 result (cuBLASLt bf16 x bf16 -> f32): every GEMM whose consumer is
+    an element-wise kernel keeps its fp32 accumulator instead of rounding the output to bf16."""
+    if x.dtype == torch.float32:
+        return torch.nn.functional.linear(x, w, b32)
+    return torch.addmm(b32, x, w.t(), out_dtype=torch.float32)
+
+
+def _matmul_f32out(a, b):
+    if a.dtype == torch.float32:
+        return torch.matmul(a, b)
+    return torch.mm(a, b, out_dtype=torch.float32)
 
 
 def _qkv_project(h1: torch.Tensor, W: FrozenLayerWeights, geom: Geometry) -> torch.Tensor:
@@ -435,16 +485,16 @@ def encoder_layer_forward(x: torch.Tensor, W: FrozenLayerWeights, geom: Geometry
     del h1
     o_br, lse_br = dilated_attn_fwd(geom, qkv, impl[0])
     a_ln, _, lse, mean_a, rstd_a = dilated_merge_ln_fwd(geom, o_br, lse_br, W.ln_in[0], W.ln_in[1])
-    attn_out = _linear(a_ln, W.w_o, W.b_o)
+    attn_out = _linear_f32out(a_ln, W.w_o, W.b_o)            # fp32 [N, 768]
     del a_ln
     x1, h2, mean2, rstd2 = add_layernorm_fwd(x, attn_out, W.ln2[0], W.ln2[1], cdt)
     del attn_out
-    f1 = _linear(h2, W.w_1, W.b_1)
+    f1 = _linear_f32out(h2, W.w_1, W.b_1)                    # fp32 [N, 3072], kept for the backward
     del h2
     g, mean_f, rstd_f = gelu_ln_fwd(f1, W.ln_ffn[0], W.ln_ffn[1], cdt)
-    f2 = _linear(g, W.w_2, W.b_2)
+    f2 = _linear_f32out(g, W.w_2, W.b_2)
     del g
-    y = x1 + f2 if f2.dtype == torch.float32 else torch.add(x1, f2)
+    y = f2.add_(x1)
     saved = (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f)
     return y, saved
 
@@ -455,20 +505,20 @@ def encoder_layer_backward(dy: torch.Tensor, saved, W: FrozenLayerWeights, geom:
     (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f) = saved
     dy = dy.contiguous()
     d_f2 = dy if cdt == torch.float32 else cast(dy, cdt)
-    dg = torch.matmul(d_f2, W.w_2)                                   # [N, 3072]
+    dg = _matmul_f32out(d_f2, W.w_2)                                 # fp32 [N, 3072]
     d_f1 = gelu_ln_bwd(dg, f1, W.ln_ffn[0], mean_f, rstd_f, cdt)
     del dg
-    dh2 = torch.matmul(d_f1, W.w_1)                                  # [N, 768]
+    dh2 = _matmul_f32out(d_f1, W.w_1)                                # fp32 [N, 768]
     del d_f1
     dx1, _, _ = layernorm_bwd(dh2, x1, W.ln2[0], mean2, rstd2, torch.float32, residual=dy)
     del dh2
     d_out = dx1 if cdt == torch.float32 else cast(dx1, cdt)
-    d_aln = torch.matmul(d_out, W.w_o)
+    d_aln = _matmul_f32out(d_out, W.w_o)                             # fp32 [N, 768]
     dattn, delta_br = dilated_merge_ln_bwd(geom, d_aln, o_br, lse_br, W.ln_in[0], mean_a, rstd_a)
     del d_aln
     dqkv = dilated_attn_bwd(geom, qkv, dattn, lse, delta_br, impl[1])   # fp32 [N, 2304]
     dqkv_c = dqkv if cdt == torch.float32 else cast(dqkv, cdt)
-    dh1 = torch.matmul(dqkv_c, W.w_qkv)
+    dh1 = _matmul_f32out(dqkv_c, W.w_qkv)
     dx, _, _ = layernorm_bwd(dh1, x, W.ln1[0], mean1, rstd1, torch.float32, residual=dx1)
     return dx
 

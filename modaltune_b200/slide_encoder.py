@@ -203,11 +203,18 @@ class LongNetViT(nn.Module):
             raise RuntimeError("the patch embedding is frozen and takes constant inputs on this path")
         outs = []
         with torch.no_grad():
-            wq = w.detach().to(cdt)
+            # fp32 operands; TF32 tensor-core GEMM in bf16 mode, exact fp32 in fp32 mode.  The token embedding feeds
+            # every later op: rounding it to bf16 costs more gradient accuracy than all bf16 GEMMs of the encoder
+            # together (DESIGN.md "numerics"), and the GEMM is 0.3% of the step's FLOPs.
+            wq = w.detach().float()
             bias = self.patch_embed.proj.bias.detach().float().contiguous()
             cls = self.cls_token.detach().reshape(-1).float().contiguous()
             for b in range(B):
-                proj = torch.matmul(x[b].to(cdt), wq.t())
+                if cdt == torch.float32:
+                    proj = torch.matmul(x[b].float(), wq.t())
+                else:
+                    with ops._tf32():
+                        proj = torch.matmul(x[b].float(), wq.t())
                 outs.append(ops.embed_assemble(proj, bias, coords[b].float().contiguous(), self.pos_table, cls,
                                                float(self.tile_size)))
         return outs[0].unsqueeze(0) if B == 1 else torch.stack(outs, 0)

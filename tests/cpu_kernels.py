@@ -155,7 +155,9 @@ def dilated_attn_bwd(geom, qkv, dattn, lse, delta_br, impl):
         torch.testing.assert_close(torch.logsumexp(L, 0), lse, rtol=1e-4, atol=1e-4)
         d3 = dattn.float().reshape(geom.n_tokens, geom.heads, geom.head_dim)
         want = _compact(geom, [(d3 * ob.detach()).sum(-1, keepdim=True) for ob in outs], 1)
-        torch.testing.assert_close(delta_br, want, rtol=2e-2, atol=2e-3)
+        loose = dattn.dtype != torch.float32  # bf16: delta was formed from the ROUNDED branch outputs
+        torch.testing.assert_close(delta_br, want, rtol=5e-2 if loose else 1e-3,
+                                   atol=(5e-2 if loose else 1e-4) * float(want.abs().max()))
         dq, dk, dv = torch.autograd.grad(out, [q, k, v], dattn.float())
     return torch.cat([dq.reshape(geom.n_tokens, -1), dk.reshape(geom.n_tokens, -1), dv.reshape(geom.n_tokens, -1)], 1)
 
