@@ -1,13 +1,388 @@
-// placeholder until the tcgen05 kernels land
+// LongNet dilated attention on the 5th-generation tensor cores (sm_100a): TMA-staged Q/K/V tiles, tcgen05 MMAs with
+// TMEM accumulators, online softmax in fp32.
+//
+// One CTA = one (branch, segment, head, 128-slot query tile); it streams the 128-slot key/value tiles of the same
+// (branch, segment, head).  The dilated gather of the reference (dilated_attention.py:22-37, 82-111) is the TMA box
+// itself: the qkv buffer [n_alloc, 3*768] is described per branch as a 3-D tensor (column, residue o, slot j) with
+// position = j * r + o, so a box of (64 columns, 1, 128 slots) IS the sparse tile of one head -- no sparse copy exists.
+// Rows >= n_tokens are zero in memory and rows >= n_alloc are zero-filled by TMA: these are the reference's zero
+// keys (score 0, value 0, counted in the softmax denominator).  Slots past the segment's own m = ceil(g / r) belong to
+// the next segment and are masked to -inf.
+//
+// head_dim = 48: the box is 64 columns wide (one 128-byte swizzle atom per row), the MMAs only consume K = 48 (three
+// k-steps of 16) for S = Q K^T and N = 48 for O = P V, so no tensor-core work is spent on the padding columns.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-5 = softmax (one query
+// row per thread = one TMEM lane).  P goes to shared memory in the K-major SWIZZLE_128B layout and is the A operand of
+// the P V MMA; each P V result lands in its own TMEM tile and is folded into fp32 register accumulators with the usual
+// online-softmax rescale, so TMEM is never read-modify-written.
+#include <cuda.h>
+
 #include "mt_common.cuh"
+#include "sm100_ptx.cuh"
+
 namespace mt {
-int dilated_attn_fwd_sm100(const mt_dilated_geometry*, const void*, int64_t, int64_t, void*, float*, cudaStream_t) {
-  set_error("tcgen05 forward not built yet");
-  return MT_E_UNSUPPORTED;
+using namespace sm100;
+
+static constexpr int DH = 48;            // head dim
+static constexpr int BT = 128;           // slots per tile (queries and keys)
+static constexpr int TILE_BYTES = BT * 128;  // [128 rows][128 B]: 64 bf16 columns per row, SWIZZLE_128B
+static constexpr int KV_STAGES = 2;
+static constexpr int FWD_THREADS = 192;
+static constexpr uint32_t TMEM_COLS = 256;  // S: [0,128)  O tiles: [128,192), [192,256)
+
+struct TensorMaps {
+  CUtensorMap m[MT_MAX_BRANCHES];
+};
+
+struct Sm100Params {
+  DilatedGeom geo;
+  int item_prefix[MT_MAX_BRANCHES + 1];  // first CTA of each launch-order branch
+  int order[MT_MAX_BRANCHES];            // launch order -> branch (longest key loops first)
+  int tiles[MT_MAX_BRANCHES];            // 128-slot tiles per (segment, head), indexed by branch
+  float scale_log2;                      // head_dim^-0.5 * log2(e)
+  float scale;
+};
+
+// smem carve-up (dynamic, base must be 1024-byte aligned)
+struct FwdSmem {
+  static constexpr int Q = 0;
+  static constexpr int K = Q + TILE_BYTES;
+  static constexpr int V = K + KV_STAGES * TILE_BYTES;
+  static constexpr int P = V + KV_STAGES * TILE_BYTES;          // two K-blocks of [128 rows][128 B]
+  static constexpr int BAR = P + 2 * TILE_BYTES;
+  // barriers (8 B each): q_full, kv_full[2], kv_empty[2], s_full, s_free, p_full, o_full[2]; then the TMEM pointer
+  static constexpr int NBAR = 10;
+  static constexpr int TMEM_PTR = BAR + NBAR * 8;
+  static constexpr int TOTAL = TMEM_PTR + 16;
+};
+
+__global__ void __launch_bounds__(FWD_THREADS, 2)
+dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Params P, __nv_bfloat16* __restrict__ o_br,
+                         float* __restrict__ lse_br, int* __restrict__ err_flag) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((sbase & 1023u) != 0) {  // SWIZZLE_128B tiles need 1024-byte alignment; never expected, but fail loudly
+    if (threadIdx.x == 0) atomicExch(err_flag, 1);
+    return;
+  }
+  // ---- which tile -------------------------------------------------------------------------------------------------
+  int oi = 0;
+  while (oi + 1 < P.geo.nb && (int)blockIdx.x >= P.item_prefix[oi + 1]) ++oi;
+  const int b = P.order[oi];
+  const BranchGeom bg = P.geo.b[b];
+  int local = blockIdx.x - P.item_prefix[oi];
+  const int qt = local % P.tiles[b];
+  local /= P.tiles[b];
+  const int h = local % P.geo.H;
+  const int s = local / P.geo.H;
+  const int H = P.geo.H, N = P.geo.N, E = H * DH;
+  const int off = (h * bg.r) / H;                    // residue of the positions this head owns
+  const int jseg = (s * bg.g) / bg.r;                // first slot of the segment in the branch's j axis
+  const int n_kv = P.tiles[b];
+  const int q0 = qt * BT;
+
+  const uint32_t bar_q_full = sbase + FwdSmem::BAR + 0;
+  const uint32_t bar_kv_full = sbase + FwdSmem::BAR + 8;    // [2]
+  const uint32_t bar_kv_empty = sbase + FwdSmem::BAR + 24;  // [2]
+  const uint32_t bar_s_full = sbase + FwdSmem::BAR + 40;
+  const uint32_t bar_s_free = sbase + FwdSmem::BAR + 48;
+  const uint32_t bar_p_full = sbase + FwdSmem::BAR + 56;
+  const uint32_t bar_o_full = sbase + FwdSmem::BAR + 64;    // [2]
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + FwdSmem::TMEM_PTR);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q_full, 1);
+    for (int i = 0; i < KV_STAGES; ++i) {
+      mbar_init(bar_kv_full + 8 * i, 1);
+      mbar_init(bar_kv_empty + 8 * i, 1);
+      mbar_init(bar_o_full + 8 * i, 1);
+    }
+    mbar_init(bar_s_full, 1);
+    mbar_init(bar_s_free, 128);
+    mbar_init(bar_p_full, 128);
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.m[b]);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32((const void*)tmem_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_s = tmem;
+  const uint32_t tmem_o = tmem + 128;
+
+  if (warp == 0) {
+    // ===== TMA producer ===============================================================================================
+    if (lane == 0) {
+      const void* map = &maps.m[b];
+      mbar_expect_tx(bar_q_full, TILE_BYTES);
+      tma_load_3d(sbase + FwdSmem::Q, map, bar_q_full, h * DH, off, jseg + q0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1, use = j >> 1;
+        mbar_wait(bar_kv_empty + 8 * st, (use & 1) ^ 1);
+        mbar_expect_tx(bar_kv_full + 8 * st, 2 * TILE_BYTES);
+        tma_load_3d(sbase + FwdSmem::K + st * TILE_BYTES, map, bar_kv_full + 8 * st, E + h * DH, off, jseg + j * BT);
+        tma_load_3d(sbase + FwdSmem::V + st * TILE_BYTES, map, bar_kv_full + 8 * st, 2 * E + h * DH, off, jseg + j * BT);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =================================================================================================
+    constexpr uint32_t IDESC_QK = umma_idesc_bf16(BT, BT, 0, 0);
+    constexpr uint32_t IDESC_PV = umma_idesc_bf16(BT, DH, 0, 1);
+    auto issue_qk = [&](int j) {  // S = Q K_j^T : three k-steps of 16 inside the 128-byte swizzle atom
+      if (lane == 0) {
+        const uint32_t ka = sbase + FwdSmem::K + (j & 1) * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_ss(tmem_s, umma_smem_desc(sbase + FwdSmem::Q + k * 32, 16, 1024), umma_smem_desc(ka + k * 32, 16, 1024),
+                  IDESC_QK, k > 0);
+        umma_commit(bar_s_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(bar_q_full, 0);
+    mbar_wait(bar_kv_full, 0);
+    tc_fence_after();
+    issue_qk(0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) {
+        mbar_wait(bar_kv_full + 8 * ((j + 1) & 1), ((j + 1) >> 1) & 1);
+        mbar_wait(bar_s_free, j & 1);  // the softmax threads have read S_j out of TMEM
+        tc_fence_after();
+        issue_qk(j + 1);
+      }
+      mbar_wait(bar_p_full, j & 1);    // P_j is in shared memory (and the O tile j&1 has been folded)
+      tc_fence_after();
+      if (lane == 0) {
+        // O_tile = P_j V_j : A = P (K-major, two 64-key blocks), B = V (MN-major: keys are the rows of the tile)
+        const uint32_t va = sbase + FwdSmem::V + (j & 1) * TILE_BYTES;
+        const uint32_t od = tmem_o + (j & 1) * 64;
+#pragma unroll
+        for (int k = 0; k < BT / 16; ++k) {
+          const uint32_t pa = sbase + FwdSmem::P + (k >> 2) * TILE_BYTES + (k & 3) * 32;
+          umma_ss(od, umma_smem_desc(pa, 16, 1024), umma_smem_desc(va + k * 16 * 128, TILE_BYTES, 1024), IDESC_PV, k > 0);
+        }
+        umma_commit(bar_kv_empty + 8 * (j & 1));
+        umma_commit(bar_o_full + 8 * (j & 1));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== softmax: one query row per thread ==========================================================================
+    const int lane_grp = warp & 3;                    // TMEM lanes this warp may touch: [32*lane_grp, +32)
+    const int row = lane_grp * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o_acc[DH];
+#pragma unroll
+    for (int i = 0; i < DH; ++i) o_acc[i] = 0.f;
+    uint8_t* p_row = smem + FwdSmem::P + row * 128;
+    const int sw = row & 7;
+
+    auto fold = [&](int j) {  // o_acc += O_tile(j)
+      mbar_wait(bar_o_full + 8 * (j & 1), (j >> 1) & 1);
+      tc_fence_after();
+      float t[16];
+#pragma unroll
+      for (int c = 0; c < DH / 16; ++c) {
+        tmem_ld16(tmem_o + t_lane + (j & 1) * 64 + c * 16, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] += t[i];
+      }
+    };
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int kvalid = bg.m - j * BT;  // key slots of this tile that belong to the segment (>= 1)
+      mbar_wait(bar_s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row maximum
+      float mx = -INFINITY;
+      float sv[32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld32(tmem_s + t_lane + c * 32, sv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < kvalid) ? sv[i] : -INFINITY);
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = ex2((m_run - m_new) * P.scale_log2);
+      if (j > 0) fold(j - 1);  // O tile j-1 is relative to m_run; P's buffer is free once that MMA has completed
+#pragma unroll
+      for (int i = 0; i < DH; ++i) o_acc[i] *= alpha;
+      l_run *= alpha;
+      m_run = m_new;
+      const float mb = m_new * P.scale_log2;
+      // pass 2: p = exp2(s * scale_log2 - mb), row sum, bf16 P into the swizzled K-major tile
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld32(tmem_s + t_lane + c * 32, sv);
+        tmem_ld_wait();
+        if (c == 3) {  // S_j is fully in registers: the MMA warp may overwrite it with S_{j+1}
+          tc_fence_before();
+          mbar_arrive(bar_s_free);
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = (c * 32 + i < kvalid) ? ex2(fmaf(sv[i], P.scale_log2, -mb)) : 0.f;
+          const float p1 = (c * 32 + i + 1 < kvalid) ? ex2(fmaf(sv[i + 1], P.scale_log2, -mb)) : 0.f;
+          rs += p0 + p1;
+          pk[i >> 1] = pack_bf16(p0, p1);
+        }
+        uint8_t* blk = p_row + (c >> 1) * TILE_BYTES;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (c & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(blk + ((chunk ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+      }
+      l_run += rs;
+      fence_proxy_async_smem();  // generic-proxy stores of P -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(bar_p_full);
+    }
+    fold(n_kv - 1);
+    // ---- epilogue: normalise and write the compact per-branch output ---------------------------------------------
+    const int slot = q0 + row;
+    const int pos = s * bg.g + off + slot * bg.r;
+    const int seg_end = min(N, (s + 1) * bg.g);
+    if (slot < bg.m && pos < seg_end) {
+      const float inv = 1.f / l_run;
+      const int slot_h = h - off * bg.hpb;
+      __nv_bfloat16* dst = o_br + bg.o_off + ((int64_t)pos * bg.hpb + slot_h) * DH;
+#pragma unroll
+      for (int c = 0; c < DH / 8; ++c) {
+        uint4 u;
+        u.x = pack_bf16(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
+        u.y = pack_bf16(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
+        u.z = pack_bf16(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv);
+        u.w = pack_bf16(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + c * 8) = u;
+      }
+      lse_br[bg.lse_off + (int64_t)pos * bg.hpb + slot_h] = m_run * P.scale + logf(l_run);
+    }
+  }
+  // ---- teardown ------------------------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 3-D view of a row-major [n_alloc, ld] bf16 matrix for dilation r: (column, residue o, slot j) -> row j*r + o
+static int encode_branch_map(CUtensorMap* map, const void* base, int64_t ld, int64_t n_alloc, int r) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return MT_E_UNSUPPORTED;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)r, (cuuint64_t)(n_alloc / r)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)r};
+  cuuint32_t box[3] = {64, 1, (cuuint32_t)BT};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for dilation %d, ld %lld, rows %lld", (int)rc, r, (long long)ld,
+              (long long)n_alloc);
+    return MT_E_BADARG;
+  }
+  return 0;
+}
+
+static int make_sm100_params(const mt_dilated_geometry* geom, Sm100Params* P) {
+  int rc = make_dilated_geom(geom, &P->geo);
+  if (rc) return rc;
+  if (P->geo.D != DH || P->geo.H != 16) {
+    set_error("tcgen05 dilated attention is built for 16 heads x 48 (got %d x %d)", P->geo.H, P->geo.D);
+    return MT_E_UNSUPPORTED;
+  }
+  const int nb = P->geo.nb;
+  for (int b = 0; b < nb; ++b) {
+    P->tiles[b] = (P->geo.b[b].m + BT - 1) / BT;
+    P->order[b] = b;
+  }
+  for (int i = 0; i < nb; ++i)  // longest key loops first
+    for (int j = i + 1; j < nb; ++j)
+      if (P->tiles[P->order[j]] > P->tiles[P->order[i]]) {
+        int t = P->order[i];
+        P->order[i] = P->order[j];
+        P->order[j] = t;
+      }
+  int total = 0;
+  for (int i = 0; i < nb; ++i) {
+    const int b = P->order[i];
+    P->item_prefix[i] = total;
+    total += P->geo.b[b].n_seg * P->geo.H * P->tiles[b];
+  }
+  P->item_prefix[nb] = total;
+  P->scale = 1.0f / sqrtf((float)DH);
+  P->scale_log2 = P->scale * 1.4426950408889634f;
+  return 0;
+}
+
+static int* error_flag() {  // one device word, allocated once (reported through the return code of the next call)
+  static int* flag = nullptr;
+  if (flag == nullptr) {
+    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flag, 0, sizeof(int));
+  }
+  return flag;
+}
+
+int dilated_attn_fwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,
+                           void* o_br, float* lse_br, cudaStream_t st) {
+  Sm100Params P;
+  int rc = make_sm100_params(geom, &P);
+  if (rc) return rc;
+  MT_REQUIRE(n_alloc >= P.geo.N && n_alloc % 128 == 0, "dilated_attn_fwd: n_alloc must be a multiple of 128 >= n_tokens");
+  MT_REQUIRE(qkv_ld % 8 == 0 && ((uintptr_t)qkv & 15) == 0, "dilated_attn_fwd: qkv must be 16-byte aligned");
+  TensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int b = 0; b < P.geo.nb; ++b) {
+    rc = encode_branch_map(&maps.m[b], qkv, qkv_ld, n_alloc, P.geo.b[b].r);
+    if (rc) return rc;
+  }
+  int* flag = error_flag();
+  MT_REQUIRE(flag != nullptr, "dilated_attn_fwd: cannot allocate the error flag");
+  MT_CUDA(cudaFuncSetAttribute(dilated_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
+  dilated_fwd_sm100_kernel<<<P.item_prefix[P.geo.nb], FWD_THREADS, FwdSmem::TOTAL, st>>>(
+      maps, P, (__nv_bfloat16*)o_br, lse_br, flag);
+  return check_launch("dilated_fwd_sm100_kernel");
+}
+
 int dilated_attn_bwd_sm100(const mt_dilated_geometry*, const void*, int64_t, int64_t, const void*, const float*,
                            const float*, float*, cudaStream_t) {
   set_error("tcgen05 backward not built yet");
   return MT_E_UNSUPPORTED;
 }
+
 }  // namespace mt

@@ -177,3 +177,26 @@ def test_dilated_attention_linearity_in_v_at_full_size():
     # rows whose branches contain zero-padded slots see value 0 there: output <= 0.75, and == 0.75 where no padding
     a3 = attn(q3)
     assert float(a3.max()) <= 0.75 + 1e-5 and float(a3.min()) > 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tcgen05 / TMA dilated attention (impl = 1) against the fp32-math SIMT kernels and the oracle
+# ---------------------------------------------------------------------------------------------------------------------
+SM100_GEOMS = GEOMS + [(5793, None), (10001, None), (300, [128, 256, 512, 1024, 2048])]
+
+
+@pytest.mark.parametrize("N,sl", SM100_GEOMS)
+def test_dilated_attention_tcgen05_forward(N, sl):
+    sl = sl or optimal_segment_lengths()
+    geom = ops.Geometry.get(N, sl, DILATED_RATIO)
+    g = torch.Generator().manual_seed(N + 1)
+    qkv = _qkv(N, geom.n_alloc, g, torch.bfloat16, 1.5).to(DEV)
+    o_s, l_s = ops.dilated_attn_fwd(geom, qkv, 0)
+    o_t, l_t = ops.dilated_attn_fwd(geom, qkv, 1)
+    torch.cuda.synchronize()
+    assert rel(l_t, l_s) < 2e-3, rel(l_t, l_s)       # P is rounded to bf16 before P V; lse itself is fp32
+    assert float((l_t - l_s).abs().max()) < 2e-2
+    assert rel(o_t, o_s) < 3e-2, rel(o_t, o_s)
+    if N <= 2049:
+        o_c, l_c = C.dilated_attn_fwd(geom, qkv.cpu(), 0)
+        assert rel(l_t, l_c) < 2e-3 and rel(o_t, o_c) < 3e-2
