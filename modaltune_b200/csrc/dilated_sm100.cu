@@ -379,10 +379,299 @@ int dilated_attn_fwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int
   return check_launch("dilated_fwd_sm100_kernel");
 }
 
-int dilated_attn_bwd_sm100(const mt_dilated_geometry*, const void*, int64_t, int64_t, const void*, const float*,
-                           const float*, float*, cudaStream_t) {
-  set_error("tcgen05 backward not built yet");
-  return MT_E_UNSUPPORTED;
+// =====================================================================================================================
+// backward
+// =====================================================================================================================
+// One CTA = one (branch, segment, head, 128-slot KEY tile); it streams the 128-slot query tiles of the same
+// (branch, segment, head).  Per (query tile i, key tile j):
+//     S  = Q_i K_j^T                  dP = dO_i V_j^T                      (tcgen05, K = 48, into TMEM)
+//     P  = exp(S * scale - lse_i)     dS = P * (dP - delta_i) * scale      (fp32, 512 threads, bf16 into smem)
+//     dV_j += P^T dO_i                dK_j += dS^T Q_i                     (tcgen05, accumulate in TMEM over i)
+//     dQ_i  = dS K_j                                                        (tcgen05, fresh TMEM tile, then
+//                                                                            red.global.add.v4.f32 into dqkv)
+// lse is the MERGED log-sum-exp over the branches and delta_i = dO_i . o_b,i the per-branch row dot: with them
+// P = w_b p_b and the formula above is the reference's backward with detached merge weights.
+// P and dS are stored once as [query][key] swizzled tiles and consumed both as K-major A (dQ) and as MN-major A
+// (P^T, dS^T); Q, dO, K are consumed in place as MN-major B operands where the contraction runs over tile rows.
+static constexpr int BWD_COMPUTE_WARPS = 16;
+static constexpr int BWD_THREADS = 64 + 32 * BWD_COMPUTE_WARPS;  // 576
+static constexpr uint32_t BWD_TMEM_COLS = 512;  // S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448) [448,512)
+
+struct BwdSmem {
+  static constexpr int K = 0;
+  static constexpr int V = K + TILE_BYTES;
+  static constexpr int Q = V + TILE_BYTES;                 // [2]
+  static constexpr int DO = Q + 2 * TILE_BYTES;            // [2]
+  static constexpr int P = DO + 2 * TILE_BYTES;            // two 64-key blocks
+  static constexpr int DS = P + 2 * TILE_BYTES;
+  static constexpr int BAR = DS + 2 * TILE_BYTES;
+  // kv_full, qdo_full[2], qdo_empty[2], s_full, s_free, pds_full, dq_full[2], dq_free[2]
+  static constexpr int NBAR = 12;
+  static constexpr int TMEM_PTR = BAR + NBAR * 8;
+  static constexpr int TOTAL = TMEM_PTR + 16;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+dilated_bwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ TensorMaps do_maps,
+                         const Sm100Params P, const float* __restrict__ lse, const float* __restrict__ delta_br,
+                         float* __restrict__ dqkv, int* __restrict__ err_flag) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((sbase & 1023u) != 0) {
+    if (threadIdx.x == 0) atomicExch(err_flag, 1);
+    return;
+  }
+  int oi = 0;
+  while (oi + 1 < P.geo.nb && (int)blockIdx.x >= P.item_prefix[oi + 1]) ++oi;
+  const int b = P.order[oi];
+  const BranchGeom bg = P.geo.b[b];
+  int local = blockIdx.x - P.item_prefix[oi];
+  const int kt = local % P.tiles[b];
+  local /= P.tiles[b];
+  const int h = local % P.geo.H;
+  const int s = local / P.geo.H;
+  const int H = P.geo.H, N = P.geo.N, E = H * DH;
+  const int off = (h * bg.r) / H;
+  const int jseg = (s * bg.g) / bg.r;
+  const int n_q = P.tiles[b];
+  const int k0 = kt * BT;
+  const int seg_end = min(N, (s + 1) * bg.g);
+  const int slot_h = h - off * bg.hpb;
+
+  const uint32_t bar_kv_full = sbase + BwdSmem::BAR + 0;
+  const uint32_t bar_qdo_full = sbase + BwdSmem::BAR + 8;    // [2]
+  const uint32_t bar_qdo_empty = sbase + BwdSmem::BAR + 24;  // [2]
+  const uint32_t bar_s_full = sbase + BwdSmem::BAR + 40;
+  const uint32_t bar_s_free = sbase + BwdSmem::BAR + 48;
+  const uint32_t bar_pds_full = sbase + BwdSmem::BAR + 56;
+  const uint32_t bar_dq_full = sbase + BwdSmem::BAR + 64;    // [2]
+  const uint32_t bar_dq_free = sbase + BwdSmem::BAR + 80;    // [2]
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + BwdSmem::TMEM_PTR);
+  constexpr int NCOMP = 32 * BWD_COMPUTE_WARPS;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_qdo_full + 8 * i, 1);
+      mbar_init(bar_qdo_empty + 8 * i, 1);
+      mbar_init(bar_dq_full + 8 * i, 1);
+      mbar_init(bar_dq_free + 8 * i, NCOMP);
+    }
+    mbar_init(bar_s_full, 1);
+    mbar_init(bar_s_free, NCOMP);
+    mbar_init(bar_pds_full, NCOMP);
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.m[b]);
+    tma_prefetch_desc(&do_maps.m[b]);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32((const void*)tmem_slot), BWD_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tm_s = tmem, tm_dp = tmem + 128, tm_dv = tmem + 256, tm_dk = tmem + 320, tm_dq = tmem + 384;
+
+  if (warp == 0) {
+    // ===== TMA producer ===============================================================================================
+    if (lane == 0) {
+      const void* map = &maps.m[b];
+      const void* dmap = &do_maps.m[b];
+      mbar_expect_tx(bar_kv_full, 2 * TILE_BYTES);
+      tma_load_3d(sbase + BwdSmem::K, map, bar_kv_full, E + h * DH, off, jseg + k0);
+      tma_load_3d(sbase + BwdSmem::V, map, bar_kv_full, 2 * E + h * DH, off, jseg + k0);
+      for (int i = 0; i < n_q; ++i) {
+        const int st = i & 1, use = i >> 1;
+        mbar_wait(bar_qdo_empty + 8 * st, (use & 1) ^ 1);
+        mbar_expect_tx(bar_qdo_full + 8 * st, 2 * TILE_BYTES);
+        tma_load_3d(sbase + BwdSmem::Q + st * TILE_BYTES, map, bar_qdo_full + 8 * st, h * DH, off, jseg + i * BT);
+        tma_load_3d(sbase + BwdSmem::DO + st * TILE_BYTES, dmap, bar_qdo_full + 8 * st, h * DH, off, jseg + i * BT);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =================================================================================================
+    constexpr uint32_t IDESC_S = umma_idesc_bf16(BT, BT, 0, 0);     // A K-major, B K-major
+    constexpr uint32_t IDESC_T = umma_idesc_bf16(BT, DH, 1, 1);     // A MN-major (P^T, dS^T), B MN-major (dO, Q)
+    constexpr uint32_t IDESC_DQ = umma_idesc_bf16(BT, DH, 0, 1);    // A K-major (dS), B MN-major (K)
+    const uint32_t sK = sbase + BwdSmem::K, sV = sbase + BwdSmem::V, sP = sbase + BwdSmem::P, sDS = sbase + BwdSmem::DS;
+    auto issue_s_dp = [&](int i) {
+      if (lane == 0) {
+        const uint32_t q = sbase + BwdSmem::Q + (i & 1) * TILE_BYTES, g = sbase + BwdSmem::DO + (i & 1) * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_ss(tm_s, umma_smem_desc(q + k * 32, 16, 1024), umma_smem_desc(sK + k * 32, 16, 1024), IDESC_S, k > 0);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_ss(tm_dp, umma_smem_desc(g + k * 32, 16, 1024), umma_smem_desc(sV + k * 32, 16, 1024), IDESC_S, k > 0);
+        umma_commit(bar_s_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(bar_kv_full, 0);
+    mbar_wait(bar_qdo_full, 0);
+    tc_fence_after();
+    issue_s_dp(0);
+    for (int i = 0; i < n_q; ++i) {
+      mbar_wait(bar_s_free, i & 1);  // S_i / dP_i are in registers
+      if (i + 1 < n_q) {
+        mbar_wait(bar_qdo_full + 8 * ((i + 1) & 1), ((i + 1) >> 1) & 1);
+        tc_fence_after();
+        issue_s_dp(i + 1);
+      }
+      mbar_wait(bar_pds_full, i & 1);  // P_i, dS_i are in shared memory
+      if (i >= 2) mbar_wait(bar_dq_free + 8 * (i & 1), ((i - 2) >> 1) & 1);  // dQ tile i&1 has been drained
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t q = sbase + BwdSmem::Q + (i & 1) * TILE_BYTES, g = sbase + BwdSmem::DO + (i & 1) * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BT / 16; ++k)  // contraction over the 128 queries (tile rows): 16 rows = 2048 B per step
+          umma_ss(tm_dv, umma_smem_desc(sP + k * 2048, TILE_BYTES, 1024), umma_smem_desc(g + k * 2048, TILE_BYTES, 1024),
+                  IDESC_T, (i > 0) || (k > 0));
+#pragma unroll
+        for (int k = 0; k < BT / 16; ++k)
+          umma_ss(tm_dk, umma_smem_desc(sDS + k * 2048, TILE_BYTES, 1024), umma_smem_desc(q + k * 2048, TILE_BYTES, 1024),
+                  IDESC_T, (i > 0) || (k > 0));
+#pragma unroll
+        for (int k = 0; k < BT / 16; ++k)  // contraction over the 128 keys: dS K-major (two 64-key blocks)
+          umma_ss(tm_dq + (i & 1) * 64, umma_smem_desc(sDS + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
+                  umma_smem_desc(sK + k * 2048, TILE_BYTES, 1024), IDESC_DQ, k > 0);
+        umma_commit(bar_qdo_empty + 8 * (i & 1));
+        umma_commit(bar_dq_full + 8 * (i & 1));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== compute: thread = (query row, 32-key quarter) ===============================================================
+    const int cw = warp - 2;
+    const int lane_grp = warp & 3;               // TMEM lanes of this warp
+    const int quarter = cw >> 2;                 // key columns [32*quarter, +32)
+    const int row = lane_grp * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
+    const int sw = row & 7;
+    const int kvalid = bg.m - k0;
+    const float LOG2E = 1.4426950408889634f;
+    uint8_t* p_row = smem + BwdSmem::P + (quarter >> 1) * TILE_BYTES + row * 128;
+    uint8_t* ds_row = smem + BwdSmem::DS + (quarter >> 1) * TILE_BYTES + row * 128;
+
+    auto drain_dq = [&](int i) {  // dQ tile of pair i -> global (this thread: 12 columns of its row)
+      mbar_wait(bar_dq_full + 8 * (i & 1), (i >> 1) & 1);
+      tc_fence_after();
+      float v[3][4];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tmem_ld4(tm_dq + t_lane + (i & 1) * 64 + quarter * 12 + c * 4, v[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_dq_free + 8 * (i & 1));
+      const int slot = i * BT + row;
+      const int pos = s * bg.g + off + slot * bg.r;
+      if (slot < bg.m && pos < seg_end) {
+        float* dst = dqkv + (int64_t)pos * (3 * E) + h * DH + quarter * 12;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) red_add_v4(dst + c * 4, v[c][0], v[c][1], v[c][2], v[c][3]);
+      }
+    };
+
+    for (int i = 0; i < n_q; ++i) {
+      // per-row statistics of this query tile
+      const int slot = i * BT + row;
+      const int pos = s * bg.g + off + slot * bg.r;
+      const bool qok = slot < bg.m && pos < seg_end;
+      const float l2 = qok ? lse[(int64_t)pos * H + h] * LOG2E : INFINITY;
+      const float de = qok ? delta_br[bg.lse_off + (int64_t)pos * bg.hpb + slot_h] : 0.f;
+      mbar_wait(bar_s_full, i & 1);
+      tc_fence_after();
+      float sv[32], dp[32];
+      tmem_ld32(tm_s + t_lane + quarter * 32, sv);
+      tmem_ld32(tm_dp + t_lane + quarter * 32, dp);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_s_free);
+      uint32_t pk[16], dk[16];
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        const bool v0 = quarter * 32 + c < kvalid, v1 = quarter * 32 + c + 1 < kvalid;
+        const float p0 = v0 ? ex2(fmaf(sv[c], P.scale_log2, -l2)) : 0.f;
+        const float p1 = v1 ? ex2(fmaf(sv[c + 1], P.scale_log2, -l2)) : 0.f;
+        pk[c >> 1] = pack_bf16(p0, p1);
+        dk[c >> 1] = pack_bf16(p0 * (dp[c] - de) * P.scale, p1 * (dp[c + 1] - de) * P.scale);
+      }
+      // P / dS buffers are free once the MMAs of pair i-1 have completed (that is what dq_full(i-1) tracks)
+      if (i > 0) mbar_wait(bar_dq_full + 8 * ((i - 1) & 1), ((i - 1) >> 1) & 1);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int chunk = (((quarter & 1) * 4 + q) ^ sw) << 4;
+        *reinterpret_cast<uint4*>(p_row + chunk) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        *reinterpret_cast<uint4*>(ds_row + chunk) = make_uint4(dk[4 * q], dk[4 * q + 1], dk[4 * q + 2], dk[4 * q + 3]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_pds_full);
+      if (i > 0) drain_dq(i - 1);
+    }
+    drain_dq(n_q - 1);
+    // ---- dK / dV of this key tile: the last dq_full also covers the last dV / dK MMAs ---------------------------------
+    {
+      float a[3][4], c2[3][4];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        tmem_ld4(tm_dk + t_lane + quarter * 12 + c * 4, a[c]);
+        tmem_ld4(tm_dv + t_lane + quarter * 12 + c * 4, c2[c]);
+      }
+      tmem_ld_wait();
+      const int slot = k0 + row;
+      const int pos = s * bg.g + off + slot * bg.r;
+      if (slot < bg.m && pos < seg_end) {
+        float* dst = dqkv + (int64_t)pos * (3 * E) + E + h * DH + quarter * 12;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          red_add_v4(dst + c * 4, a[c][0], a[c][1], a[c][2], a[c][3]);
+          red_add_v4(dst + E + c * 4, c2[c][0], c2[c][1], c2[c][2], c2[c][3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, BWD_TMEM_COLS);
+}
+
+int dilated_attn_bwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,
+                           const void* dattn, const float* lse, const float* delta_br, float* dqkv, cudaStream_t st) {
+  Sm100Params P;
+  int rc = make_sm100_params(geom, &P);
+  if (rc) return rc;
+  MT_REQUIRE(n_alloc >= P.geo.N && n_alloc % 128 == 0, "dilated_attn_bwd: n_alloc must be a multiple of 128 >= n_tokens");
+  MT_REQUIRE(qkv_ld % 8 == 0 && ((uintptr_t)qkv & 15) == 0 && ((uintptr_t)dattn & 15) == 0 && ((uintptr_t)dqkv & 15) == 0,
+             "dilated_attn_bwd: buffers must be 16-byte aligned");
+  TensorMaps maps, do_maps;
+  memset(&maps, 0, sizeof(maps));
+  memset(&do_maps, 0, sizeof(do_maps));
+  const int64_t E = (int64_t)P.geo.H * DH;
+  for (int b = 0; b < P.geo.nb; ++b) {
+    rc = encode_branch_map(&maps.m[b], qkv, qkv_ld, n_alloc, P.geo.b[b].r);
+    if (rc) return rc;
+    rc = encode_branch_map(&do_maps.m[b], dattn, E, n_alloc, P.geo.b[b].r);  // dattn: [n_alloc, 768], zero tail rows
+    if (rc) return rc;
+  }
+  int* flag = error_flag();
+  MT_REQUIRE(flag != nullptr, "dilated_attn_bwd: cannot allocate the error flag");
+  MT_CUDA(cudaFuncSetAttribute(dilated_bwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL));
+  dilated_bwd_sm100_kernel<<<P.item_prefix[P.geo.nb], BWD_THREADS, BwdSmem::TOTAL, st>>>(maps, do_maps, P, lse, delta_br,
+                                                                                       dqkv, flag);
+  return check_launch("dilated_bwd_sm100_kernel");
 }
 
 }  // namespace mt

@@ -218,7 +218,10 @@ def dilated_merge_ln_fwd(geom: Geometry, o_br, lse_br, gamma, beta, eps: float =
 
 def dilated_merge_ln_bwd(geom: Geometry, dy, o_br, lse_br, gamma, mean, rstd):
     N, E = geom.n_tokens, geom.heads * geom.head_dim
-    dattn = torch.empty((N, E), device=o_br.device, dtype=o_br.dtype)
+    # n_alloc rows with a zero tail: the tcgen05 backward reads dO tiles through TMA like the qkv buffer
+    dattn = torch.empty((geom.n_alloc, E), device=o_br.device, dtype=o_br.dtype)
+    if geom.n_alloc > N:
+        dattn[N:].zero_()
     delta_br = torch.empty(geom.lse_elems, device=o_br.device, dtype=torch.float32)
     rc = _lib.load().mt_dilated_merge_ln_bwd(geom.ref(), _p(dy), _dt(dy), _p(o_br), _p(lse_br), _p(gamma), _p(mean),
                                              _p(rstd), _dt(o_br), _p(dattn), _p(delta_br), _stream())
@@ -227,7 +230,9 @@ def dilated_merge_ln_bwd(geom: Geometry, dy, o_br, lse_br, gamma, mean, rstd):
 
 
 def dilated_attn_bwd(geom: Geometry, qkv, dattn, lse, delta_br, impl: int):
+    """dattn [n_alloc, E] (rows >= N zero), merged lse [N, H], per-branch delta -> dqkv fp32 [N, 3E]."""
     N, E = geom.n_tokens, geom.heads * geom.head_dim
+    assert dattn.shape[0] == geom.n_alloc, "dattn must have n_alloc rows (zero tail), see dilated_merge_ln_bwd"
     dqkv = torch.empty((N, 3 * E), device=qkv.device, dtype=torch.float32)
     with _timed("dilated_attn_bwd"):
         rc = _lib.load().mt_dilated_attn_bwd(geom.ref(), _p(qkv), qkv.stride(0), qkv.shape[0], _p(dattn), _p(lse),

@@ -143,7 +143,9 @@ def dilated_merge_ln_bwd(geom, dy, o_br, lse_br, gamma, mean, rstd):
     dattn = dattn.to(o_br.dtype)
     d3 = dattn.float().reshape(geom.n_tokens, geom.heads, geom.head_dim)
     delta = [(d3 * ob).sum(-1, keepdim=True) for ob in outs]
-    return dattn, _compact(geom, delta, 1)
+    padded = torch.zeros(geom.n_alloc, dattn.shape[1], dtype=dattn.dtype)
+    padded[:geom.n_tokens] = dattn
+    return padded, _compact(geom, delta, 1)
 
 
 def dilated_attn_bwd(geom, qkv, dattn, lse, delta_br, impl):
@@ -153,6 +155,7 @@ def dilated_attn_bwd(geom, qkv, dattn, lse, delta_br, impl):
         # the plumbing the real kernel depends on: merged lse and per-branch delta handed in by the caller
         L = torch.stack(lses, 0)
         torch.testing.assert_close(torch.logsumexp(L, 0), lse, rtol=1e-4, atol=1e-4)
+        dattn = dattn[:geom.n_tokens]
         d3 = dattn.float().reshape(geom.n_tokens, geom.heads, geom.head_dim)
         want = _compact(geom, [(d3 * ob.detach()).sum(-1, keepdim=True) for ob in outs], 1)
         loose = dattn.dtype != torch.float32  # bf16: delta was formed from the ROUNDED branch outputs

@@ -148,6 +148,7 @@ def test_dilated_attention_simt_vs_oracle(N, sl, dt):
     assert rel(a, a_c) < tol(dt) and rel(lse, lse_c) < 1e-5 and rel(y, y_c) < 2 * tol(dt)
     da_c, de_c = C.dilated_merge_ln_bwd(geom, dy, o_c, l_c, gamma, m_c, r_c)
     da, de = ops.dilated_merge_ln_bwd(geom, dy.to(DEV), o, l, gamma.to(DEV), m, r)
+    assert da.shape[0] == geom.n_alloc and float(da[N:].abs().sum()) == 0.0
     assert rel(da, da_c) < 2 * tol(dt) and rel(de, de_c) < 2 * tol(dt)
     dq_c = C.dilated_attn_bwd(geom, qkv, da_c, lse_c, de_c, 0)
     dq = ops.dilated_attn_bwd(geom, qkv.to(DEV), da_c.to(DEV), lse_c.to(DEV), de_c.to(DEV), 0)
@@ -200,3 +201,22 @@ def test_dilated_attention_tcgen05_forward(N, sl):
     if N <= 2049:
         o_c, l_c = C.dilated_attn_fwd(geom, qkv.cpu(), 0)
         assert rel(l_t, l_c) < 2e-3 and rel(o_t, o_c) < 3e-2
+
+
+@pytest.mark.parametrize("N,sl", SM100_GEOMS)
+def test_dilated_attention_tcgen05_backward(N, sl):
+    sl = sl or optimal_segment_lengths()
+    geom = ops.Geometry.get(N, sl, DILATED_RATIO)
+    g = torch.Generator().manual_seed(N + 2)
+    qkv = _qkv(N, geom.n_alloc, g, torch.bfloat16, 1.5).to(DEV)
+    gamma, beta = (1 + 0.1 * torch.randn(768, generator=g)).to(DEV), (0.1 * torch.randn(768, generator=g)).to(DEV)
+    dy = torch.randn(N, 768, generator=g).to(DEV)
+    o, l = ops.dilated_attn_fwd(geom, qkv, 0)
+    y, _, lse, m, r = ops.dilated_merge_ln_fwd(geom, o, l, gamma, beta)
+    dattn, delta = ops.dilated_merge_ln_bwd(geom, dy, o, l, gamma, m, r)
+    dq_s = ops.dilated_attn_bwd(geom, qkv, dattn, lse, delta, 0)
+    dq_t = ops.dilated_attn_bwd(geom, qkv, dattn, lse, delta, 1)
+    torch.cuda.synchronize()
+    for name, sl_ in (("dq", slice(0, 768)), ("dk", slice(768, 1536)), ("dv", slice(1536, 2304))):
+        e = rel(dq_t[:, sl_], dq_s[:, sl_])
+        assert e < 3e-2, (name, e)
