@@ -40,7 +40,7 @@ def compute_dtype() -> torch.dtype:
 
 
 # what "auto" resolves to in bf16 mode, per direction (flipped to 1 as the tcgen05 kernels are validated on B200)
-AUTO_IMPL = {"fwd": 0, "bwd": 0}
+AUTO_IMPL = {"fwd": 1, "bwd": 1}
 
 
 def attn_impl(direction: str = "fwd") -> int:
