@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--attn", default="auto", choices=["auto", "simt", "sm100"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -165,24 +166,6 @@ class Clocks:
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
-def pack_host_slide(slide):
-    """Pinned host staging of one case: the 331 pathway vectors are packed into one buffer (one H2D copy, not 331)."""
-    sizes = [slide["genes"][i].shape[1] for i in range(len(slide["genes"]))]
-    genes = torch.cat([slide["genes"][i].reshape(-1) for i in range(len(sizes))])
-    host = {"x": slide["x"], "coords": slide["coords"], "genes_flat": genes, "clinical": slide["clinical"],
-            "text": slide["text"]}
-    host = {k: v.contiguous().pin_memory() for k, v in host.items()}
-    nbytes = sum(v.numel() * v.element_size() for v in host.values())
-    return host, sizes, nbytes
-
-
-def host_to_device(host, sizes, dev):
-    d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-    parts = torch.split(d.pop("genes_flat"), sizes)
-    d["genes"] = {i: p.unsqueeze(0) for i, p in enumerate(parts)}
-    return d
-
-
 def main():
     args = parse()
     if args.impl == "reference":
@@ -209,16 +192,20 @@ def main():
     proj = helpers.build_projector(0, dev)
     flat = train_step.FlatGradAllReduce([p for p in model.parameters() if p.requires_grad])
     n_slides = 2
-    hosts = [pack_host_slide(synthetic.synthetic_slide(args.tiles, seed=1000 + rank * 100 + i)) for i in range(n_slides)]
-    resident = [host_to_device(h, s, dev) for h, s, _ in hosts]
-    h2d_bytes = hosts[0][2]
+    hosts = [train_step.pack_host_slide(synthetic.synthetic_slide(args.tiles, seed=1000 + rank * 100 + i))
+             for i in range(n_slides)]
+    sizes, h2d_bytes = hosts[0][1], hosts[0][2]
+    resident = [{k: v.to(dev) for k, v in h.items()} for h, _, _ in hosts]
     geom = ops.Geometry.get(args.tiles + 1, model.segment_lengths, (1, 2, 4, 8, 16))
 
-    def step(slide):
+    def eager_step(packed):
         flat.zero()
-        loss, logits = train_step.forward_backward(model, proj, slide)
+        loss, logits = train_step.forward_backward(model, proj, train_step.unpack_slide(packed, sizes))
         flat.all_reduce()
         return loss, logits
+
+    graphed = None if args.no_graph else train_step.GraphedStep(model, proj, resident[0], sizes, flat)
+    step = eager_step if graphed is None else graphed
 
     def barrier():
         if world > 1:
@@ -243,29 +230,36 @@ def main():
         step(resident[i % n_slides])
     torch.cuda.synchronize()
 
-    # ---- device-resident timed region --------------------------------------------------------------------------------
+    # ---- device-resident timed region (inputs already in HBM; every step takes the other slide) -----------------------
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
-    ops.kernel_events = {}
     launches0 = ops.launch_count
     ms = timed(lambda i: step(resident[i % n_slides]), args.steps)
-    launches = ops.launch_count - launches0
-    events, ops.kernel_events = ops.kernel_events, None
     value = world * args.steps / (ms / 1e3)
 
     # ---- end to end: pinned host -> device, step, loss/logits back to the host ---------------------------------------
     out = {}
 
     def e2e_step(i):
-        h, s, _ = hosts[i % n_slides]
-        loss, logits = step(host_to_device(h, s, dev))
+        h = hosts[i % n_slides][0]
+        if graphed is None:
+            loss, logits = eager_step({k: v.to(dev, non_blocking=True) for k, v in h.items()})
+        else:
+            loss, logits = graphed(h)
         out["loss"], out["logits"] = float(loss), logits.float().cpu()   # D2H reads (synchronising, like loss.item())
 
     e2e_step(0)
     ms_e2e = timed(e2e_step, args.steps)
-    clk = clocks.stop() if rank == 0 else None
     e2e_value = world * args.steps / (ms_e2e / 1e3)
+
+    # ---- per-kernel timing + launch count: the same step issued eagerly with CUDA events around the attention kernels -
+    ops.kernel_events = {}
+    launches0 = ops.launch_count
+    ms_eager = timed(lambda i: eager_step(resident[i % n_slides]), args.steps)
+    launches = (ops.launch_count - launches0) // args.steps
+    events, ops.kernel_events = ops.kernel_events, None
+    clk = clocks.stop() if rank == 0 else None
 
     if rank != 0:
         if world > 1:
@@ -293,10 +287,11 @@ def main():
         "bound": "tensor", "kernel": f"dilated_attn_bwd[{impl_names[config.attn_impl('bwd')]}]", "achieved": ach_bwd,
         "peak": peak, "peak_source": peak_src, "unit": "TFLOP/s", "frac": ach_bwd / peak, "traffic": None,
         "launch_ms": t_bwd, "launches_timed": n_bwd, "algorithmic_gflop_per_launch": f_bwd / 1e9,
-        "share_of_step": t_bwd * n_bwd / ms,
+        "share_of_step": t_bwd * n_bwd / args.steps / (ms / args.steps),
+        "timing": "CUDA events on the launching stream, eager pass of the same step inside this run",
         "fwd": {"kernel": f"dilated_attn_fwd[{impl_names[config.attn_impl('fwd')]}]", "achieved": ach_fwd,
                 "frac": ach_fwd / peak, "launch_ms": t_fwd, "launches_timed": n_fwd,
-                "algorithmic_gflop_per_launch": f_fwd / 1e9, "share_of_step": t_fwd * n_fwd / ms},
+                "algorithmic_gflop_per_launch": f_fwd / 1e9, "share_of_step": t_fwd * n_fwd / args.steps / (ms / args.steps)},
     }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -305,7 +300,9 @@ def main():
         "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4 + 3 * 256 * 4, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "clocks": clk, "roofline": roofline,
+        "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+        "execution": "eager" if graphed is None else "cuda-graph replay of the captured step (one graph per token count)",
+        "eager_ms_per_step": ms_eager / args.steps, "clocks": clk, "roofline": roofline,
         "attention_tflops": {"fwd": ach_fwd, "bwd": ach_bwd},
         "loss": out.get("loss"),
     }

@@ -137,9 +137,24 @@ class LongNetGeneAdapter(LongNetViT):
             nn.init.constant_(m.weight, 1.0)
 
     # -- forward ---------------------------------------------------------------------------------------------------------
-    def _modal_tokens(self, genes, clinical, task_token):
+    def _shared_inputs(self, x, coords, genes):
+        """The task-independent part of a forward: embedded slide tokens [1, N, 768] and the gene-encoder tokens."""
+        return self.embed(x, coords), self.gene_encoder(genes)
+
+    def forward_tasks(self, x, coords, genes, clinical=None, task_tokens=()):
+        """Several task-conditioned passes over ONE slide (what ``multitask_forward`` does with one ``forward`` per task,
+        train_modaltune.py:156-179) sharing the token embedding and the gene-encoder output, which do not depend on the
+        task.  Eval-mode only: in train mode the reference draws fresh dropout masks per pass."""
+        if self.training:
+            return torch.cat([self._adapter_forward(x, coords, genes, clinical, t, None, None, None)
+                              for t in task_tokens], 0)
+        shared = self._shared_inputs(x, coords, genes)
+        return torch.cat([self._adapter_forward(None, None, None, clinical, t, None, None, None, shared=shared)
+                          for t in task_tokens], 0)
+
+    def _modal_tokens(self, gene_tokens, clinical, task_token):
         """[1, M, 768] modal tokens: (clinical) | (task) | (gene cls) | 64 pathway tokens  (:257-266, 568-584)."""
-        c = self.gene_encoder(genes)
+        c = gene_tokens
         if self.prompt_agg == "cls":
             c = torch.cat((self.gene_cls, c), dim=1)
         if self.is_multi:
@@ -150,13 +165,15 @@ class LongNetGeneAdapter(LongNetViT):
         return c
 
     def _adapter_forward(self, x, coords, genes, clinical, task_token, attn_mask, multiway_split_position,
-                         incremental_state):
-        x = self.embed(x, coords)
+                         incremental_state, shared=None):
+        if shared is None:
+            shared = self._shared_inputs(x, coords, genes)
+        x, gene_tokens = shared
         x, _, encoder_padding_mask, rel_pos_bias = self.encoder.prepare_forward(src_tokens=None, token_embeddings=x)
         layer_configs = {"rel_pos": rel_pos_bias,
                          "encoder_padding_mask": encoder_padding_mask if incremental_state is None else None,
                          "attn_mask": attn_mask, "multiway_split_position": multiway_split_position}
-        c = self._modal_tokens(genes, clinical, task_token)
+        c = self._modal_tokens(gene_tokens, clinical, task_token)
         for idx, blk in enumerate(self.encoder.layers[0:self.interaction_indexes[0][0]]):
             x, _ = blk(x, incremental_state=None, **layer_configs)
         cls, x = x[:, :1], x[:, 1:]

@@ -39,13 +39,13 @@ def text_targets(projector: nn.Module, text: torch.Tensor) -> torch.Tensor:
 def multitask_forward(model, slide: Dict, task_ids: Sequence[int] = (0, 1, 2)) -> torch.Tensor:
     """[len(task_ids), 256] task-conditioned embeddings (train_modaltune.py:156-179)."""
     eye = torch.eye(NUM_TASKS, device=slide["x"].device)
+    clinical = slide.get("clinical") if getattr(model, "_HAS_CLINICAL", False) else None
+    if hasattr(model, "forward_tasks"):
+        return model.forward_tasks(slide["x"], slide["coords"], slide["genes"], clinical, [eye[t] for t in task_ids])
     outs = []
     for t in task_ids:
-        if "clinical" in slide and getattr(model, "_HAS_CLINICAL", False):
-            outs.append(model(x=slide["x"], coords=slide["coords"], genes=slide["genes"], clinical=slide["clinical"],
-                              task_token=eye[t]))
-        else:
-            outs.append(model(x=slide["x"], coords=slide["coords"], genes=slide["genes"], task_token=eye[t]))
+        kw = {"clinical": clinical} if clinical is not None else {}
+        outs.append(model(x=slide["x"], coords=slide["coords"], genes=slide["genes"], task_token=eye[t], **kw))
     return torch.cat(outs, 0)
 
 
@@ -76,31 +76,105 @@ def slide_to_device(slide: Dict, device, non_blocking: bool = True) -> Dict:
 
 
 class FlatGradAllReduce:
-    """Data-parallel gradient exchange: one all-reduce (sum, then / world) over a single contiguous fp32 buffer that the
-    ``.grad`` of every trainable parameter aliases.  Replaces DDP's 25 MB-bucket all-reduces."""
+    """Data-parallel gradient exchange: the gradients of all trainable parameters are gathered into ONE contiguous fp32
+    buffer (one cat kernel), all-reduced with a single NCCL call (sum, then / world) and handed back as views, so
+    ``p.grad`` of every parameter aliases the reduced buffer.  Replaces DDP's 25 MB-bucket all-reduces
+    (utils/base_trainer.py:205-211).  ``zero()`` drops the gradients (set-to-none): the next backward then WRITES
+    instead of accumulating, which saves one tiny add kernel per parameter (1 500+ per step for the gene encoder)."""
 
     def __init__(self, params: Sequence[torch.nn.Parameter]):
         self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
-        dev = self.params[0].device
-        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
-        off = 0
-        for p in self.params:
-            assert p.dtype == torch.float32
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        assert all(p.dtype == torch.float32 for p in self.params)
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = None
 
     def zero(self):
-        self.flat.zero_()
+        for p in self.params:
+            p.grad = None
+
+    def gather(self):
+        """Flatten the current gradients into one buffer and re-point ``p.grad`` at its slices."""
+        dev = self.params[0].device
+        parts = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
+        self.flat = torch.cat(parts)
         off = 0
-        for p in self.params:  # re-alias in case an optimizer / zero_grad(set_to_none) dropped the views
-            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * off:
-                p.grad = self.flat[off:off + p.numel()].view_as(p)
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
+        return self.flat
 
     def all_reduce(self):
         import torch.distributed as dist
 
+        flat = self.gather()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.div_(dist.get_world_size())
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat.div_(dist.get_world_size())
+        return flat
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CUDA-graph step
+# ---------------------------------------------------------------------------------------------------------------------
+def pack_host_slide(slide: Dict, pin: bool = True):
+    """Host staging of one case: x, coords, clinical, text plus the 331 pathway vectors packed into ONE buffer (one H2D
+    copy instead of the reference's 331, train_modaltune.py:205-208).  Returns (tensors, pathway sizes, bytes)."""
+    sizes = [slide["genes"][i].shape[1] for i in range(len(slide["genes"]))]
+    host = {"x": slide["x"].float(), "coords": slide["coords"].float(),
+            "genes_flat": torch.cat([slide["genes"][i].reshape(-1) for i in range(len(sizes))]).float(),
+            "clinical": slide["clinical"].float(), "text": slide["text"].float()}
+    host = {k: (v.contiguous().pin_memory() if pin and torch.cuda.is_available() else v.contiguous())
+            for k, v in host.items()}
+    return host, sizes, sum(v.numel() * v.element_size() for v in host.values())
+
+
+def unpack_slide(packed: Dict, sizes: Sequence[int]) -> Dict:
+    """Views of a packed slide in the layout the model takes (``genes`` as a dict of [1, n_i] views)."""
+    d = {k: v for k, v in packed.items() if k != "genes_flat"}
+    d["genes"] = {i: p.unsqueeze(0) for i, p in enumerate(torch.split(packed["genes_flat"], list(sizes)))}
+    return d
+
+
+class GraphedStep:
+    """forward (3 task passes) + loss + backward + gradient flattening of ONE slide shape captured in a CUDA graph.
+
+    A step launches ~5 000 kernels, most of them tiny (gene encoder, modal-token side of the adapter, autograd glue);
+    issued eagerly from Python the step is CPU-bound.  Captured once per token count, a step is one
+    ``cudaGraphLaunch``: the inputs are copied into static device buffers, the graph is replayed, the single NCCL
+    all-reduce of the flat gradient buffer runs after it.  Gradients live in ``flat.flat`` / ``p.grad`` views."""
+
+    def __init__(self, model, projector, packed_example: Dict, sizes: Sequence[int], flat: FlatGradAllReduce,
+                 warmup: int = 3):
+        self.model, self.projector, self.flat, self.sizes = model, projector, flat, list(sizes)
+        dev = next(model.parameters()).device
+        self.static = {k: v.to(dev).clone() for k, v in packed_example.items()}
+        slide = unpack_slide(self.static, self.sizes)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                flat.zero()
+                forward_backward(model, projector, slide)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        flat.zero()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.logits = forward_backward(model, projector, slide)
+            self.grads = flat.gather()
+
+    def load(self, packed: Dict):
+        """Copy one packed slide (pinned host or device tensors of the captured shapes) into the static inputs."""
+        for k, v in self.static.items():
+            v.copy_(packed[k], non_blocking=True)
+
+    def __call__(self, packed: Optional[Dict] = None):
+        if packed is not None:
+            self.load(packed)
+        self.graph.replay()
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+            self.grads.div_(dist.get_world_size())
+        return self.loss, self.logits

@@ -36,6 +36,7 @@ def _worker(rank, world, port, out_dir):
     for p in flat.params:
         assert p.grad.data_ptr() == flat.flat.data_ptr() + 4 * off
         off += p.numel()
+    assert off == flat.numel
     torch.save(flat.flat.clone(), os.path.join(out_dir, f"rank{rank}.pt"))
     dist.destroy_process_group()
 
@@ -48,14 +49,18 @@ def test_flat_allreduce_world2_gloo(tmp_path):
     r0, r1 = (torch.load(os.path.join(tmp_path, f"rank{r}.pt")) for r in (0, 1))
     assert torch.equal(r0, r1)
     torch.set_num_threads(4)
-    serial = sum(_grads_for(500 + r)[1].flat for r in (0, 1)) / 2
+    serial = sum(_grads_for(500 + r)[1].gather() for r in (0, 1)) / 2
     assert helpers.relerr(r0, serial) < 1e-5
 
 
-def test_flat_buffer_survives_zero_grad():
+def test_zero_drops_grads_and_gather_realiases():
     model = helpers.build_model(helpers.SMALL_GROUPS)
     flat = train_step.FlatGradAllReduce([p for p in model.parameters() if p.requires_grad])
-    model.zero_grad(set_to_none=True)
+    for p in flat.params:
+        p.grad = torch.ones_like(p)
+    buf = flat.gather()
+    assert buf.numel() == sum(p.numel() for p in model.parameters() if p.requires_grad) and float(buf.min()) == 1.0
+    buf.mul_(2.0)
+    assert all(float(p.grad.max()) == 2.0 for p in flat.params)   # views of the flat buffer
     flat.zero()
-    assert all(p.grad is not None and p.grad.data_ptr() >= flat.flat.data_ptr() for p in flat.params)
-    assert flat.flat.numel() == sum(p.numel() for p in model.parameters() if p.requires_grad)
+    assert all(p.grad is None for p in flat.params)

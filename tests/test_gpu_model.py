@@ -185,3 +185,27 @@ def test_full_gradient_cosine_vs_oracle_bf16_and_fp32(model):
             assert glob > 0.9999, glob
             assert min(cs.values()) > 0.995, min(cs.items(), key=lambda kv: kv[1])
             assert sum(c > 0.999 for c in cs.values()) >= 0.98 * len(cs), sorted(cs.values())[:8]
+
+
+def test_graphed_step_equals_eager_step(model):
+    """The CUDA-graph replay of a step (train_step.GraphedStep) reproduces the eager step on a NEW slide of the shape."""
+    proj = helpers.build_projector(0, DEV)
+    flat = train_step.FlatGradAllReduce([p for p in model.parameters() if p.requires_grad])
+    slides = [synthetic.synthetic_slide(700, seed=s, group_sizes=helpers.SMALL_GROUPS) for s in (31, 32)]
+    packed = [train_step.pack_host_slide(s) for s in slides]
+    sizes = packed[0][1]
+    with config.using(mode="bf16"):
+        graphed = train_step.GraphedStep(model, proj, packed[0][0], sizes, flat)
+        loss_g, logits_g = graphed(packed[1][0])          # pinned host -> static buffers -> replay
+        torch.cuda.synchronize()
+        g_graph = graphed.grads.clone()
+        loss_g, logits_g = float(loss_g), logits_g.clone()
+        flat.zero()
+        dev_slide = train_step.unpack_slide({k: v.to(DEV) for k, v in packed[1][0].items()}, sizes)
+        loss_e, logits_e = train_step.forward_backward(model, proj, dev_slide)
+        g_eager = flat.gather()
+    assert abs(loss_g - float(loss_e)) < 1e-5 * abs(float(loss_e)) + 1e-7
+    assert helpers.relerr(logits_g, logits_e) < 1e-5
+    # fp32 atomics in the attention backward reorder between runs: equality up to that noise
+    assert _cos(g_graph, g_eager) > 0.999999
+    assert helpers.relerr(g_graph, g_eager) < 1e-3
