@@ -254,6 +254,8 @@ def main():
     e2e_value = world * args.steps / (ms_e2e / 1e3)
 
     # ---- per-kernel timing + launch count: the same step issued eagerly with CUDA events around the attention kernels -
+    for i in range(2):  # the caching allocator needs its blocks back on this stream after the graph capture
+        eager_step(resident[i % n_slides])
     ops.kernel_events = {}
     launches0 = ops.launch_count
     ms_eager = timed(lambda i: eager_step(resident[i % n_slides]), args.steps)

@@ -53,7 +53,7 @@ def distill_loss(logits: torch.Tensor, text_proj: torch.Tensor) -> torch.Tensor:
     """10 * KLDiv_sum(log_softmax(z/|z|), softmax(t[[0,1,3]]))   (train_modaltune.py:225-233)."""
     z = logits.float()
     z = z / z.norm(dim=-1, keepdim=True)
-    tgt = F.softmax(text_proj[list(TEXT_ROWS)], dim=1)
+    tgt = F.softmax(torch.stack([text_proj[r] for r in TEXT_ROWS], 0), dim=1)  # no host index tensor (graph capture)
     return F.kl_div(F.log_softmax(z, dim=1), tgt, reduction="sum") * 10.0
 
 

@@ -26,5 +26,5 @@ ev = prof.key_averages()
 rows = sorted(((e.device_time_total, e.count, e.key) for e in ev if e.device_time_total > 0 and e.device_type.name == "CUDA"), reverse=True)
 tot = sum(r[0] for r in rows)
 print(f"GPU kernel time total {tot/1e3:.2f} ms over {sum(r[1] for r in rows)} kernels")
-for t, c, k in rows[:40]:
+for t, c, k in rows[:45]:
     print(f"{t/1e3:9.3f} ms {c:6d}x {100*t/tot:5.1f}%  {k[:110]}")
