@@ -148,12 +148,15 @@ class CrossAttentionLayer(nn.Module):
             if p.dim() > 1:
                 nn.init.xavier_uniform_(p)
 
-    def attend(self, tgt, memory, pos=None, query_pos=None):
+    def attend(self, tgt, memory, pos=None, query_pos=None, tgt_row0: int = 0, mem_row0: int = 0):
         """The attention branch of ``forward_pre`` (:210-234) WITHOUT the trailing ``tgt +``: [Lq, 768] fp32.
-        LayerNorm of both streams with the positional add fused; pos goes into the value input too."""
+        LayerNorm of both streams with the positional add fused; pos goes into the value input too.  ``*_row0`` = 1
+        when the stream is the [cls | tiles] buffer and only the tile rows take part (no slice copies)."""
         assert self.multihead_attn.dropout == 0.0 or not self.training, "attention dropout is 0 in ModalTune's config"
-        t2 = ops.layer_norm(tgt, self.norm.weight, self.norm.bias, add=_pos_rows(query_pos, tgt.shape[0]))
-        mem = ops.layer_norm(memory, self.norm_kq.weight, self.norm_kq.bias, add=_pos_rows(pos, memory.shape[0]))
+        t2 = ops.layer_norm(tgt, self.norm.weight, self.norm.bias, add=_pos_rows(query_pos, tgt.shape[0] - tgt_row0),
+                            row0=tgt_row0)
+        mem = ops.layer_norm(memory, self.norm_kq.weight, self.norm_kq.bias,
+                             add=_pos_rows(pos, memory.shape[0] - mem_row0), row0=mem_row0)
         query = _lin(t2, self.q_proj.weight, self.q_proj.bias) if self.with_cffn else t2
         a = _mha_core(self.multihead_attn, query, mem, mem)
         if self.with_cffn:
@@ -218,6 +221,15 @@ class Extractor(nn.Module):
             query = query + self.drop_path(self.ffn(query))
         return query
 
+    def forward_full(self, query, xfull, pos=None):
+        """Same as ``forward`` with ``feat`` = the tile rows (1..) of the [1, N, 768] [cls | tiles] buffer ``xfull``."""
+        c = _rows(query).float()
+        a = self.attn.attend(c, _rows(xfull), None, pos, mem_row0=1)
+        query = (c + (c + a)).unsqueeze(0)
+        if self.with_cffn:
+            query = query + self.drop_path(self.ffn(query))
+        return query
+
 
 class Injector(nn.Module):
     """x <- x + gamma * (x + attn(x, c, pos=pe))   (reference :338-369), tail fused in one kernel."""
@@ -233,6 +245,12 @@ class Injector(nn.Module):
         x = _rows(query).float()
         a = self.attn.attend(x, _rows(feat).float(), pos, None)
         return ops.gated_residual(x, a, self.gamma).unsqueeze(0)
+
+    def forward_full(self, xfull, feat, pos=None):
+        """Same as ``forward`` on the tile rows (1..) of the [1, N, 768] [cls | tiles] buffer; the cls row passes through."""
+        x = _rows(xfull)
+        a = self.attn.attend(x, _rows(feat).float(), pos, None, tgt_row0=1)
+        return ops.gated_residual(x, a, self.gamma, row0=1).unsqueeze(0)
 
 
 class InteractionBlockWithCls(nn.Module):
@@ -266,3 +284,16 @@ class InteractionBlockWithCls_LongNetViT(InteractionBlockWithCls):
             for extractor in self.extra_extractors:
                 c = extractor(query=c, feat=x, pos=query_pos)
         return x, c, cls
+
+    def forward_full(self, xfull, c, blocks, incremental_state, layer_configs, query_pos=None):
+        """``forward`` on the [1, N, 768] buffer that keeps cls at row 0: the reference's ``cat((cls, x))`` and
+        ``x[:, :1], x[:, 1:]`` (:492-505) and their backward copies disappear; same arithmetic."""
+        xfull = self.injector.forward_full(xfull, c, query_pos)
+        for idx, blk in enumerate(blocks):
+            xfull, _ = blk(xfull, incremental_state=(incremental_state[idx] if incremental_state is not None else None),
+                           **layer_configs)
+        c = self.extractor.forward_full(c, xfull, query_pos)
+        if self.extra_extractors is not None:
+            for extractor in self.extra_extractors:
+                c = extractor.forward_full(c, xfull, query_pos)
+        return xfull, c

@@ -18,6 +18,8 @@
 // online-softmax rescale, so TMEM is never read-modify-written.
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "mt_common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -197,7 +199,10 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
       }
     };
 
-    for (int j = 0; j < n_kv; ++j) {
+    const float scale_log2 = P.scale_log2;
+    // one key tile: MASK = the tile holds slots past the segment's m (only ever the last tile of the loop)
+    auto tile = [&](int j, auto mask_tag) {
+      constexpr bool MASK = decltype(mask_tag)::value;
       const int kvalid = bg.m - j * BT;  // key slots of this tile that belong to the segment (>= 1)
       mbar_wait(bar_s_full, j & 1);
       tc_fence_after();
@@ -209,16 +214,16 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
         tmem_ld32(tmem_s + t_lane + c * 32, sv);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < kvalid) ? sv[i] : -INFINITY);
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (!MASK || c * 32 + i < kvalid) ? sv[i] : -INFINITY);
       }
       const float m_new = fmaxf(m_run, mx);
-      const float alpha = ex2((m_run - m_new) * P.scale_log2);
+      const float alpha = ex2((m_run - m_new) * scale_log2);
       if (j > 0) fold(j - 1);  // O tile j-1 is relative to m_run; P's buffer is free once that MMA has completed
 #pragma unroll
       for (int i = 0; i < DH; ++i) o_acc[i] *= alpha;
       l_run *= alpha;
       m_run = m_new;
-      const float mb = m_new * P.scale_log2;
+      const float mb = m_new * scale_log2;
       // pass 2: p = exp2(s * scale_log2 - mb), row sum, bf16 P into the swizzled K-major tile
       float rs = 0.f;
 #pragma unroll
@@ -232,8 +237,12 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = (c * 32 + i < kvalid) ? ex2(fmaf(sv[i], P.scale_log2, -mb)) : 0.f;
-          const float p1 = (c * 32 + i + 1 < kvalid) ? ex2(fmaf(sv[i + 1], P.scale_log2, -mb)) : 0.f;
+          float p0 = ex2(fmaf(sv[i], scale_log2, -mb));
+          float p1 = ex2(fmaf(sv[i + 1], scale_log2, -mb));
+          if (MASK) {
+            p0 = (c * 32 + i < kvalid) ? p0 : 0.f;
+            p1 = (c * 32 + i + 1 < kvalid) ? p1 : 0.f;
+          }
           rs += p0 + p1;
           pk[i >> 1] = pack_bf16(p0, p1);
         }
@@ -248,6 +257,10 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
       fence_proxy_async_smem();  // generic-proxy stores of P -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(bar_p_full);
+    };
+    for (int j = 0; j < n_kv; ++j) {
+      if (bg.m - j * BT >= BT) tile(j, std::false_type{});
+      else tile(j, std::true_type{});
     }
     fold(n_kv - 1);
     // ---- epilogue: normalise and write the compact per-branch output ---------------------------------------------
@@ -564,6 +577,7 @@ dilated_bwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
     const int sw = row & 7;
     const int kvalid = bg.m - k0;
     const float LOG2E = 1.4426950408889634f;
+    const float scale_log2 = P.scale_log2, sc = P.scale;
     uint8_t* p_row = smem + BwdSmem::P + (quarter >> 1) * TILE_BYTES + row * 128;
     uint8_t* ds_row = smem + BwdSmem::DS + (quarter >> 1) * TILE_BYTES + row * 128;
 
@@ -601,13 +615,24 @@ dilated_bwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
       tc_fence_before();
       mbar_arrive(bar_s_free);
       uint32_t pk[16], dk[16];
+      const float nde = -de * sc;  // dS = p * (dp - delta) * scale = p * fma(dp, scale, -delta * scale)
+      if (kvalid >= BT) {
 #pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        const bool v0 = quarter * 32 + c < kvalid, v1 = quarter * 32 + c + 1 < kvalid;
-        const float p0 = v0 ? ex2(fmaf(sv[c], P.scale_log2, -l2)) : 0.f;
-        const float p1 = v1 ? ex2(fmaf(sv[c + 1], P.scale_log2, -l2)) : 0.f;
-        pk[c >> 1] = pack_bf16(p0, p1);
-        dk[c >> 1] = pack_bf16(p0 * (dp[c] - de) * P.scale, p1 * (dp[c + 1] - de) * P.scale);
+        for (int c = 0; c < 32; c += 2) {
+          const float p0 = ex2(fmaf(sv[c], scale_log2, -l2));
+          const float p1 = ex2(fmaf(sv[c + 1], scale_log2, -l2));
+          pk[c >> 1] = pack_bf16(p0, p1);
+          dk[c >> 1] = pack_bf16(p0 * fmaf(dp[c], sc, nde), p1 * fmaf(dp[c + 1], sc, nde));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const bool v0 = quarter * 32 + c < kvalid, v1 = quarter * 32 + c + 1 < kvalid;
+          const float p0 = v0 ? ex2(fmaf(sv[c], scale_log2, -l2)) : 0.f;
+          const float p1 = v1 ? ex2(fmaf(sv[c + 1], scale_log2, -l2)) : 0.f;
+          pk[c >> 1] = pack_bf16(p0, p1);
+          dk[c >> 1] = pack_bf16(p0 * fmaf(dp[c], sc, nde), p1 * fmaf(dp[c + 1], sc, nde));
+        }
       }
       // P / dS buffers are free once the MMAs of pair i-1 have completed (that is what dq_full(i-1) tracks)
       if (i > 0) mbar_wait(bar_dq_full + 8 * ((i - 1) & 1), ((i - 1) >> 1) & 1);

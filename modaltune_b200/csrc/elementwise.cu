@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
   for (int64_t row0 = (int64_t)blockIdx.x * C::RPB; row0 < rows; row0 += (int64_t)gridDim.x * C::RPB) {
     const int64_t row = row0 + rib;
     const bool live = row < rows;
-    float xh[3][8], g[3][8], raw[3][8];
+    float xh[3][8], g[3][8], raw[3][8];  // raw holds x, or gelu'(x) when GELU
     const float mu = live ? mean[row] : 0.f, rs = live ? rstd[row] : 0.f;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -142,7 +142,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float u = GELU ? gelu_erf(raw[i][j]) : raw[i][j];
+        float u = raw[i][j];
+        if (GELU) {  // value and derivative share the erf: u = x * cdf, gelu' = cdf + x * pdf
+          const float xv = raw[i][j];
+          const float cdf = 0.5f * (1.f + erff(xv * 0.70710678118654752f));
+          u = xv * cdf;
+          raw[i][j] = cdf + xv * 0.3989422804014327f * __expf(-0.5f * xv * xv);
+        }
         xh[i][j] = (u - mu) * rs;
         g[i][j] = d[j] * gam[i][j];
         s1 += g[i][j];
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           o[j] = rs * (g[i][j] - m1 - xh[i][j] * m2);
-          if (GELU) o[j] *= gelu_erf_grad(raw[i][j]);
+          if (GELU) o[j] *= raw[i][j];
         }
         if (residual != nullptr) {
           float r[8];
@@ -176,14 +182,24 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
     }
   }
   if constexpr (WGRAD) {
+    // the RPB row-lanes of the block hold partials for the same columns: combine them in shared memory first, so that
+    // every column receives ONE global atomic per block (same-address atomics serialise in L2)
+    __shared__ float wsum[2 * COLS];
+    for (int c = threadIdx.x; c < 2 * COLS; c += blockDim.x) wsum[c] = 0.f;
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = (i * C::TPR + t) * 8 + j;
-        atomicAdd(dgamma + c, dg_acc[i][j]);
-        atomicAdd(dbeta + c, db_acc[i][j]);
+        atomicAdd(wsum + c, dg_acc[i][j]);
+        atomicAdd(wsum + COLS + c, db_acc[i][j]);
       }
+    __syncthreads();
+    for (int c = threadIdx.x; c < COLS; c += blockDim.x) {
+      atomicAdd(dgamma + c, wsum[c]);
+      atomicAdd(dbeta + c, wsum[COLS + c]);
+    }
   }
 }
 

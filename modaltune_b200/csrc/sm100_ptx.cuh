@@ -33,11 +33,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must not hang the GPU.  ~2 s at 2 GHz, then the kernel traps (the launch reports an error).
+// Bounded wait: a protocol bug must not hang the GPU.  The hot loop is try_wait + branch only (the instruction itself
+// suspends the warp for a hardware time slice); the clock is consulted once per 1024 failed polls and the kernel traps
+// after ~2 s, so a broken protocol surfaces as a launch error instead of a hung box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (true) {
+#pragma unroll 1
+    for (int i = 0; i < 1024; ++i)
+      if (mbar_try_wait(bar, parity)) return;
     if (clock64() - t0 > 4000000000ll) {
       printf("modaltune_b200: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
              parity);

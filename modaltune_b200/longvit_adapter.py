@@ -176,13 +176,13 @@ class LongNetGeneAdapter(LongNetViT):
         c = self._modal_tokens(gene_tokens, clinical, task_token)
         for idx, blk in enumerate(self.encoder.layers[0:self.interaction_indexes[0][0]]):
             x, _ = blk(x, incremental_state=None, **layer_configs)
-        cls, x = x[:, :1], x[:, 1:]
+        # cls stays at row 0 of one [1, N, 768] buffer; Injector / Extractor work on rows 1.. in place
         for i, layer in enumerate(self.interactions):
             lo, hi = self.interaction_indexes[i][0], self.interaction_indexes[i][-1]
             c = self.prompt_selfattention[i](c, self.gene_pe)
-            x, c, cls = layer(x, c, cls, self.encoder.layers[lo:hi + 1], incremental_state, layer_configs,
-                              self.gene_pe)
-        img_outcome = x.mean(dim=1).unsqueeze(0) if self.global_pool else cls
+            x, c = layer.forward_full(x, c, self.encoder.layers[lo:hi + 1], incremental_state, layer_configs,
+                                      self.gene_pe)
+        img_outcome = x[:, 1:].mean(dim=1).unsqueeze(0) if self.global_pool else x[:, :1]
         if self.add_prompt_feature:
             k = int(self._HAS_CLINICAL)
             m = int(self.is_multi)

@@ -144,9 +144,9 @@ def layernorm_fwd(x, gamma, beta, out_dtype, add=None, eps: float = LN_EPS, want
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx_dtype, residual=None, want_wgrad: bool = False):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_dtype, residual=None, want_wgrad: bool = False, out=None):
     rows, cols = x.shape
-    dx = torch.empty((rows, cols), device=x.device, dtype=dx_dtype)
+    dx = out if out is not None else torch.empty((rows, cols), device=x.device, dtype=dx_dtype)
     dgamma = dbeta = None
     if want_wgrad:
         dgamma = torch.zeros(cols, device=x.device, dtype=torch.float32)
@@ -289,34 +289,45 @@ def cast(src: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 # autograd: trainable LayerNorm, cross-attention core, Injector tail
 # ---------------------------------------------------------------------------------------------------------------------
 class LayerNormFn(torch.autograd.Function):
-    """y = LN(x) * gamma + beta [+ add]  with x [rows, 768] fp32; y in ``out_dtype``.  Grads for x, gamma, beta, add."""
+    """y = LN(x[row0:]) * gamma + beta [+ add]  with x [rows, 768] fp32; y in ``out_dtype``.  Grads for x (full, rows
+    < row0 get zero), gamma, beta, add.  ``row0`` lets the adapter normalise the tile tokens of the [cls | tiles] buffer
+    in place: no slice / concat copies of the [N, 768] stream, forward or backward."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, add, out_dtype):
+    def forward(ctx, x, gamma, beta, add, out_dtype, row0):
         x = x.contiguous()
+        xv = x[row0:] if row0 else x
         g32, b32 = _f32(gamma).contiguous(), _f32(beta).contiguous()
         addc = None
         if add is not None:
-            assert add.shape == x.shape
+            assert add.shape == xv.shape
             addc = add.contiguous()
-        y, mean, rstd = layernorm_fwd(x, g32, b32, out_dtype, add=addc)
+        y, mean, rstd = layernorm_fwd(xv, g32, b32, out_dtype, add=addc)
         ctx.save_for_backward(x, g32, mean, rstd)
         ctx.has_add = add is not None
         ctx.add_dtype = add.dtype if add is not None else None
         ctx.need_w = gamma.requires_grad or beta.requires_grad
+        ctx.row0 = row0
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, g32, mean, rstd = ctx.saved_tensors
         dy = dy.contiguous()
-        dx, dgamma, dbeta = layernorm_bwd(dy, x, g32, mean, rstd, x.dtype, want_wgrad=ctx.need_w)
+        row0 = ctx.row0
+        if row0:
+            dx = torch.empty_like(x)
+            dx[:row0].zero_()
+            _, dgamma, dbeta = layernorm_bwd(dy, x[row0:], g32, mean, rstd, x.dtype, want_wgrad=ctx.need_w,
+                                             out=dx[row0:])
+        else:
+            dx, dgamma, dbeta = layernorm_bwd(dy, x, g32, mean, rstd, x.dtype, want_wgrad=ctx.need_w)
         dadd = dy.to(ctx.add_dtype) if ctx.has_add else None
-        return dx, dgamma, dbeta, dadd, None
+        return dx, dgamma, dbeta, dadd, None, None
 
 
-def layer_norm(x, gamma, beta, add=None, out_dtype=None):
-    return LayerNormFn.apply(x, gamma, beta, add, out_dtype or x.dtype)
+def layer_norm(x, gamma, beta, add=None, out_dtype=None, row0: int = 0):
+    return LayerNormFn.apply(x, gamma, beta, add, out_dtype or x.dtype, row0)
 
 
 class CrossAttnFn(torch.autograd.Function):
@@ -341,17 +352,17 @@ def cross_attention(q, k, v, heads: int):
     return CrossAttnFn.apply(q, k, v, heads)
 
 
-def gated_residual_fwd(a, b, g32):
-    y = torch.empty_like(a)
+def gated_residual_fwd(a, b, g32, out=None):
+    y = out if out is not None else torch.empty_like(a)
     rows, cols = a.shape
     rc = _lib.load().mt_gated_residual(_p(a), _p(b), _dt(b), _p(g32), _p(y), rows, cols, _stream())
     _check(rc, "mt_gated_residual")
     return y
 
 
-def gated_residual_bwd(dy, a, b, g32):
+def gated_residual_bwd(dy, a, b, g32, out=None):
     rows, cols = a.shape
-    da = torch.empty_like(a)
+    da = out if out is not None else torch.empty_like(a)
     db = torch.empty_like(b)
     dgate = torch.empty(cols, device=a.device, dtype=torch.float32)
     rc = _lib.load().mt_gated_residual_bwd(_p(dy), _p(a), _p(b), _dt(b), _p(g32), _p(da), _p(db), _dt(db), _p(dgate),
@@ -397,24 +408,40 @@ def linear_tf32(x, w, b):
 
 
 class GatedResidualFn(torch.autograd.Function):
-    """y = a + gate * (a + b): the Injector tail ``query + gamma * (query + attn)`` (adapter_modules.py:231,362)."""
+    """y[row0:] = a[row0:] + gate * (a[row0:] + b), y[:row0] = a[:row0]: the Injector tail
+    ``query + gamma * (query + attn)`` (adapter_modules.py:231,362) applied to the tile rows of the [cls | tiles]
+    buffer ``a`` (row0 = 1) or to a plain [L, 768] tensor (row0 = 0)."""
 
     @staticmethod
-    def forward(ctx, a, b, gate):
+    def forward(ctx, a, b, gate, row0):
         a, b = a.contiguous(), b.contiguous()
         g32 = _f32(gate).contiguous()
-        y = gated_residual_fwd(a, b, g32)
+        if row0:
+            y = torch.empty_like(a)
+            y[:row0].copy_(a[:row0])
+            gated_residual_fwd(a[row0:], b, g32, out=y[row0:])
+        else:
+            y = gated_residual_fwd(a, b, g32)
         ctx.save_for_backward(a, b, g32)
+        ctx.row0 = row0
         return y
 
     @staticmethod
     def backward(ctx, dy):
         a, b, g32 = ctx.saved_tensors
-        return gated_residual_bwd(dy.contiguous(), a, b, g32)
+        dy = dy.contiguous()
+        row0 = ctx.row0
+        if row0:
+            da = torch.empty_like(a)
+            da[:row0].copy_(dy[:row0])
+            _, db, dgate = gated_residual_bwd(dy[row0:], a[row0:], b, g32, out=da[row0:])
+        else:
+            da, db, dgate = gated_residual_bwd(dy, a, b, g32)
+        return da, db, dgate, None
 
 
-def gated_residual(a, b, gate):
-    return GatedResidualFn.apply(a, b, gate)
+def gated_residual(a, b, gate, row0: int = 0):
+    return GatedResidualFn.apply(a, b, gate, row0)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

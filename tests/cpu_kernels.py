@@ -36,13 +36,17 @@ def _ln_bwd(dy, u, gamma, mean, rstd):
     return rstd[:, None] * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True)), xh
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx_dtype, residual=None, want_wgrad=False):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_dtype, residual=None, want_wgrad=False, out=None):
     dx, xh = _ln_bwd(dy, x.float(), gamma, mean, rstd)
     if residual is not None:
         dx = dx + residual.float()
     dg = (dy.float() * xh).sum(0) if want_wgrad else None
     db = dy.float().sum(0) if want_wgrad else None
-    return dx.to(dx_dtype), dg, db
+    dx = dx.to(dx_dtype)
+    if out is not None:
+        out.copy_(dx)
+        dx = out
+    return dx, dg, db
 
 
 def add_layernorm_fwd(x, a, gamma, beta, out_dtype, eps=1e-5):
@@ -195,12 +199,20 @@ def cast(src, dtype):
     return src.to(dtype)
 
 
-def gated_residual_fwd(a, b, g32):
-    return a + g32 * (a + b.float())
+def gated_residual_fwd(a, b, g32, out=None):
+    y = a + g32 * (a + b.float())
+    if out is not None:
+        out.copy_(y)
+        y = out
+    return y
 
 
-def gated_residual_bwd(dy, a, b, g32):
-    return dy * (1 + g32), (dy * g32).to(b.dtype), (dy * (a + b.float())).sum(0)
+def gated_residual_bwd(dy, a, b, g32, out=None):
+    da = dy * (1 + g32)
+    if out is not None:
+        out.copy_(da)
+        da = out
+    return da, (dy * g32).to(b.dtype), (dy * (a + b.float())).sum(0)
 
 
 _NAMES = ["layernorm_fwd", "layernorm_bwd", "add_layernorm_fwd", "gelu_ln_fwd", "gelu_ln_bwd", "dilated_attn_fwd",
