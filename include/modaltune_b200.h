@@ -71,18 +71,22 @@ int mt_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, c
                      float* dbeta, int64_t rows, int64_t cols, void* stream);
 
 /* residual add fused with the next pre-LN (torchscale/architecture/encoder.py:152-166):
- * x_out = x + a (f32 residual stream, a in a_dtype), y = LN(x_out).  cols = 768. */
-int mt_add_layernorm_fwd(const float* x, const void* a, int a_dtype, const float* gamma, const float* beta,
-                         float* x_out, void* y, int y_dtype, float* mean, float* rstd, int64_t rows, int64_t cols,
+ * x_out = x + a [+ abias] (f32 residual stream, a in a_dtype, abias [cols] f32 or NULL = bias of the GEMM that
+ * produced a), y = LN(x_out).  cols = 768. */
+int mt_add_layernorm_fwd(const float* x, const void* a, int a_dtype, const float* abias, const float* gamma,
+                         const float* beta, float* x_out, void* y, int y_dtype, float* mean, float* rstd, int64_t rows, int64_t cols,
                          float eps, void* stream);
 
 /* ---- A6: GELU(fp32) + LayerNorm(3072) between fc1 and fc2 ---------------------------------------------------------
  * replaces: `activation_fn(x.float()).type_as(x)` + ffn_layernorm (torchscale/component/feedforward_network.py:135-140)
- * h [rows, cols] = fc1 output (bias included).  y = LN(gelu_erf(h)). */
-int mt_gelu_ln_fwd(const void* h, int h_dtype, const float* gamma, const float* beta, void* y, int y_dtype,
+ * h [rows, cols] = fc1 output; hbias [cols] f32 or NULL is added to it first (fc1's bias, so that the GEMM can keep a
+ * plain fp32 output).  y = LN(gelu_erf(h + hbias)). */
+int mt_gelu_ln_fwd(const void* h, int h_dtype, const float* hbias, const float* gamma, const float* beta, void* y,
+                   int y_dtype,
                    float* mean, float* rstd, int64_t rows, int64_t cols, float eps, void* stream);
 /* dh = gelu'(h) * LN'(dy) with u = gelu(h) recomputed. */
-int mt_gelu_ln_bwd(const void* dy, int dy_dtype, const void* h, int h_dtype, const float* gamma, const float* mean,
+int mt_gelu_ln_bwd(const void* dy, int dy_dtype, const void* h, int h_dtype, const float* hbias, const float* gamma,
+                   const float* mean,
                    const float* rstd, void* dh, int dh_dtype, int64_t rows, int64_t cols, void* stream);
 
 /* ---- A3/A4: dilated attention, all branches, per-branch outputs ---------------------------------------------------
@@ -112,8 +116,8 @@ int mt_dilated_merge_ln_bwd(const mt_dilated_geometry* geom, const void* dy, int
 
 /* ---- backward of A3/A4/A5 -----------------------------------------------------------------------------------------
  * replaces: autograd of the five flash_attn_func calls + gather/scatter (no reference source; flash-attn bwd).
- * dS_b = exp(S - LSE) * (dO V^T - delta_b);  dqkv_f32 [N, 3E] float is ZEROED by the call and accumulated with
- * reductions over branches. */
+ * dS_b = exp(S - LSE) * (dO V^T - delta_b);  dqkv_f32 [n_alloc, 3E] float (rows >= N are scratch) is ZEROED by the call
+ * and accumulated with reductions over branches; dattn [n_alloc, E] with zero rows >= N. */
 int mt_dilated_attn_bwd(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,
                         const void* dattn, const float* lse, const float* delta_br, int dtype, float* dqkv_f32,
                         int impl, void* stream);
@@ -139,6 +143,9 @@ int mt_gated_residual(const float* a, const void* b, int b_dtype, const float* g
  * (dgate is zeroed by the call and accumulated with atomics). */
 int mt_gated_residual_bwd(const float* dy, const float* a, const void* b, int b_dtype, const float* gate, float* da,
                           void* db, int db_dtype, float* dgate, int64_t rows, int64_t cols, void* stream);
+/* y = x + a + bias: residual add after fc2 (torchscale/architecture/encoder.py:169-175), bias [cols] f32 or NULL. */
+int mt_residual_bias_add(const float* x, const void* a, int a_dtype, const float* bias, float* y, int64_t rows,
+                         int64_t cols, void* stream);
 int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
 
 #ifdef __cplusplus

@@ -43,6 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     if verbose:
         flags += ["-Xptxas", "-v"]
+    flags += os.environ.get("MT_EXTRA_NVCC_FLAGS", "").split()  # experiments only (e.g. -DMT_DEBUG_...)
 
     def compile_one(src):
         s = os.path.join(CSRC, src)

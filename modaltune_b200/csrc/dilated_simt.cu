@@ -538,7 +538,8 @@ extern "C" int mt_dilated_attn_bwd(const mt_dilated_geometry* geom, const void* 
   MT_REQUIRE(dtype == MT_F32 || dtype == MT_BF16, "dilated_attn_bwd: bad dtype %d", dtype);
   MT_REQUIRE(geom != nullptr, "dilated_attn_bwd: geometry is NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  MT_CUDA(cudaMemsetAsync(dqkv_f32, 0, sizeof(float) * (size_t)geom->n_tokens * 3 * geom->n_heads * geom->head_dim, st));
+  MT_REQUIRE(n_alloc >= geom->n_tokens, "dilated_attn_bwd: n_alloc < n_tokens");
+  MT_CUDA(cudaMemsetAsync(dqkv_f32, 0, sizeof(float) * (size_t)n_alloc * 3 * geom->n_heads * geom->head_dim, st));
   if (impl == 0) return dilated_attn_bwd_simt(geom, qkv, qkv_ld, dattn, lse, delta_br, dtype, dqkv_f32, st);
   MT_REQUIRE(dtype == MT_BF16, "dilated_attn_bwd: the tcgen05 path computes in bf16");
   return dilated_attn_bwd_sm100(geom, qkv, qkv_ld, n_alloc, dattn, lse, delta_br, dqkv_f32, st);

@@ -41,7 +41,8 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 
 // y = LN(f(x)) * gamma + beta (+ add[row % add_rows]);  f = identity or GELU
 template <int COLS, typename TX, typename TY, typename TA, bool GELU>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ xbias,
+                                                     const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, const TA* __restrict__ add,
                                                      int64_t add_rows, TY* __restrict__ y, float* __restrict__ mean,
                                                      float* __restrict__ rstd, int64_t rows, float eps) {
@@ -57,6 +58,12 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, c
     for (int i = 0; i < 3; ++i) {
       if (live) {
         load8(x + row * COLS + (i * C::TPR + t) * 8, v[i]);
+        if (xbias != nullptr) {  // bias of the producing GEMM, folded in here (the GEMM keeps a plain fp32 output)
+          float bv[8];
+          load8(xbias + (i * C::TPR + t) * 8, bv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] += bv[j];
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
@@ -106,6 +113,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, c
 // dx = [gelu'(x)] * rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ residual), g = dy * gamma, xhat = (f(x) - mean) * rstd
 template <int COLS, typename TDY, typename TX, typename TR, typename TDX, bool GELU, bool WGRAD>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
+                                                     const float* __restrict__ xbias,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const TR* __restrict__ residual,
                                                      TDX* __restrict__ dx, float* __restrict__ dgamma,
@@ -136,6 +144,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
       if (live) {
         load8(x + row * COLS + c, raw[i]);
         load8(dy + row * COLS + c, d);
+        if (xbias != nullptr) {
+          float bv[8];
+          load8(xbias + c, bv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) raw[i][j] += bv[j];
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) raw[i][j] = d[j] = 0.f;
@@ -260,6 +274,7 @@ __global__ void __launch_bounds__(256) gated_residual_kernel(const float* __rest
 // fused with the next block's pre-LN (encoder.py:152-166), one pass over HBM.
 template <int COLS, typename TA, typename TY>
 __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict__ x, const TA* __restrict__ a,
+                                                         const float* __restrict__ abias,
                                                          const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ x_out,
                                                          TY* __restrict__ y, float* __restrict__ mean,
@@ -280,6 +295,11 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict
         load8(a + row * COLS + (i * C::TPR + t) * 8, av);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[i][j] += av[j];
+        if (abias != nullptr) {
+          load8(abias + (i * C::TPR + t) * 8, av);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] += av[j];
+        }
         store8(x_out + row * COLS + (i * C::TPR + t) * 8, v[i]);
       } else {
 #pragma unroll
@@ -353,6 +373,26 @@ __global__ void __launch_bounds__(256) gated_residual_bwd_kernel(const float* __
   for (int j = 0; j < 8; ++j) atomicAdd(dgate + ch * 8 + j, acc[j]);
 }
 
+// y = x + a + bias[c]: the residual add after fc2 (encoder.py:169-175) with the GEMM's bias folded in
+template <typename TA>
+__global__ void __launch_bounds__(256) residual_bias_add_kernel(const float* __restrict__ x, const TA* __restrict__ a,
+                                                                const float* __restrict__ bias, float* __restrict__ y,
+                                                                int64_t rows, int cols) {
+  const int chunks = cols / 8;
+  const int64_t total = rows * chunks;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % chunks) * 8;
+    float xv[8], av[8], bv[8], o[8];
+    load8(x + idx * 8, xv);
+    load8(a + idx * 8, av);
+    if (bias != nullptr) load8(bias + c, bv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = xv[j] + av[j] + (bias != nullptr ? bv[j] : 0.f);
+    store8(y + idx * 8, o);
+  }
+}
+
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256) cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n8, int64_t n) {
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n8; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -375,38 +415,38 @@ static inline int grid_for(int64_t work_items, int per_block) {
 
 // ---- dispatch helpers ------------------------------------------------------------------------------------------------
 template <int COLS, bool GELU, typename TX, typename TY>
-static int launch_ln_fwd(const void* x, const float* gamma, const float* beta, const void* add, int add_dtype,
+static int launch_ln_fwd(const void* x, const float* xbias, const float* gamma, const float* beta, const void* add, int add_dtype,
                          int64_t add_rows, void* y, float* mean, float* rstd, int64_t rows, float eps, cudaStream_t st) {
   using C = RowCfg<COLS>;
   const int grid = grid_for(rows, C::RPB);
   if (add == nullptr || add_dtype == MT_F32)
-    ln_fwd_kernel<COLS, TX, TY, float, GELU><<<grid, 256, 0, st>>>((const TX*)x, gamma, beta, (const float*)add,
+    ln_fwd_kernel<COLS, TX, TY, float, GELU><<<grid, 256, 0, st>>>((const TX*)x, xbias, gamma, beta, (const float*)add,
                                                                    add_rows > 0 ? add_rows : 1, (TY*)y, mean, rstd,
                                                                    rows, eps);
   else
     ln_fwd_kernel<COLS, TX, TY, __nv_bfloat16, GELU><<<grid, 256, 0, st>>>(
-        (const TX*)x, gamma, beta, (const __nv_bfloat16*)add, add_rows > 0 ? add_rows : 1, (TY*)y, mean, rstd, rows, eps);
+        (const TX*)x, xbias, gamma, beta, (const __nv_bfloat16*)add, add_rows > 0 ? add_rows : 1, (TY*)y, mean, rstd, rows, eps);
   return check_launch("ln_fwd_kernel");
 }
 
 template <int COLS, bool GELU>
-static int dispatch_ln_fwd(const void* x, int xd, const float* gamma, const float* beta, const void* add, int ad,
+static int dispatch_ln_fwd(const void* x, int xd, const float* xbias, const float* gamma, const float* beta, const void* add, int ad,
                            int64_t add_rows, void* y, int yd, float* mean, float* rstd, int64_t rows, float eps,
                            cudaStream_t st) {
   if (xd == MT_F32 && yd == MT_F32)
-    return launch_ln_fwd<COLS, GELU, float, float>(x, gamma, beta, add, ad, add_rows, y, mean, rstd, rows, eps, st);
+    return launch_ln_fwd<COLS, GELU, float, float>(x, xbias, gamma, beta, add, ad, add_rows, y, mean, rstd, rows, eps, st);
   if (xd == MT_F32 && yd == MT_BF16)
-    return launch_ln_fwd<COLS, GELU, float, __nv_bfloat16>(x, gamma, beta, add, ad, add_rows, y, mean, rstd, rows, eps, st);
+    return launch_ln_fwd<COLS, GELU, float, __nv_bfloat16>(x, xbias, gamma, beta, add, ad, add_rows, y, mean, rstd, rows, eps, st);
   if (xd == MT_BF16 && yd == MT_BF16)
-    return launch_ln_fwd<COLS, GELU, __nv_bfloat16, __nv_bfloat16>(x, gamma, beta, add, ad, add_rows, y, mean, rstd, rows, eps, st);
+    return launch_ln_fwd<COLS, GELU, __nv_bfloat16, __nv_bfloat16>(x, xbias, gamma, beta, add, ad, add_rows, y, mean, rstd, rows, eps, st);
   if (xd == MT_BF16 && yd == MT_F32)
-    return launch_ln_fwd<COLS, GELU, __nv_bfloat16, float>(x, gamma, beta, add, ad, add_rows, y, mean, rstd, rows, eps, st);
+    return launch_ln_fwd<COLS, GELU, __nv_bfloat16, float>(x, xbias, gamma, beta, add, ad, add_rows, y, mean, rstd, rows, eps, st);
   set_error("layernorm: unsupported dtype combination");
   return MT_E_UNSUPPORTED;
 }
 
 template <int COLS, bool GELU, typename TDY, typename TX, typename TDX>
-static int launch_ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+static int launch_ln_bwd(const void* dy, const void* x, const float* xbias, const float* gamma, const float* mean, const float* rstd,
                          const void* residual, int rd, void* dx, float* dgamma, float* dbeta, int64_t rows,
                          cudaStream_t st) {
   using C = RowCfg<COLS>;
@@ -419,23 +459,23 @@ static int launch_ln_bwd(const void* dy, const void* x, const float* gamma, cons
         return MT_E_UNSUPPORTED;
       }
       ln_bwd_kernel<COLS, TDY, TX, float, TDX, GELU, true><<<grid, 256, 0, st>>>(
-          (const TDY*)dy, (const TX*)x, gamma, mean, rstd, (const float*)residual, (TDX*)dx, dgamma, dbeta, rows);
+          (const TDY*)dy, (const TX*)x, xbias, gamma, mean, rstd, (const float*)residual, (TDX*)dx, dgamma, dbeta, rows);
     }
   } else if (residual == nullptr || rd == MT_F32)
     ln_bwd_kernel<COLS, TDY, TX, float, TDX, GELU, false><<<grid, 256, 0, st>>>(
-        (const TDY*)dy, (const TX*)x, gamma, mean, rstd, (const float*)residual, (TDX*)dx, dgamma, dbeta, rows);
+        (const TDY*)dy, (const TX*)x, xbias, gamma, mean, rstd, (const float*)residual, (TDX*)dx, dgamma, dbeta, rows);
   else
     ln_bwd_kernel<COLS, TDY, TX, __nv_bfloat16, TDX, GELU, false><<<grid, 256, 0, st>>>(
-        (const TDY*)dy, (const TX*)x, gamma, mean, rstd, (const __nv_bfloat16*)residual, (TDX*)dx, dgamma, dbeta, rows);
+        (const TDY*)dy, (const TX*)x, xbias, gamma, mean, rstd, (const __nv_bfloat16*)residual, (TDX*)dx, dgamma, dbeta, rows);
   return check_launch("ln_bwd_kernel");
 }
 
 template <int COLS, bool GELU>
-static int dispatch_ln_bwd(const void* dy, int dyd, const void* x, int xd, const float* gamma, const float* mean,
+static int dispatch_ln_bwd(const void* dy, int dyd, const void* x, int xd, const float* xbias, const float* gamma, const float* mean,
                            const float* rstd, const void* residual, int rd, void* dx, int dxd, float* dgamma,
                            float* dbeta, int64_t rows, cudaStream_t st) {
 #define MT_LNB(TDY, TX, TDX) \
-  return launch_ln_bwd<COLS, GELU, TDY, TX, TDX>(dy, x, gamma, mean, rstd, residual, rd, dx, dgamma, dbeta, rows, st)
+  return launch_ln_bwd<COLS, GELU, TDY, TX, TDX>(dy, x, xbias, gamma, mean, rstd, residual, rd, dx, dgamma, dbeta, rows, st)
   using bf = __nv_bfloat16;
   if (dyd == MT_F32 && xd == MT_F32 && dxd == MT_F32) MT_LNB(float, float, float);
   if (dyd == MT_BF16 && xd == MT_F32 && dxd == MT_F32) MT_LNB(bf, float, float);
@@ -475,9 +515,9 @@ extern "C" int mt_layernorm_fwd(const void* x, int x_dtype, const float* gamma, 
   cudaStream_t st = (cudaStream_t)stream;
   if (rows == 0) return 0;
   if (cols == 768)
-    return dispatch_ln_fwd<768, false>(x, x_dtype, gamma, beta, add, add_dtype, add_rows, y, y_dtype, mean, rstd, rows, eps, st);
+    return dispatch_ln_fwd<768, false>(x, x_dtype, nullptr, gamma, beta, add, add_dtype, add_rows, y, y_dtype, mean, rstd, rows, eps, st);
   if (cols == 3072)
-    return dispatch_ln_fwd<3072, false>(x, x_dtype, gamma, beta, add, add_dtype, add_rows, y, y_dtype, mean, rstd, rows, eps, st);
+    return dispatch_ln_fwd<3072, false>(x, x_dtype, nullptr, gamma, beta, add, add_dtype, add_rows, y, y_dtype, mean, rstd, rows, eps, st);
   set_error("layernorm: width %lld not supported (768, 3072)", (long long)cols);
   return MT_E_UNSUPPORTED;
 }
@@ -489,34 +529,36 @@ extern "C" int mt_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int
   if (rows == 0) return 0;
   MT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm bwd: dgamma and dbeta go together");
   if (cols == 768)
-    return dispatch_ln_bwd<768, false>(dy, dy_dtype, x, x_dtype, gamma, mean, rstd, residual, res_dtype, dx, dx_dtype, dgamma, dbeta, rows, st);
+    return dispatch_ln_bwd<768, false>(dy, dy_dtype, x, x_dtype, nullptr, gamma, mean, rstd, residual, res_dtype, dx, dx_dtype, dgamma, dbeta, rows, st);
   if (cols == 3072)
-    return dispatch_ln_bwd<3072, false>(dy, dy_dtype, x, x_dtype, gamma, mean, rstd, residual, res_dtype, dx, dx_dtype, dgamma, dbeta, rows, st);
+    return dispatch_ln_bwd<3072, false>(dy, dy_dtype, x, x_dtype, nullptr, gamma, mean, rstd, residual, res_dtype, dx, dx_dtype, dgamma, dbeta, rows, st);
   set_error("layernorm bwd: width %lld not supported (768, 3072)", (long long)cols);
   return MT_E_UNSUPPORTED;
 }
 
-extern "C" int mt_gelu_ln_fwd(const void* h, int h_dtype, const float* gamma, const float* beta, void* y, int y_dtype,
+extern "C" int mt_gelu_ln_fwd(const void* h, int h_dtype, const float* hbias, const float* gamma, const float* beta,
+                              void* y, int y_dtype,
                               float* mean, float* rstd, int64_t rows, int64_t cols, float eps, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (rows == 0) return 0;
   if (cols == 3072)
-    return dispatch_ln_fwd<3072, true>(h, h_dtype, gamma, beta, nullptr, 0, 1, y, y_dtype, mean, rstd, rows, eps, st);
+    return dispatch_ln_fwd<3072, true>(h, h_dtype, hbias, gamma, beta, nullptr, 0, 1, y, y_dtype, mean, rstd, rows, eps, st);
   if (cols == 768)
-    return dispatch_ln_fwd<768, true>(h, h_dtype, gamma, beta, nullptr, 0, 1, y, y_dtype, mean, rstd, rows, eps, st);
+    return dispatch_ln_fwd<768, true>(h, h_dtype, hbias, gamma, beta, nullptr, 0, 1, y, y_dtype, mean, rstd, rows, eps, st);
   set_error("gelu_ln: width %lld not supported (768, 3072)", (long long)cols);
   return MT_E_UNSUPPORTED;
 }
 
-extern "C" int mt_gelu_ln_bwd(const void* dy, int dy_dtype, const void* h, int h_dtype, const float* gamma,
+extern "C" int mt_gelu_ln_bwd(const void* dy, int dy_dtype, const void* h, int h_dtype, const float* hbias,
+                              const float* gamma,
                               const float* mean, const float* rstd, void* dh, int dh_dtype, int64_t rows, int64_t cols,
                               void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (rows == 0) return 0;
   if (cols == 3072)
-    return dispatch_ln_bwd<3072, true>(dy, dy_dtype, h, h_dtype, gamma, mean, rstd, nullptr, 0, dh, dh_dtype, nullptr, nullptr, rows, st);
+    return dispatch_ln_bwd<3072, true>(dy, dy_dtype, h, h_dtype, hbias, gamma, mean, rstd, nullptr, 0, dh, dh_dtype, nullptr, nullptr, rows, st);
   if (cols == 768)
-    return dispatch_ln_bwd<768, true>(dy, dy_dtype, h, h_dtype, gamma, mean, rstd, nullptr, 0, dh, dh_dtype, nullptr, nullptr, rows, st);
+    return dispatch_ln_bwd<768, true>(dy, dy_dtype, h, h_dtype, hbias, gamma, mean, rstd, nullptr, 0, dh, dh_dtype, nullptr, nullptr, rows, st);
   set_error("gelu_ln bwd: width %lld not supported (768, 3072)", (long long)cols);
   return MT_E_UNSUPPORTED;
 }
@@ -534,7 +576,8 @@ extern "C" int mt_gated_residual(const float* a, const void* b, int b_dtype, con
   return check_launch("gated_residual_kernel");
 }
 
-extern "C" int mt_add_layernorm_fwd(const float* x, const void* a, int a_dtype, const float* gamma, const float* beta,
+extern "C" int mt_add_layernorm_fwd(const float* x, const void* a, int a_dtype, const float* abias, const float* gamma,
+                                    const float* beta,
                                     float* x_out, void* y, int y_dtype, float* mean, float* rstd, int64_t rows,
                                     int64_t cols, float eps, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -544,13 +587,13 @@ extern "C" int mt_add_layernorm_fwd(const float* x, const void* a, int a_dtype, 
   using bf = __nv_bfloat16;
   const int grid = grid_for(rows, C::RPB);
   if (a_dtype == MT_F32 && y_dtype == MT_F32)
-    add_ln_fwd_kernel<768, float, float><<<grid, 256, 0, st>>>(x, (const float*)a, gamma, beta, x_out, (float*)y, mean, rstd, rows, eps);
+    add_ln_fwd_kernel<768, float, float><<<grid, 256, 0, st>>>(x, (const float*)a, abias, gamma, beta, x_out, (float*)y, mean, rstd, rows, eps);
   else if (a_dtype == MT_BF16 && y_dtype == MT_BF16)
-    add_ln_fwd_kernel<768, bf, bf><<<grid, 256, 0, st>>>(x, (const bf*)a, gamma, beta, x_out, (bf*)y, mean, rstd, rows, eps);
+    add_ln_fwd_kernel<768, bf, bf><<<grid, 256, 0, st>>>(x, (const bf*)a, abias, gamma, beta, x_out, (bf*)y, mean, rstd, rows, eps);
   else if (a_dtype == MT_F32 && y_dtype == MT_BF16)
-    add_ln_fwd_kernel<768, float, bf><<<grid, 256, 0, st>>>(x, (const float*)a, gamma, beta, x_out, (bf*)y, mean, rstd, rows, eps);
+    add_ln_fwd_kernel<768, float, bf><<<grid, 256, 0, st>>>(x, (const float*)a, abias, gamma, beta, x_out, (bf*)y, mean, rstd, rows, eps);
   else
-    add_ln_fwd_kernel<768, bf, float><<<grid, 256, 0, st>>>(x, (const bf*)a, gamma, beta, x_out, (float*)y, mean, rstd, rows, eps);
+    add_ln_fwd_kernel<768, bf, float><<<grid, 256, 0, st>>>(x, (const bf*)a, abias, gamma, beta, x_out, (float*)y, mean, rstd, rows, eps);
   return check_launch("add_ln_fwd_kernel");
 }
 
@@ -571,6 +614,19 @@ extern "C" int mt_gated_residual_bwd(const float* dy, const float* a, const void
   else
     gated_residual_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dy, a, (const __nv_bfloat16*)b, gate, da, (__nv_bfloat16*)db, dgate, rows, (int)cols);
   return check_launch("gated_residual_bwd_kernel");
+}
+
+extern "C" int mt_residual_bias_add(const float* x, const void* a, int a_dtype, const float* bias, float* y,
+                                    int64_t rows, int64_t cols, void* stream) {
+  MT_REQUIRE(cols % 8 == 0, "residual_bias_add: cols must be a multiple of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows == 0) return 0;
+  const int grid = grid_for(rows * (cols / 8), 256);
+  if (a_dtype == MT_F32)
+    residual_bias_add_kernel<float><<<grid, 256, 0, st>>>(x, (const float*)a, bias, y, rows, (int)cols);
+  else
+    residual_bias_add_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, (const __nv_bfloat16*)a, bias, y, rows, (int)cols);
+  return check_launch("residual_bias_add_kernel");
 }
 
 extern "C" int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream) {

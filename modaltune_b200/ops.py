@@ -158,38 +158,47 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx_dtype, residual=None, want_wgrad:
     return dx, dgamma, dbeta
 
 
-def add_layernorm_fwd(x, a, gamma, beta, out_dtype, eps: float = LN_EPS):
-    """x_out = x + a (fp32), y = LN(x_out)."""
+def add_layernorm_fwd(x, a, gamma, beta, out_dtype, eps: float = LN_EPS, abias=None):
+    """x_out = x + a [+ abias] (fp32), y = LN(x_out)."""
     rows, cols = x.shape
     assert x.dtype == torch.float32
     x_out = torch.empty_like(x)
     y = torch.empty((rows, cols), device=x.device, dtype=out_dtype)
     mean = torch.empty(rows, device=x.device, dtype=torch.float32)
     rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
-    rc = _lib.load().mt_add_layernorm_fwd(_p(x), _p(a), _dt(a), _p(gamma), _p(beta), _p(x_out), _p(y), _dt(y), _p(mean),
-                                          _p(rstd), rows, cols, eps, _stream())
+    rc = _lib.load().mt_add_layernorm_fwd(_p(x), _p(a), _dt(a), _p(abias), _p(gamma), _p(beta), _p(x_out), _p(y), _dt(y),
+                                          _p(mean), _p(rstd), rows, cols, eps, _stream())
     _check(rc, "mt_add_layernorm_fwd")
     return x_out, y, mean, rstd
 
 
-def gelu_ln_fwd(h, gamma, beta, out_dtype, eps: float = LN_EPS):
+def gelu_ln_fwd(h, gamma, beta, out_dtype, eps: float = LN_EPS, hbias=None):
     rows, cols = h.shape
     y = torch.empty((rows, cols), device=h.device, dtype=out_dtype)
     mean = torch.empty(rows, device=h.device, dtype=torch.float32)
     rstd = torch.empty(rows, device=h.device, dtype=torch.float32)
-    rc = _lib.load().mt_gelu_ln_fwd(_p(h), _dt(h), _p(gamma), _p(beta), _p(y), _dt(y), _p(mean), _p(rstd), rows, cols,
-                                    eps, _stream())
+    rc = _lib.load().mt_gelu_ln_fwd(_p(h), _dt(h), _p(hbias), _p(gamma), _p(beta), _p(y), _dt(y), _p(mean), _p(rstd), rows,
+                                    cols, eps, _stream())
     _check(rc, "mt_gelu_ln_fwd")
     return y, mean, rstd
 
 
-def gelu_ln_bwd(dy, h, gamma, mean, rstd, out_dtype):
+def gelu_ln_bwd(dy, h, gamma, mean, rstd, out_dtype, hbias=None):
     rows, cols = h.shape
     dh = torch.empty((rows, cols), device=h.device, dtype=out_dtype)
-    rc = _lib.load().mt_gelu_ln_bwd(_p(dy), _dt(dy), _p(h), _dt(h), _p(gamma), _p(mean), _p(rstd), _p(dh), _dt(dh),
-                                    rows, cols, _stream())
+    rc = _lib.load().mt_gelu_ln_bwd(_p(dy), _dt(dy), _p(h), _dt(h), _p(hbias), _p(gamma), _p(mean), _p(rstd), _p(dh),
+                                    _dt(dh), rows, cols, _stream())
     _check(rc, "mt_gelu_ln_bwd")
     return dh
+
+
+def residual_bias_add(x, a, bias):
+    """y = x + a + bias (fp32 residual stream)."""
+    rows, cols = x.shape
+    y = torch.empty_like(x)
+    rc = _lib.load().mt_residual_bias_add(_p(x), _p(a), _dt(a), _p(bias), _p(y), rows, cols, _stream())
+    _check(rc, "mt_residual_bias_add")
+    return y
 
 
 def dilated_attn_fwd(geom: Geometry, qkv: torch.Tensor, impl: int):
@@ -233,12 +242,12 @@ def dilated_attn_bwd(geom: Geometry, qkv, dattn, lse, delta_br, impl: int):
     """dattn [n_alloc, E] (rows >= N zero), merged lse [N, H], per-branch delta -> dqkv fp32 [N, 3E]."""
     N, E = geom.n_tokens, geom.heads * geom.head_dim
     assert dattn.shape[0] == geom.n_alloc, "dattn must have n_alloc rows (zero tail), see dilated_merge_ln_bwd"
-    dqkv = torch.empty((N, 3 * E), device=qkv.device, dtype=torch.float32)
+    dqkv = torch.empty((geom.n_alloc, 3 * E), device=qkv.device, dtype=torch.float32)  # rows >= N: reduce scratch
     with _timed("dilated_attn_bwd"):
         rc = _lib.load().mt_dilated_attn_bwd(geom.ref(), _p(qkv), qkv.stride(0), qkv.shape[0], _p(dattn), _p(lse),
                                              _p(delta_br), _dt(qkv), _p(dqkv), impl, _stream())
     _check(rc, "mt_dilated_attn_bwd", 2)
-    return dqkv
+    return dqkv[:N]
 
 
 def cross_attn_fwd(q, k, v, heads: int):
@@ -485,12 +494,14 @@ def _linear(x, w, b):
     return torch.nn.functional.linear(x, w, b)
 
 
-def _linear_f32out(x, w, b32):
-    """x @ w^T + b with 16-bit operands and an fp32 result (cuBLASLt bf16 x bf16 -> f32): every GEMM whose consumer is
-    an element-wise kernel keeps its fp32 accumulator instead of rounding the output to bf16."""
+def _linear_f32out(x, w):
+    """x @ w^T with 16-bit operands and an fp32 result (cuBLASLt bf16 x bf16 -> f32): every GEMM whose consumer is an
+    element-wise kernel keeps its fp32 accumulator instead of rounding the output to bf16.  No bias: cuBLAS has no
+    fused bias epilogue for this combination (it costs a broadcast copy + a beta pass), so the bias is added by the
+    consuming kernel."""
     if x.dtype == torch.float32:
-        return torch.nn.functional.linear(x, w, b32)
-    return torch.addmm(b32, x, w.t(), out_dtype=torch.float32)
+        return torch.nn.functional.linear(x, w)
+    return torch.mm(x, w.t(), out_dtype=torch.float32)
 
 
 def _matmul_f32out(a, b):
@@ -517,16 +528,16 @@ def encoder_layer_forward(x: torch.Tensor, W: FrozenLayerWeights, geom: Geometry
     del h1
     o_br, lse_br = dilated_attn_fwd(geom, qkv, impl[0])
     a_ln, _, lse, mean_a, rstd_a = dilated_merge_ln_fwd(geom, o_br, lse_br, W.ln_in[0], W.ln_in[1])
-    attn_out = _linear_f32out(a_ln, W.w_o, W.b_o)            # fp32 [N, 768]
+    attn_out = _linear_f32out(a_ln, W.w_o)                   # fp32 [N, 768], bias added by the consumer
     del a_ln
-    x1, h2, mean2, rstd2 = add_layernorm_fwd(x, attn_out, W.ln2[0], W.ln2[1], cdt)
+    x1, h2, mean2, rstd2 = add_layernorm_fwd(x, attn_out, W.ln2[0], W.ln2[1], cdt, abias=W.b_o)
     del attn_out
-    f1 = _linear_f32out(h2, W.w_1, W.b_1)                    # fp32 [N, 3072], kept for the backward
+    f1 = _linear_f32out(h2, W.w_1)                           # fp32 [N, 3072] WITHOUT fc1's bias, kept for the backward
     del h2
-    g, mean_f, rstd_f = gelu_ln_fwd(f1, W.ln_ffn[0], W.ln_ffn[1], cdt)
-    f2 = _linear_f32out(g, W.w_2, W.b_2)
+    g, mean_f, rstd_f = gelu_ln_fwd(f1, W.ln_ffn[0], W.ln_ffn[1], cdt, hbias=W.b_1)
+    f2 = _linear_f32out(g, W.w_2)
     del g
-    y = f2.add_(x1)
+    y = residual_bias_add(x1, f2, W.b_2)
     saved = (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f)
     return y, saved
 
@@ -538,7 +549,7 @@ def encoder_layer_backward(dy: torch.Tensor, saved, W: FrozenLayerWeights, geom:
     dy = dy.contiguous()
     d_f2 = dy if cdt == torch.float32 else cast(dy, cdt)
     dg = _matmul_f32out(d_f2, W.w_2)                                 # fp32 [N, 3072]
-    d_f1 = gelu_ln_bwd(dg, f1, W.ln_ffn[0], mean_f, rstd_f, cdt)
+    d_f1 = gelu_ln_bwd(dg, f1, W.ln_ffn[0], mean_f, rstd_f, cdt, hbias=W.b_1)
     del dg
     dh2 = _matmul_f32out(d_f1, W.w_1)                                # fp32 [N, 768]
     del d_f1

@@ -49,18 +49,23 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx_dtype, residual=None, want_wgrad=
     return dx, dg, db
 
 
-def add_layernorm_fwd(x, a, gamma, beta, out_dtype, eps=1e-5):
-    x_out = x + a.float()
+def add_layernorm_fwd(x, a, gamma, beta, out_dtype, eps=1e-5, abias=None):
+    x_out = x + a.float() + (abias if abias is not None else 0.0)
     y, mean, rstd = layernorm_fwd(x_out, gamma, beta, out_dtype, eps=eps)
     return x_out, y, mean, rstd
 
 
-def gelu_ln_fwd(h, gamma, beta, out_dtype, eps=1e-5):
-    return layernorm_fwd(F.gelu(h.float()), gamma, beta, out_dtype, eps=eps)
+def gelu_ln_fwd(h, gamma, beta, out_dtype, eps=1e-5, hbias=None):
+    hb = h.float() + (hbias if hbias is not None else 0.0)
+    return layernorm_fwd(F.gelu(hb), gamma, beta, out_dtype, eps=eps)
 
 
-def gelu_ln_bwd(dy, h, gamma, mean, rstd, out_dtype):
-    hf = h.float().detach().requires_grad_(True)
+def residual_bias_add(x, a, bias):
+    return x + a.float() + (bias if bias is not None else 0.0)
+
+
+def gelu_ln_bwd(dy, h, gamma, mean, rstd, out_dtype, hbias=None):
+    hf = (h.float() + (hbias if hbias is not None else 0.0)).detach().requires_grad_(True)
     with torch.enable_grad():
         u = F.gelu(hf)
         du, _ = _ln_bwd(dy, u.detach(), gamma, mean, rstd)
@@ -217,7 +222,7 @@ def gated_residual_bwd(dy, a, b, g32, out=None):
 
 _NAMES = ["layernorm_fwd", "layernorm_bwd", "add_layernorm_fwd", "gelu_ln_fwd", "gelu_ln_bwd", "dilated_attn_fwd",
           "dilated_merge_ln_fwd", "dilated_merge_ln_bwd", "dilated_attn_bwd", "cross_attn_fwd", "cross_attn_bwd",
-          "embed_assemble", "cast", "gated_residual_fwd", "gated_residual_bwd"]
+          "embed_assemble", "cast", "gated_residual_fwd", "gated_residual_bwd", "residual_bias_add"]
 
 
 @contextlib.contextmanager

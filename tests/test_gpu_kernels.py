@@ -58,10 +58,15 @@ def test_layernorm_fused_add_and_add_layernorm():
     y_c, _, _ = C.layernorm_fwd(x, gamma, beta, torch.float32, add=a)
     y, _, _ = ops.layernorm_fwd(x.to(DEV), gamma.to(DEV), beta.to(DEV), torch.float32, add=a.to(DEV))
     assert rel(y, y_c) < 2e-5
+    ab = torch.randn(768, generator=g)
     for adt in (torch.float32, torch.bfloat16):
-        xo_c, y_c, m_c, r_c = C.add_layernorm_fwd(x, a.to(adt), gamma, beta, adt)
-        xo, y, m, r = ops.add_layernorm_fwd(x.to(DEV), a.to(adt).to(DEV), gamma.to(DEV), beta.to(DEV), adt)
-        assert rel(xo, xo_c) < 1e-6 and rel(y, y_c) < tol(adt) and rel(m, m_c) < 1e-5 and rel(r, r_c) < 1e-4
+        for bias in (None, ab):
+            xo_c, y_c, m_c, r_c = C.add_layernorm_fwd(x, a.to(adt), gamma, beta, adt, abias=bias)
+            xo, y, m, r = ops.add_layernorm_fwd(x.to(DEV), a.to(adt).to(DEV), gamma.to(DEV), beta.to(DEV), adt,
+                                                abias=None if bias is None else bias.to(DEV))
+            assert rel(xo, xo_c) < 1e-6 and rel(y, y_c) < tol(adt) and rel(m, m_c) < 1e-5 and rel(r, r_c) < 1e-4
+        yb = ops.residual_bias_add(x.to(DEV), a.to(adt).to(DEV), ab.to(DEV))
+        assert rel(yb, C.residual_bias_add(x, a.to(adt), ab)) < 1e-6
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
@@ -75,6 +80,13 @@ def test_gelu_ln_fwd_bwd(dt):
     assert rel(y, y_c) < tol(dt) and rel(m, m_c) < 1e-4 and rel(r, r_c) < 1e-4
     dh_c = C.gelu_ln_bwd(dy, h, gamma, m_c, r_c, dt)
     dh = ops.gelu_ln_bwd(dy.to(DEV), h.to(DEV), gamma.to(DEV), m, r, dt)
+    assert rel(dh, dh_c) < tol(dt)
+    hb = torch.randn(3072, generator=g)   # bias of the producing GEMM folded into the kernels
+    y_c, m_c, r_c = C.gelu_ln_fwd(h, gamma, beta, dt, hbias=hb)
+    y, m, r = ops.gelu_ln_fwd(h.to(DEV), gamma.to(DEV), beta.to(DEV), dt, hbias=hb.to(DEV))
+    assert rel(y, y_c) < tol(dt) and rel(m, m_c) < 1e-4
+    dh_c = C.gelu_ln_bwd(dy, h, gamma, m_c, r_c, dt, hbias=hb)
+    dh = ops.gelu_ln_bwd(dy.to(DEV), h.to(DEV), gamma.to(DEV), m, r, dt, hbias=hb.to(DEV))
     assert rel(dh, dh_c) < tol(dt)
 
 

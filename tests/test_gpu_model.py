@@ -34,7 +34,7 @@ def _self_attention(layer, x, geom, cdt, impl):
     qkv = ops._qkv_project(x.to(cdt), W, geom)
     o_br, lse_br = ops.dilated_attn_fwd(geom, qkv, impl)
     a_ln, _, lse, mean, rstd = ops.dilated_merge_ln_fwd(geom, o_br, lse_br, W.ln_in[0], W.ln_in[1])
-    y = ops._linear_f32out(a_ln, W.w_o, W.b_o)
+    y = ops._linear_f32out(a_ln, W.w_o) + W.b_o
     return y, (W, qkv, o_br, lse_br, lse, mean, rstd)
 
 
