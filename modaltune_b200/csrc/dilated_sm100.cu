@@ -13,9 +13,10 @@
 // k-steps of 16) for S = Q K^T and N = 48 for O = P V, so no tensor-core work is spent on the padding columns.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-5 = softmax (one query
-// row per thread = one TMEM lane).  P goes to shared memory in the K-major SWIZZLE_128B layout and is the A operand of
-// the P V MMA; each P V result lands in its own TMEM tile and is folded into fp32 register accumulators with the usual
-// online-softmax rescale, so TMEM is never read-modify-written.
+// row per thread = one TMEM lane).  P is written back to TMEM as packed bf16 (tcgen05.st) and is the A operand of the
+// P V MMA straight from TMEM (no shared-memory round trip); each P V result lands in a TMEM tile of its own and is
+// folded into fp32 register accumulators with the usual online-softmax rescale, so no accumulator is ever
+// read-modify-written in TMEM.
 #include <cuda.h>
 
 #include <type_traits>
@@ -26,12 +27,23 @@
 namespace mt {
 using namespace sm100;
 
+// experiment-only phase tracing (compile with -DMT_DEBUG_TRACE): block 0 prints clock64 stamps of its first iterations
+#ifdef MT_DEBUG_TRACE
+#define MT_TRACE_DECL long long tr_[96]; int trn_ = 0; const bool tron_ = (blockIdx.x == 0);
+#define MT_TRACE(tag) do { if (tron_ && trn_ < 94) { tr_[trn_++] = (long long)(tag); tr_[trn_++] = clock64(); } } while (0)
+#define MT_TRACE_DUMP(who) do { if (tron_) for (int q_ = 0; q_ + 1 < trn_; q_ += 2) printf("%s %lld %lld\n", who, tr_[q_], tr_[q_ + 1] - tr_[1]); } while (0)
+#else
+#define MT_TRACE_DECL
+#define MT_TRACE(tag)
+#define MT_TRACE_DUMP(who)
+#endif
+
 static constexpr int DH = 48;            // head dim
 static constexpr int BT = 128;           // slots per tile (queries and keys)
 static constexpr int TILE_BYTES = BT * 128;  // [128 rows][128 B]: 64 bf16 columns per row, SWIZZLE_128B
 static constexpr int KV_STAGES = 2;
 static constexpr int FWD_THREADS = 192;
-static constexpr uint32_t TMEM_COLS = 256;  // S: [0,128)  O tiles: [128,192), [192,256)
+static constexpr uint32_t TMEM_COLS = 256;  // S: [0,128)  P (bf16 pairs): [128,192)  O tile: [192,256)
 
 struct TensorMaps {
   CUtensorMap m[MT_MAX_BRANCHES];
@@ -51,8 +63,7 @@ struct FwdSmem {
   static constexpr int Q = 0;
   static constexpr int K = Q + TILE_BYTES;
   static constexpr int V = K + KV_STAGES * TILE_BYTES;
-  static constexpr int P = V + KV_STAGES * TILE_BYTES;          // two K-blocks of [128 rows][128 B]
-  static constexpr int BAR = P + 2 * TILE_BYTES;
+  static constexpr int BAR = V + KV_STAGES * TILE_BYTES;
   // barriers (8 B each): q_full, kv_full[2], kv_empty[2], s_full, s_free, p_full, o_full[2]; then the TMEM pointer
   static constexpr int NBAR = 10;
   static constexpr int TMEM_PTR = BAR + NBAR * 8;
@@ -116,7 +127,8 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_s = tmem;
-  const uint32_t tmem_o = tmem + 128;
+  const uint32_t tmem_p = tmem + 128;  // P as the A operand of P V: lane = query row, column k/2 holds keys (k, k+1)
+  const uint32_t tmem_o = tmem + 192;
 
   if (warp == 0) {
     // ===== TMA producer ===============================================================================================
@@ -147,33 +159,37 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
       }
       __syncwarp();
     };
+    MT_TRACE_DECL
     mbar_wait(bar_q_full, 0);
     mbar_wait(bar_kv_full, 0);
     tc_fence_after();
+    MT_TRACE(0);
     issue_qk(0);
     for (int j = 0; j < n_kv; ++j) {
       if (j + 1 < n_kv) {
         mbar_wait(bar_kv_full + 8 * ((j + 1) & 1), ((j + 1) >> 1) & 1);
+        MT_TRACE(100 + j);
         mbar_wait(bar_s_free, j & 1);  // the softmax threads have read S_j out of TMEM
         tc_fence_after();
+        MT_TRACE(200 + j);
         issue_qk(j + 1);
       }
-      mbar_wait(bar_p_full, j & 1);    // P_j is in shared memory (and the O tile j&1 has been folded)
+      mbar_wait(bar_p_full, j & 1);    // P_j is in TMEM (and the O tile of P_{j-1} V_{j-1} has been folded)
       tc_fence_after();
+      MT_TRACE(300 + j);
       if (lane == 0) {
-        // O_tile = P_j V_j : A = P (K-major, two 64-key blocks), B = V (MN-major: keys are the rows of the tile)
+        // O_tile = P_j V_j : A = P straight from TMEM (16 keys = 8 packed columns per k-step), B = V in place as an
+        // MN-major operand (keys are the rows of the tile)
         const uint32_t va = sbase + FwdSmem::V + (j & 1) * TILE_BYTES;
-        const uint32_t od = tmem_o + (j & 1) * 64;
 #pragma unroll
-        for (int k = 0; k < BT / 16; ++k) {
-          const uint32_t pa = sbase + FwdSmem::P + (k >> 2) * TILE_BYTES + (k & 3) * 32;
-          umma_ss(od, umma_smem_desc(pa, 16, 1024), umma_smem_desc(va + k * 16 * 128, TILE_BYTES, 1024), IDESC_PV, k > 0);
-        }
+        for (int k = 0; k < BT / 16; ++k)
+          umma_ts(tmem_o, tmem_p + k * 8, umma_smem_desc(va + k * 16 * 128, TILE_BYTES, 1024), IDESC_PV, k > 0);
         umma_commit(bar_kv_empty + 8 * (j & 1));
-        umma_commit(bar_o_full + 8 * (j & 1));
+        umma_commit(bar_o_full);
       }
       __syncwarp();
     }
+    if (lane == 0) { MT_TRACE_DUMP("mma"); }
   } else {
     // ===== softmax: one query row per thread ==========================================================================
     const int lane_grp = warp & 3;                    // TMEM lanes this warp may touch: [32*lane_grp, +32)
@@ -183,16 +199,14 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
     float o_acc[DH];
 #pragma unroll
     for (int i = 0; i < DH; ++i) o_acc[i] = 0.f;
-    uint8_t* p_row = smem + FwdSmem::P + row * 128;
-    const int sw = row & 7;
 
     auto fold = [&](int j) {  // o_acc += O_tile(j)
-      mbar_wait(bar_o_full + 8 * (j & 1), (j >> 1) & 1);
+      mbar_wait(bar_o_full, j & 1);
       tc_fence_after();
       float t[16];
 #pragma unroll
       for (int c = 0; c < DH / 16; ++c) {
-        tmem_ld16(tmem_o + t_lane + (j & 1) * 64 + c * 16, t);
+        tmem_ld16(tmem_o + t_lane + c * 16, t);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] += t[i];
@@ -200,15 +214,21 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
     };
 
     const float scale_log2 = P.scale_log2;
+    MT_TRACE_DECL
     // one key tile: MASK = the tile holds slots past the segment's m (only ever the last tile of the loop)
     auto tile = [&](int j, auto mask_tag) {
       constexpr bool MASK = decltype(mask_tag)::value;
       const int kvalid = bg.m - j * BT;  // key slots of this tile that belong to the segment (>= 1)
+      MT_TRACE(1000 + j);
       mbar_wait(bar_s_full, j & 1);
       tc_fence_after();
+      MT_TRACE(1100 + j);
       // pass 1: row maximum
       float mx = -INFINITY;
       float sv[32];
+#ifdef MT_DEBUG_FWD_NOMAX
+      mx = 4.f;
+#else
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         tmem_ld32(tmem_s + t_lane + c * 32, sv);
@@ -216,15 +236,18 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
 #pragma unroll
         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (!MASK || c * 32 + i < kvalid) ? sv[i] : -INFINITY);
       }
+#endif
       const float m_new = fmaxf(m_run, mx);
       const float alpha = ex2((m_run - m_new) * scale_log2);
-      if (j > 0) fold(j - 1);  // O tile j-1 is relative to m_run; P's buffer is free once that MMA has completed
+      MT_TRACE(1200 + j);
+      if (j > 0) fold(j - 1);  // O tile j-1 is relative to m_run; P's columns are free once that MMA has completed
+      MT_TRACE(1300 + j);
 #pragma unroll
       for (int i = 0; i < DH; ++i) o_acc[i] *= alpha;
       l_run *= alpha;
       m_run = m_new;
       const float mb = m_new * scale_log2;
-      // pass 2: p = exp2(s * scale_log2 - mb), row sum, bf16 P into the swizzled K-major tile
+      // pass 2: p = exp2(s * scale_log2 - mb), row sum, bf16 P into TMEM
       float rs = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -246,23 +269,20 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
           rs += p0 + p1;
           pk[i >> 1] = pack_bf16(p0, p1);
         }
-        uint8_t* blk = p_row + (c >> 1) * TILE_BYTES;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = (c & 1) * 4 + q;
-          *reinterpret_cast<uint4*>(blk + ((chunk ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
+        tmem_st16(tmem_p + t_lane + c * 16, pk);  // 32 keys = 16 packed columns
       }
       l_run += rs;
-      fence_proxy_async_smem();  // generic-proxy stores of P -> visible to the tensor core (async proxy)
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar_p_full);
+      MT_TRACE(1400 + j);
     };
     for (int j = 0; j < n_kv; ++j) {
       if (bg.m - j * BT >= BT) tile(j, std::false_type{});
       else tile(j, std::true_type{});
     }
     fold(n_kv - 1);
+    if (warp == 2 && lane == 0) { MT_TRACE_DUMP("smx"); }
     // ---- epilogue: normalise and write the compact per-branch output ---------------------------------------------
     const int slot = q0 + row;
     const int pos = s * bg.g + off + slot * bg.r;
@@ -558,22 +578,29 @@ dilated_bwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
       }
       __syncwarp();
     };
+    MT_TRACE_DECL
     mbar_wait(bar_kv_full, 0);
     mbar_wait(bar_qdo_full, 0);
     tc_fence_after();
+    MT_TRACE(0);
     issue_s_dp(0);
     for (int i = 0; i < n_q; ++i) {
       mbar_wait(bar_s_free, i & 1);  // S_i / dP_i are in registers
+      MT_TRACE(100 + i);
       if (i + 1 < n_q) {
         mbar_wait(bar_qdo_full + 8 * ((i + 1) & 1), ((i + 1) >> 1) & 1);
         tc_fence_after();
+        MT_TRACE(200 + i);
         issue_s_dp(i + 1);
       }
       mbar_wait(bar_pds_full, i & 1);  // P_i, dS_i are in shared memory
+      MT_TRACE(300 + i);
       if (i >= 2) mbar_wait(bar_dq_free + 8 * (i & 1), ((i - 2) >> 1) & 1);  // dQ tile i&1 has been drained
       tc_fence_after();
+      MT_TRACE(400 + i);
       if (lane == 0) {
         const uint32_t q = sbase + BwdSmem::Q + (i & 1) * TILE_BYTES, g = sbase + BwdSmem::DO + (i & 1) * TILE_BYTES;
+#ifndef MT_DEBUG_BWD_NO_T
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k)  // contraction over the 128 queries (tile rows): 16 rows = 2048 B per step
           umma_ss(tm_dv, umma_smem_desc(sP + k * 2048, TILE_BYTES, 1024), umma_smem_desc(g + k * 2048, TILE_BYTES, 1024),
@@ -582,15 +609,19 @@ dilated_bwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
         for (int k = 0; k < BT / 16; ++k)
           umma_ss(tm_dk, umma_smem_desc(sDS + k * 2048, TILE_BYTES, 1024), umma_smem_desc(q + k * 2048, TILE_BYTES, 1024),
                   IDESC_T, (i > 0) || (k > 0));
+#endif
+#ifndef MT_DEBUG_BWD_NO_DQ_MMA
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k)  // contraction over the 128 keys: dS K-major (two 64-key blocks)
           umma_ss(tm_dq + (i & 1) * 64, umma_smem_desc(sDS + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
                   umma_smem_desc(sK + k * 2048, TILE_BYTES, 1024), IDESC_DQ, k > 0);
+#endif
         umma_commit(bar_qdo_empty + 8 * (i & 1));
         umma_commit(bar_dq_full + 8 * (i & 1));
       }
       __syncwarp();
     }
+    if (lane == 0) { MT_TRACE_DUMP("mma"); }
   } else {
     // ===== compute: thread = (query row, 32-key quarter) ===============================================================
     const int cw = warp - 2;
@@ -645,18 +676,22 @@ dilated_bwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
     };
     float l_next, d_next;
     load_stats(0, l_next, d_next);
+    MT_TRACE_DECL
     for (int i = 0; i < n_q; ++i) {
       const float l2 = l_next * LOG2E;
       const float de = d_next;
       load_stats(i + 1, l_next, d_next);
+      MT_TRACE(1000 + i);
       mbar_wait(bar_s_full, i & 1);
       tc_fence_after();
+      MT_TRACE(1100 + i);
       float sv[32], dp[32];
       tmem_ld32(tm_s + t_lane + quarter * 32, sv);
       tmem_ld32(tm_dp + t_lane + quarter * 32, dp);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(bar_s_free);
+      MT_TRACE(1200 + i);
       uint32_t pk[16], dk[16];
       const float nde = -de * sc;  // dS = p * (dp - delta) * scale = p * fma(dp, scale, -delta * scale)
       if (kvalid >= BT) {
@@ -678,7 +713,9 @@ dilated_bwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
         }
       }
       // P / dS buffers are free once the MMAs of pair i-1 have completed (that is what dq_full(i-1) tracks)
+      MT_TRACE(1300 + i);
       if (i > 0) mbar_wait(bar_dq_full + 8 * ((i - 1) & 1), ((i - 1) >> 1) & 1);
+      MT_TRACE(1400 + i);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int chunk = (((quarter & 1) * 4 + q) ^ sw) << 4;
@@ -687,9 +724,12 @@ dilated_bwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
       }
       fence_proxy_async_smem();
       mbar_arrive(bar_pds_full);
+      MT_TRACE(1500 + i);
       if (i > 0) drain_dq(i - 1);
+      MT_TRACE(1600 + i);
     }
     drain_dq(n_q - 1);
+    if (cw == 0 && lane == 0) { MT_TRACE_DUMP("cmp"); }
     if (issuer) bulk_wait_group_all();
     // ---- dK / dV of this key tile: the last dq_full also covers the last dV / dK MMAs ---------------------------------
     {

@@ -41,7 +41,7 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 
 // y = LN(f(x)) * gamma + beta (+ add[row % add_rows]);  f = identity or GELU
 template <int COLS, typename TX, typename TY, typename TA, bool GELU>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ xbias,
+__global__ void __launch_bounds__(256, 2) ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ xbias,
                                                      const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, const TA* __restrict__ add,
                                                      int64_t add_rows, TY* __restrict__ y, float* __restrict__ mean,
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, c
 
 // dx = [gelu'(x)] * rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ residual), g = dy * gamma, xhat = (f(x) - mean) * rstd
 template <int COLS, typename TDY, typename TX, typename TR, typename TDX, bool GELU, bool WGRAD>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
+__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
                                                      const float* __restrict__ xbias,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const TR* __restrict__ residual,
