@@ -40,17 +40,18 @@ def compute_dtype() -> torch.dtype:
 
 
 # what "auto" resolves to in bf16 mode, per direction (flipped to 1 as the tcgen05 kernels are validated on B200)
-AUTO_IMPL = {"fwd": 1, "bwd": 1}
+AUTO_IMPL = {"fwd": 1, "bwd": 2}
 
 
 def attn_impl(direction: str = "fwd") -> int:
-    """0 = SIMT, 1 = tcgen05 (the ``impl`` argument of mt_dilated_attn_{fwd,bwd})."""
+    """The ``impl`` argument of mt_dilated_attn_{fwd,bwd}: 0 = SIMT, 1 = tcgen05 (operands staged in shared memory),
+    2 = tcgen05 backward in the transposed formulation with its A operands in TMEM."""
     impl = _state["attn_impl"]
     if impl == "simt" or _state["mode"] == "fp32":
         if impl == "sm100":
             raise RuntimeError("the tcgen05 dilated-attention kernels compute in bf16; fp32 mode needs attn_impl simt/auto")
         return 0
-    return 1 if impl == "sm100" else AUTO_IMPL[direction]
+    return AUTO_IMPL[direction]
 
 
 @contextlib.contextmanager

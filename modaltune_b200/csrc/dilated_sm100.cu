@@ -467,17 +467,6 @@ struct BwdSmem {
   static constexpr int TOTAL = TMEM_PTR + 16;
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(taddr)
-               : "memory");
-}
-
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 dilated_bwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ TensorMaps do_maps,
                          const __grid_constant__ TensorMaps dq_maps, const Sm100Params P, const float* __restrict__ lse, const float* __restrict__ delta_br,
@@ -784,6 +773,393 @@ int dilated_attn_bwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int
   dilated_bwd_sm100_kernel<<<P.item_prefix[P.geo.nb], BWD_THREADS, BwdSmem::TOTAL, st>>>(maps, do_maps, dq_maps, P, lse,
                                                                                        delta_br, dqkv, flag);
   return check_launch("dilated_bwd_sm100_kernel");
+}
+
+// =====================================================================================================================
+// backward, second version: transposed formulation with the A operands in TMEM
+// =====================================================================================================================
+// The first version is bound by SHARED-MEMORY bandwidth (P and dS written to smem, re-read as A operands of three N = 48
+// MMAs, dQ staged through smem: ~320 KB of smem traffic per tile pair against 128 B/clk).  Here the CTA (one key tile)
+// computes the TRANSPOSED tiles, keys on the TMEM lanes, in half tiles of 64 queries:
+//     S^T  = K  Q_h^T      dP^T = V dO_h^T        A = K / V resident in TMEM (copied once), B = Q / dO half tile
+//     P^T  = exp(S^T scale - lse[q])              dS^T = P^T (dP^T - delta[q]) scale       (per-query stats from smem)
+//     dV  += P^T dO_h      dK  += dS^T Q_h        A = P^T / dS^T as packed bf16 written back to TMEM over the very
+//                                                 columns each thread has just read (tcgen05.st), B in place (MN-major)
+//     dQ   = dS K  (once per 128 queries)         A = dS^T tile in smem read as an MN-major operand, B = K in place
+// S^T / dP^T are double buffered in TMEM (2 x 128 columns), so the MMAs of half g+1 overlap the exponentials of half g.
+// Shared-memory traffic per 128-query tile drops to ~150 KB; dQ goes out with red.global.add.v4.f32 from registers.
+static constexpr int BWD2_THREADS = 64 + 512 + 128;  // TMA, MMA, 16 compute warps, 4 statistics / dQ-drain warps
+struct Bwd2Smem {
+  static constexpr int K = 0;
+  static constexpr int V = K + TILE_BYTES;
+  static constexpr int NQ = 3;                             // Q / dO stages (the TMA latency of a tile is ~2 tile times)
+  static constexpr int Q = V + TILE_BYTES;                 // [NQ]
+  static constexpr int DO = Q + NQ * TILE_BYTES;           // [NQ]
+  static constexpr int DS = DO + NQ * TILE_BYTES;          // [2] dS^T tiles: [128 key rows][2 blocks of 64 queries]
+  static constexpr int NSTAT = 8;                          // per-query stats ring (written 3 tiles ahead)
+  static constexpr int STATS = DS + 4 * TILE_BYTES;        // [NSTAT][2][128] floats: lse * log2e, -delta * scale
+  static constexpr int BAR = STATS + NSTAT * 2 * BT * 4;
+  // kv_full, st_full[2], pt_full[2], dq_full, dq_free, kvt_full, all_done, qdo_full[NQ], qdo_empty[NQ], stats_full[NSTAT]
+  static constexpr int NBAR = 9 + 2 * NQ + NSTAT;
+  static constexpr int TMEM_PTR = BAR + NBAR * 8;
+  static constexpr int TOTAL = TMEM_PTR + 16;
+};
+
+__global__ void __launch_bounds__(BWD2_THREADS, 1)
+dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ TensorMaps do_maps,
+                          const Sm100Params P, const float* __restrict__ lse, const float* __restrict__ delta_br,
+                          float* __restrict__ dqkv, int* __restrict__ err_flag) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((sbase & 1023u) != 0) {
+    if (threadIdx.x == 0) atomicExch(err_flag, 1);
+    return;
+  }
+  int oi = 0;
+  while (oi + 1 < P.geo.nb && (int)blockIdx.x >= P.item_prefix[oi + 1]) ++oi;
+  const int b = P.order[oi];
+  const BranchGeom bg = P.geo.b[b];
+  int local = blockIdx.x - P.item_prefix[oi];
+  const int kt = local % P.tiles[b];
+  local /= P.tiles[b];
+  const int h = local % P.geo.H;
+  const int s = local / P.geo.H;
+  const int H = P.geo.H, N = P.geo.N, E = H * DH;
+  const int off = (h * bg.r) / H;
+  const int jseg = (s * bg.g) / bg.r;
+  const int n_q = P.tiles[b];
+  const int k0 = kt * BT;
+  const int seg_end = min(N, (s + 1) * bg.g);
+  const int slot_h = h - off * bg.hpb;
+
+  constexpr int NQ = Bwd2Smem::NQ;
+  const uint32_t bar_kv_full = sbase + Bwd2Smem::BAR + 0;
+  const uint32_t bar_st_full = sbase + Bwd2Smem::BAR + 8;      // [2]
+  const uint32_t bar_pt_full = sbase + Bwd2Smem::BAR + 24;     // [2]
+  const uint32_t bar_dq_full = sbase + Bwd2Smem::BAR + 40;
+  const uint32_t bar_dq_free = sbase + Bwd2Smem::BAR + 48;
+  const uint32_t bar_kvt_full = sbase + Bwd2Smem::BAR + 56;
+  const uint32_t bar_done = sbase + Bwd2Smem::BAR + 64;        // every MMA of the CTA has completed
+  const uint32_t bar_qdo_full = sbase + Bwd2Smem::BAR + 72;    // [NQ]
+  const uint32_t bar_qdo_empty = bar_qdo_full + 8 * NQ;        // [NQ]
+  const uint32_t bar_stats_full = bar_qdo_empty + 8 * NQ;      // [NSTAT]
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Bwd2Smem::TMEM_PTR);
+  constexpr int NCOMP = 512;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_st_full + 8 * i, 1);
+      mbar_init(bar_pt_full + 8 * i, NCOMP);
+    }
+    for (int i = 0; i < NQ; ++i) {
+      mbar_init(bar_qdo_full + 8 * i, 1);
+      mbar_init(bar_qdo_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < Bwd2Smem::NSTAT; ++i) mbar_init(bar_stats_full + 8 * i, 128);
+    mbar_init(bar_dq_full, 1);
+    mbar_init(bar_dq_free, 128);
+    mbar_init(bar_kvt_full, 256);
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.m[b]);
+    tma_prefetch_desc(&do_maps.m[b]);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // columns: [0,64) S^T buf0 | [64,128) dP^T buf0 | [128,192) S^T buf1 | [192,256) dP^T buf1 | dV 256 | dK 320 | dQ 384
+  //          K (bf16 pairs) 448..471 | V 480..503
+  const uint32_t tm_dv = tmem + 256, tm_dk = tmem + 320, tm_dq = tmem + 384, tm_k = tmem + 448, tm_v = tmem + 480;
+
+  if (warp == 0) {
+    // ===== TMA producer ===============================================================================================
+    if (lane == 0) {
+      const void* map = &maps.m[b];
+      const void* dmap = &do_maps.m[b];
+      mbar_expect_tx(bar_kv_full, 2 * TILE_BYTES);
+      tma_load_3d(sbase + Bwd2Smem::K, map, bar_kv_full, E + h * DH, off, jseg + k0);
+      tma_load_3d(sbase + Bwd2Smem::V, map, bar_kv_full, 2 * E + h * DH, off, jseg + k0);
+      for (int i = 0; i < n_q; ++i) {
+        const int st = i % NQ, use = i / NQ;
+        mbar_wait(bar_qdo_empty + 8 * st, (use & 1) ^ 1);
+        mbar_expect_tx(bar_qdo_full + 8 * st, 2 * TILE_BYTES);
+        tma_load_3d(sbase + Bwd2Smem::Q + st * TILE_BYTES, map, bar_qdo_full + 8 * st, h * DH, off, jseg + i * BT);
+        tma_load_3d(sbase + Bwd2Smem::DO + st * TILE_BYTES, dmap, bar_qdo_full + 8 * st, h * DH, off, jseg + i * BT);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =================================================================================================
+    constexpr uint32_t IDESC_ST = umma_idesc_bf16(BT, 64, 0, 0);    // A = K / V (TMEM), B = Q / dO half tile (K-major)
+    constexpr uint32_t IDESC_TS = umma_idesc_bf16(BT, DH, 0, 1);    // A = P^T / dS^T (TMEM), B = dO / Q (MN-major)
+    constexpr uint32_t IDESC_DQ = umma_idesc_bf16(BT, DH, 1, 1);    // A = dS^T tile (smem, MN-major), B = K (MN-major)
+    const uint32_t sK = sbase + Bwd2Smem::K;
+    const int n_half = 2 * n_q;
+    auto issue_st = [&](int g) {  // S^T and dP^T of half tile g into TMEM buffer g & 1
+      if (lane == 0) {
+        const int i = g >> 1, hh = g & 1;
+        const uint32_t q = sbase + Bwd2Smem::Q + (i % NQ) * TILE_BYTES + hh * 64 * 128;
+        const uint32_t d = sbase + Bwd2Smem::DO + (i % NQ) * TILE_BYTES + hh * 64 * 128;
+        const uint32_t ts = tmem + (g & 1) * 128, td = ts + 64;
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_ts(ts, tm_k + k * 8, umma_smem_desc(q + k * 32, 16, 1024), IDESC_ST, k > 0);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_ts(td, tm_v + k * 8, umma_smem_desc(d + k * 32, 16, 1024), IDESC_ST, k > 0);
+        umma_commit(bar_st_full + 8 * (g & 1));
+      }
+      __syncwarp();
+    };
+    MT_TRACE_DECL
+    mbar_wait(bar_kvt_full, 0);       // K and V are in TMEM
+    mbar_wait(bar_qdo_full, 0);
+    tc_fence_after();
+    MT_TRACE(0);
+    issue_st(0);
+    issue_st(1);
+    for (int g = 0; g < n_half; ++g) {
+      const int i = g >> 1, hh = g & 1;
+      mbar_wait(bar_pt_full + 8 * (g & 1), (g >> 1) & 1);   // P^T, dS^T of half g are in TMEM (+ dS^T half in smem)
+      tc_fence_after();
+      MT_TRACE(100 + g);
+      if (lane == 0) {
+        const uint32_t q = sbase + Bwd2Smem::Q + (i % NQ) * TILE_BYTES + hh * 64 * 128;
+        const uint32_t d = sbase + Bwd2Smem::DO + (i % NQ) * TILE_BYTES + hh * 64 * 128;
+        const uint32_t ts = tmem + (g & 1) * 128, td = ts + 64;
+        // packed P^T / dS^T: query pair (2c, 2c+1) of 16-query quarter qq sits in column 16*qq + c of its buffer
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // 64 queries = 4 k-steps of 16 (rows of the dO / Q half tile: 2048 B each)
+          umma_ts(tm_dv, ts + k * 16, umma_smem_desc(d + k * 2048, TILE_BYTES, 1024), IDESC_TS, (g > 0) || (k > 0));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ts(tm_dk, td + k * 16, umma_smem_desc(q + k * 2048, TILE_BYTES, 1024), IDESC_TS, (g > 0) || (k > 0));
+        if (hh == 1) umma_commit(bar_qdo_empty + 8 * (i % NQ));   // last readers of this Q / dO stage (dQ reads K, dS)
+      }
+      __syncwarp();
+      if (g + 2 < n_half) {          // the buffer is free once the MMAs above have consumed it (the pipe is in order)
+        if (((g + 2) & 1) == 0) mbar_wait(bar_qdo_full + 8 * (((g + 2) >> 1) % NQ), (((g + 2) >> 1) / NQ) & 1);
+        tc_fence_after();
+        MT_TRACE(200 + g);
+        issue_st(g + 2);
+      }
+      if (hh == 1) {                 // both halves of query tile i are done: dQ_i = dS_i K
+        if (i > 0) mbar_wait(bar_dq_free, (i - 1) & 1);
+        tc_fence_after();
+        MT_TRACE(300 + g);
+        if (lane == 0) {
+          const uint32_t ds = sbase + Bwd2Smem::DS + (i & 1) * 2 * TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BT / 16; ++k)   // contraction over the 128 keys = rows of the dS^T tile and of K
+            umma_ss(tm_dq, umma_smem_desc(ds + k * 2048, TILE_BYTES, 1024), umma_smem_desc(sK + k * 2048, TILE_BYTES, 1024),
+                    IDESC_DQ, k > 0);
+          umma_commit(bar_dq_full);
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) umma_commit(bar_done);
+    __syncwarp();
+    if (lane == 0) { MT_TRACE_DUMP("mma2"); }
+  } else if (warp < 18) {
+    // ===== compute: thread = (key row, 16-query quarter of the current half tile) =====================================
+    const int cw = warp - 2;
+    const int lane_grp = warp & 3;               // TMEM lanes of this warp
+    const int qq = cw >> 2;                      // query columns [16 qq, 16 qq + 16) of the half tile
+    const int row = lane_grp * 32 + lane;        // key slot k0 + row
+    const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
+    const int sw = row & 7;
+    const bool key_ok = (k0 + row) < bg.m;       // rows past m belong to the next segment: P = dS = 0
+    const float LOG2E = 1.4426950408889634f;
+    const float scale_log2 = P.scale_log2, sc = P.scale;
+    float* stats = reinterpret_cast<float*>(smem + Bwd2Smem::STATS);
+
+    // ---- K and V tiles -> TMEM (A operands of S^T / dP^T for the whole CTA): quarter 0 copies K, quarter 1 copies V
+    mbar_wait(bar_kv_full, 0);
+    if (qq < 2) {
+      const uint8_t* src = smem + (qq == 0 ? Bwd2Smem::K : Bwd2Smem::V) + row * 128;
+      uint32_t w[24];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const uint4 u = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));
+        w[4 * c] = u.x; w[4 * c + 1] = u.y; w[4 * c + 2] = u.z; w[4 * c + 3] = u.w;
+      }
+      const uint32_t dst = (qq == 0 ? tm_k : tm_v) + t_lane;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        uint32_t r8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r8[e] = w[8 * c + e];
+        tmem_st8(dst + c * 8, r8);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_kvt_full);
+    }
+
+    MT_TRACE_DECL
+    for (int i = 0; i < n_q; ++i) {
+      mbar_wait(bar_stats_full + 8 * (i % Bwd2Smem::NSTAT), (i / Bwd2Smem::NSTAT) & 1);
+      const float* st_l = stats + (i % Bwd2Smem::NSTAT) * 2 * BT;
+      uint8_t* ds_tile = smem + Bwd2Smem::DS + (i & 1) * 2 * TILE_BYTES;
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        const int g = 2 * i + hh;
+        const uint32_t ts = tmem + (g & 1) * 128 + t_lane + qq * 16, td = ts + 64;
+        float l2[16], nde[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 a = *reinterpret_cast<const float4*>(st_l + hh * 64 + qq * 16 + c * 4);
+          const float4 e = *reinterpret_cast<const float4*>(st_l + BT + hh * 64 + qq * 16 + c * 4);
+          l2[4 * c] = a.x; l2[4 * c + 1] = a.y; l2[4 * c + 2] = a.z; l2[4 * c + 3] = a.w;
+          nde[4 * c] = e.x; nde[4 * c + 1] = e.y; nde[4 * c + 2] = e.z; nde[4 * c + 3] = e.w;
+        }
+        MT_TRACE(1000 + g);
+        mbar_wait(bar_st_full + 8 * (g & 1), (g >> 1) & 1);
+        tc_fence_after();
+        MT_TRACE(1100 + g);
+        float sv[16], dp[16];
+        tmem_ld16(ts, sv);
+        tmem_ld16(td, dp);
+        tmem_ld_wait();
+        MT_TRACE(1200 + g);
+        uint32_t pk[8], dk[8];
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) {
+          float p0 = ex2(fmaf(sv[c], scale_log2, -l2[c]));
+          float p1 = ex2(fmaf(sv[c + 1], scale_log2, -l2[c + 1]));
+          if (!key_ok) p0 = p1 = 0.f;
+          pk[c >> 1] = pack_bf16(p0, p1);
+          dk[c >> 1] = pack_bf16(p0 * fmaf(dp[c], sc, nde[c]), p1 * fmaf(dp[c + 1], sc, nde[c + 1]));
+        }
+        MT_TRACE(1300 + g);
+        // packed results over the first 8 of the 16 columns this thread has just read (nobody else touches them)
+        tmem_st8(ts, pk);
+        tmem_st8(td, dk);
+        // dS^T half tile for dQ = dS K: [key row][64 queries] block hh, this thread's 16 queries = 2 swizzled chunks
+        uint8_t* drow = ds_tile + hh * TILE_BYTES + row * 128;
+        *reinterpret_cast<uint4*>(drow + (((2 * qq) ^ sw) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+        *reinterpret_cast<uint4*>(drow + (((2 * qq + 1) ^ sw) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+        tmem_st_wait();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_pt_full + 8 * (g & 1));
+        MT_TRACE(1400 + g);
+      }
+    }
+    if (cw == 0 && lane == 0) { MT_TRACE_DUMP("cmp2"); }
+    mbar_wait(bar_done, 0);                      // (a parity wait on dq_full would alias: these warps run 2 tiles ahead)
+    tc_fence_after();
+    // ---- dK / dV of this key tile (the last dq_full commit also covers the last dV / dK MMAs) --------------------------
+    {
+      float a[3][4], c2[3][4];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        tmem_ld4(tm_dk + t_lane + qq * 12 + c * 4, a[c]);
+        tmem_ld4(tm_dv + t_lane + qq * 12 + c * 4, c2[c]);
+      }
+      tmem_ld_wait();
+      const int slot = k0 + row;
+      const int pos = s * bg.g + off + slot * bg.r;
+      if (slot < bg.m && pos < seg_end) {
+        float* dst = dqkv + (int64_t)pos * (3 * E) + E + h * DH + qq * 12;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          red_add_v4(dst + c * 4, a[c][0], a[c][1], a[c][2], a[c][3]);
+          red_add_v4(dst + E + c * 4, c2[c][0], c2[c][1], c2[c][2], c2[c][3]);
+        }
+      }
+    }
+  } else {
+    // ===== statistics + dQ drain (4 warps, one query row per thread) ==================================================
+    const int lane_grp = warp & 3;
+    const int row = lane_grp * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
+    const float LOG2E = 1.4426950408889634f;
+    const float sc = P.scale;
+    float* stats = reinterpret_cast<float*>(smem + Bwd2Smem::STATS);
+    // per-query statistics of tile i -> smem ring (lse * log2e, -delta * scale): strided 4-byte global loads, issued
+    // two tiles ahead of their use by the compute warps
+    auto load_stats = [&](int i, float& l, float& d) {
+      const int slot = i * BT + row;
+      const int pos = s * bg.g + off + slot * bg.r;
+      const bool qok = i < n_q && slot < bg.m && pos < seg_end;
+      l = qok ? lse[(int64_t)pos * H + h] * LOG2E : INFINITY;   // +inf -> P = 0 for rows that do not exist
+      d = qok ? -delta_br[bg.lse_off + (int64_t)pos * bg.hpb + slot_h] * sc : 0.f;
+    };
+    auto store_stats = [&](int i, float l, float d) {
+      if (i < n_q) {
+        float* dst = stats + (i % Bwd2Smem::NSTAT) * 2 * BT;
+        dst[row] = l;
+        dst[BT + row] = d;
+        mbar_arrive(bar_stats_full + 8 * (i % Bwd2Smem::NSTAT));
+      }
+    };
+    float l_n, d_n;
+    for (int i = 0; i < 3; ++i) {
+      load_stats(i, l_n, d_n);
+      store_stats(i, l_n, d_n);
+    }
+    for (int i = 0; i < n_q; ++i) {
+      load_stats(i + 3, l_n, d_n);   // requested now, consumed after the drain below (hides the L2 latency)
+      // dQ of query tile i: TMEM -> registers -> red.global.add.v4.f32 (48 columns of this thread's query row)
+      mbar_wait(bar_dq_full, i & 1);
+      tc_fence_after();
+      float v[3][16];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tmem_ld16(tm_dq + t_lane + c * 16, v[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_dq_free);
+      const int slot = i * BT + row;
+      const int pos = s * bg.g + off + slot * bg.r;
+#ifdef MT_DEBUG_SKIP_DQ_RED
+      if (slot < 0) {
+#else
+      if (slot < bg.m && pos < seg_end) {
+#endif
+        float* dst = dqkv + (int64_t)pos * (3 * E) + h * DH;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) red_add_v4(dst + c * 16 + e, v[c][e], v[c][e + 1], v[c][e + 2], v[c][e + 3]);
+      }
+      store_stats(i + 3, l_n, d_n);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+int dilated_attn_bwd2_sm100(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,
+                            const void* dattn, const float* lse, const float* delta_br, float* dqkv, cudaStream_t st) {
+  Sm100Params P;
+  int rc = make_sm100_params(geom, &P);
+  if (rc) return rc;
+  MT_REQUIRE(n_alloc >= P.geo.N && n_alloc % 128 == 0, "dilated_attn_bwd: n_alloc must be a multiple of 128 >= n_tokens");
+  MT_REQUIRE(qkv_ld % 8 == 0 && ((uintptr_t)qkv & 15) == 0 && ((uintptr_t)dattn & 15) == 0 && ((uintptr_t)dqkv & 15) == 0,
+             "dilated_attn_bwd: buffers must be 16-byte aligned");
+  TensorMaps maps, do_maps;
+  memset(&maps, 0, sizeof(maps));
+  memset(&do_maps, 0, sizeof(do_maps));
+  const int64_t E = (int64_t)P.geo.H * DH;
+  for (int b = 0; b < P.geo.nb; ++b) {
+    rc = encode_branch_map(&maps.m[b], qkv, qkv_ld, n_alloc, P.geo.b[b].r);
+    if (rc) return rc;
+    rc = encode_branch_map(&do_maps.m[b], dattn, E, n_alloc, P.geo.b[b].r);
+    if (rc) return rc;
+  }
+  int* flag = error_flag();
+  MT_REQUIRE(flag != nullptr, "dilated_attn_bwd: cannot allocate the error flag");
+  MT_CUDA(cudaFuncSetAttribute(dilated_bwd2_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd2Smem::TOTAL));
+  dilated_bwd2_sm100_kernel<<<P.item_prefix[P.geo.nb], BWD2_THREADS, Bwd2Smem::TOTAL, st>>>(maps, do_maps, P, lse,
+                                                                                          delta_br, dqkv, flag);
+  return check_launch("dilated_bwd2_sm100_kernel");
 }
 
 }  // namespace mt

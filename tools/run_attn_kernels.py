@@ -6,6 +6,7 @@ from modaltune_b200 import ops
 from modaltune_b200.slide_encoder import DILATED_RATIO, optimal_segment_lengths
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 10001
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+bwd_impl = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 dev = "cuda"
 geom = ops.Geometry.get(N, optimal_segment_lengths(), DILATED_RATIO)
 g = torch.Generator().manual_seed(0)
@@ -22,7 +23,7 @@ for i in range(reps):
     y, _, lse, m, r = ops.dilated_merge_ln_fwd(geom, o, l, gamma, beta)
     dattn, delta = ops.dilated_merge_ln_bwd(geom, dy, o, l, gamma, m, r)
     ev[2].record()
-    dq = ops.dilated_attn_bwd(geom, qkv, dattn, lse, delta, 1)
+    dq = ops.dilated_attn_bwd(geom, qkv, dattn, lse, delta, bwd_impl)
     ev[3].record()
 torch.cuda.synchronize()
 f, b = ops.attention_flops(geom)
