@@ -31,7 +31,7 @@ using namespace sm100;
 #ifdef MT_DEBUG_TRACE
 #define MT_TRACE_DECL long long tr_[96]; int trn_ = 0; const bool tron_ = (blockIdx.x == 0);
 #define MT_TRACE(tag) do { if (tron_ && trn_ < 94) { tr_[trn_++] = (long long)(tag); tr_[trn_++] = clock64(); } } while (0)
-#define MT_TRACE_DUMP(who) do { if (tron_) for (int q_ = 0; q_ + 1 < trn_; q_ += 2) printf("%s %lld %lld\n", who, tr_[q_], tr_[q_ + 1] - tr_[1]); } while (0)
+#define MT_TRACE_DUMP(who) do { if (tron_) for (int q_ = 0; q_ + 1 < trn_; q_ += 2) printf("%s %lld %lld\n", who, tr_[q_], tr_[q_ + 1] & 0xffffffffll); } while (0)
 #else
 #define MT_TRACE_DECL
 #define MT_TRACE(tag)
@@ -75,7 +75,9 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
                          float* __restrict__ lse_br, int* __restrict__ err_flag) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
+  // roles by warp id: the scheduler favours high warp ids, so the latency-critical single-thread roles sit last
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int W_TMA = 4, W_MMA = 5;
   if ((sbase & 1023u) != 0) {  // SWIZZLE_128B tiles need 1024-byte alignment; never expected, but fail loudly
     if (threadIdx.x == 0) atomicExch(err_flag, 1);
     return;
@@ -118,7 +120,7 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
     fence_barrier_init();
     tma_prefetch_desc(&maps.m[b]);
   }
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tmem_alloc(smem_u32((const void*)tmem_slot), TMEM_COLS);
     tmem_relinquish();
   }
@@ -130,7 +132,7 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
   const uint32_t tmem_p = tmem + 128;  // P as the A operand of P V: lane = query row, column k/2 holds keys (k, k+1)
   const uint32_t tmem_o = tmem + 192;
 
-  if (warp == 0) {
+  if (warp == W_TMA) {
     // ===== TMA producer ===============================================================================================
     if (lane == 0) {
       const void* map = &maps.m[b];
@@ -144,7 +146,7 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
         tma_load_3d(sbase + FwdSmem::V + st * TILE_BYTES, map, bar_kv_full + 8 * st, 2 * E + h * DH, off, jseg + j * BT);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // ===== MMA issuer =================================================================================================
     constexpr uint32_t IDESC_QK = umma_idesc_bf16(BT, BT, 0, 0);
     constexpr uint32_t IDESC_PV = umma_idesc_bf16(BT, DH, 0, 1);
@@ -282,7 +284,7 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
       else tile(j, std::true_type{});
     }
     fold(n_kv - 1);
-    if (warp == 2 && lane == 0) { MT_TRACE_DUMP("smx"); }
+    if (warp == 0 && lane == 0) { MT_TRACE_DUMP("smx"); }
     // ---- epilogue: normalise and write the compact per-branch output ---------------------------------------------
     const int slot = q0 + row;
     const int pos = s * bg.g + off + slot * bg.r;
@@ -306,7 +308,7 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
   // ---- teardown ------------------------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == W_MMA) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -811,7 +813,10 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
                           float* __restrict__ dqkv, int* __restrict__ err_flag) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
+  // roles by warp id: compute 0-15, statistics / dQ drain 16-19, TMA 20, MMA 21 (the scheduler favours high warp ids:
+  // the single-thread MMA issuer must never starve behind the math warps of its sub-partition)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int W_TMA = 20, W_MMA = 21, W_EPI = 16;
   if ((sbase & 1023u) != 0) {
     if (threadIdx.x == 0) atomicExch(err_flag, 1);
     return;
@@ -851,7 +856,7 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
     mbar_init(bar_kv_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_st_full + 8 * i, 1);
-      mbar_init(bar_pt_full + 8 * i, NCOMP);
+      mbar_init(bar_pt_full + 8 * i, NCOMP / 2);   // one compute group per half-tile parity
     }
     for (int i = 0; i < NQ; ++i) {
       mbar_init(bar_qdo_full + 8 * i, 1);
@@ -866,7 +871,7 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
     tma_prefetch_desc(&maps.m[b]);
     tma_prefetch_desc(&do_maps.m[b]);
   }
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tmem_alloc(smem_u32((const void*)tmem_slot), 512);
     tmem_relinquish();
   }
@@ -878,7 +883,7 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
   //          K (bf16 pairs) 448..471 | V 480..503
   const uint32_t tm_dv = tmem + 256, tm_dk = tmem + 320, tm_dq = tmem + 384, tm_k = tmem + 448, tm_v = tmem + 480;
 
-  if (warp == 0) {
+  if (warp == W_TMA) {
     // ===== TMA producer ===============================================================================================
     if (lane == 0) {
       const void* map = &maps.m[b];
@@ -894,7 +899,7 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
         tma_load_3d(sbase + Bwd2Smem::DO + st * TILE_BYTES, dmap, bar_qdo_full + 8 * st, h * DH, off, jseg + i * BT);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // ===== MMA issuer =================================================================================================
     constexpr uint32_t IDESC_ST = umma_idesc_bf16(BT, 64, 0, 0);    // A = K / V (TMEM), B = Q / dO half tile (K-major)
     constexpr uint32_t IDESC_TS = umma_idesc_bf16(BT, DH, 0, 1);    // A = P^T / dS^T (TMEM), B = dO / Q (MN-major)
@@ -965,11 +970,15 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
     if (lane == 0) umma_commit(bar_done);
     __syncwarp();
     if (lane == 0) { MT_TRACE_DUMP("mma2"); }
-  } else if (warp < 18) {
-    // ===== compute: thread = (key row, 16-query quarter of the current half tile) =====================================
-    const int cw = warp - 2;
+  } else if (warp < W_EPI) {
+    // ===== compute: two groups of 8 warps ping-pong over the half tiles (group 0: even halves, group 1: odd halves), so
+    // one group's exponentials overlap the other group's TMEM / shared-memory traffic and barrier waits.
+    // thread = (key row, 32 of the 64 queries of its half tile, processed as two 16-query chunks)
+    const int cw = warp;
     const int lane_grp = warp & 3;               // TMEM lanes of this warp
-    const int qq = cw >> 2;                      // query columns [16 qq, 16 qq + 16) of the half tile
+    const int qq = cw >> 2;                      // used for the K / V copy and the final dK / dV columns
+    const int grp = cw >> 3;                     // which half of every query tile this warp works on
+    const int sub = (cw >> 2) & 1;               // which 32 queries of the half
     const int row = lane_grp * 32 + lane;        // key slot k0 + row
     const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
     const int sw = row & 7;
@@ -1006,44 +1015,47 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
       mbar_wait(bar_stats_full + 8 * (i % Bwd2Smem::NSTAT), (i / Bwd2Smem::NSTAT) & 1);
       const float* st_l = stats + (i % Bwd2Smem::NSTAT) * 2 * BT;
       uint8_t* ds_tile = smem + Bwd2Smem::DS + (i & 1) * 2 * TILE_BYTES;
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
+      {
+        const int hh = grp;
         const int g = 2 * i + hh;
-        const uint32_t ts = tmem + (g & 1) * 128 + t_lane + qq * 16, td = ts + 64;
-        float l2[16], nde[16];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float4 a = *reinterpret_cast<const float4*>(st_l + hh * 64 + qq * 16 + c * 4);
-          const float4 e = *reinterpret_cast<const float4*>(st_l + BT + hh * 64 + qq * 16 + c * 4);
-          l2[4 * c] = a.x; l2[4 * c + 1] = a.y; l2[4 * c + 2] = a.z; l2[4 * c + 3] = a.w;
-          nde[4 * c] = e.x; nde[4 * c + 1] = e.y; nde[4 * c + 2] = e.z; nde[4 * c + 3] = e.w;
-        }
         MT_TRACE(1000 + g);
         mbar_wait(bar_st_full + 8 * (g & 1), (g >> 1) & 1);
         tc_fence_after();
         MT_TRACE(1100 + g);
-        float sv[16], dp[16];
-        tmem_ld16(ts, sv);
-        tmem_ld16(td, dp);
-        tmem_ld_wait();
-        MT_TRACE(1200 + g);
-        uint32_t pk[8], dk[8];
+        uint8_t* drow = ds_tile + hh * TILE_BYTES + row * 128;
 #pragma unroll
-        for (int c = 0; c < 16; c += 2) {
-          float p0 = ex2(fmaf(sv[c], scale_log2, -l2[c]));
-          float p1 = ex2(fmaf(sv[c + 1], scale_log2, -l2[c + 1]));
-          if (!key_ok) p0 = p1 = 0.f;
-          pk[c >> 1] = pack_bf16(p0, p1);
-          dk[c >> 1] = pack_bf16(p0 * fmaf(dp[c], sc, nde[c]), p1 * fmaf(dp[c + 1], sc, nde[c + 1]));
+        for (int t = 0; t < 2; ++t) {
+          const int q16 = sub * 2 + t;           // 16-query chunk of the half tile
+          const uint32_t ts = tmem + (g & 1) * 128 + t_lane + q16 * 16, td = ts + 64;
+          float sv[16], dp[16];
+          tmem_ld16(ts, sv);
+          tmem_ld16(td, dp);
+          float l2[16], nde[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 a = *reinterpret_cast<const float4*>(st_l + hh * 64 + q16 * 16 + c * 4);
+            const float4 e = *reinterpret_cast<const float4*>(st_l + BT + hh * 64 + q16 * 16 + c * 4);
+            l2[4 * c] = a.x; l2[4 * c + 1] = a.y; l2[4 * c + 2] = a.z; l2[4 * c + 3] = a.w;
+            nde[4 * c] = e.x; nde[4 * c + 1] = e.y; nde[4 * c + 2] = e.z; nde[4 * c + 3] = e.w;
+          }
+          tmem_ld_wait();
+          uint32_t pk[8], dk[8];
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            float p0 = ex2(fmaf(sv[c], scale_log2, -l2[c]));
+            float p1 = ex2(fmaf(sv[c + 1], scale_log2, -l2[c + 1]));
+            if (!key_ok) p0 = p1 = 0.f;
+            pk[c >> 1] = pack_bf16(p0, p1);
+            dk[c >> 1] = pack_bf16(p0 * fmaf(dp[c], sc, nde[c]), p1 * fmaf(dp[c + 1], sc, nde[c + 1]));
+          }
+          // packed results over the first 8 of the 16 columns this thread has just read (nobody else touches them)
+          tmem_st8(ts, pk);
+          tmem_st8(td, dk);
+          // dS^T half tile for dQ = dS K: [key row][64 queries] block hh, 16 queries = 2 swizzled 16-byte chunks
+          *reinterpret_cast<uint4*>(drow + (((2 * q16) ^ sw) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+          *reinterpret_cast<uint4*>(drow + (((2 * q16 + 1) ^ sw) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
         }
         MT_TRACE(1300 + g);
-        // packed results over the first 8 of the 16 columns this thread has just read (nobody else touches them)
-        tmem_st8(ts, pk);
-        tmem_st8(td, dk);
-        // dS^T half tile for dQ = dS K: [key row][64 queries] block hh, this thread's 16 queries = 2 swizzled chunks
-        uint8_t* drow = ds_tile + hh * TILE_BYTES + row * 128;
-        *reinterpret_cast<uint4*>(drow + (((2 * qq) ^ sw) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
-        *reinterpret_cast<uint4*>(drow + (((2 * qq + 1) ^ sw) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
         tmem_st_wait();
         fence_proxy_async_smem();
         tc_fence_before();
@@ -1051,7 +1063,7 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
         MT_TRACE(1400 + g);
       }
     }
-    if (cw == 0 && lane == 0) { MT_TRACE_DUMP("cmp2"); }
+    if ((cw == 0 || cw == 8) && lane == 0) { MT_TRACE_DUMP(cw == 0 ? "cmpA" : "cmpB"); }
     mbar_wait(bar_done, 0);                      // (a parity wait on dq_full would alias: these warps run 2 tiles ahead)
     tc_fence_after();
     // ---- dK / dV of this key tile (the last dq_full commit also covers the last dV / dK MMAs) --------------------------
@@ -1133,7 +1145,7 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == W_MMA) tmem_dealloc(tmem, 512);
 }
 
 int dilated_attn_bwd2_sm100(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,
