@@ -150,13 +150,18 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
     // ===== MMA issuer =================================================================================================
     constexpr uint32_t IDESC_QK = umma_idesc_bf16(BT, BT, 0, 0);
     constexpr uint32_t IDESC_PV = umma_idesc_bf16(BT, DH, 0, 1);
+    // descriptors are built once; inside the loops an MMA costs one UTCHMMA (+ a constant descriptor advance)
+    const uint64_t q_desc = umma_smem_desc(sbase + FwdSmem::Q, 16, 1024);
+    const uint64_t k_desc0 = umma_smem_desc(sbase + FwdSmem::K, 16, 1024);
+    const uint64_t k_desc1 = umma_smem_desc(sbase + FwdSmem::K + TILE_BYTES, 16, 1024);
+    const uint64_t v_desc0 = umma_smem_desc(sbase + FwdSmem::V, TILE_BYTES, 1024);
+    const uint64_t v_desc1 = umma_smem_desc(sbase + FwdSmem::V + TILE_BYTES, TILE_BYTES, 1024);
     auto issue_qk = [&](int j) {  // S = Q K_j^T : three k-steps of 16 inside the 128-byte swizzle atom
-      if (lane == 0) {
-        const uint32_t ka = sbase + FwdSmem::K + (j & 1) * TILE_BYTES;
+      if (elect_one()) {
+        const uint64_t kd = (j & 1) ? k_desc1 : k_desc0;
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
-          umma_ss(tmem_s, umma_smem_desc(sbase + FwdSmem::Q + k * 32, 16, 1024), umma_smem_desc(ka + k * 32, 16, 1024),
-                  IDESC_QK, k > 0);
+          umma_ss(tmem_s, umma_desc_adv(q_desc, k * 32), umma_desc_adv(kd, k * 32), IDESC_QK, k > 0);
         umma_commit(bar_s_full);
       }
       __syncwarp();
@@ -179,13 +184,13 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
       mbar_wait(bar_p_full, j & 1);    // P_j is in TMEM (and the O tile of P_{j-1} V_{j-1} has been folded)
       tc_fence_after();
       MT_TRACE(300 + j);
-      if (lane == 0) {
+      if (elect_one()) {
         // O_tile = P_j V_j : A = P straight from TMEM (16 keys = 8 packed columns per k-step), B = V in place as an
-        // MN-major operand (keys are the rows of the tile)
-        const uint32_t va = sbase + FwdSmem::V + (j & 1) * TILE_BYTES;
+        // MN-major operand (keys are the rows of the tile: 16 rows = 2048 B per k-step)
+        const uint64_t vd = (j & 1) ? v_desc1 : v_desc0;
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k)
-          umma_ts(tmem_o, tmem_p + k * 8, umma_smem_desc(va + k * 16 * 128, TILE_BYTES, 1024), IDESC_PV, k > 0);
+          umma_ts(tmem_o, tmem_p + k * 8, umma_desc_adv(vd, k * 2048), IDESC_PV, k > 0);
         umma_commit(bar_kv_empty + 8 * (j & 1));
         umma_commit(bar_o_full);
       }
@@ -904,18 +909,30 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
     constexpr uint32_t IDESC_ST = umma_idesc_bf16(BT, 64, 0, 0);    // A = K / V (TMEM), B = Q / dO half tile (K-major)
     constexpr uint32_t IDESC_TS = umma_idesc_bf16(BT, DH, 0, 1);    // A = P^T / dS^T (TMEM), B = dO / Q (MN-major)
     constexpr uint32_t IDESC_DQ = umma_idesc_bf16(BT, DH, 1, 1);    // A = dS^T tile (smem, MN-major), B = K (MN-major)
-    const uint32_t sK = sbase + Bwd2Smem::K;
     const int n_half = 2 * n_q;
+    // every descriptor is built once; inside the loops an MMA is one UTCHMMA plus a constant descriptor advance
+    uint64_t qk_desc[NQ], dk_desc[NQ], qm_desc[NQ], dm_desc[NQ];   // Q / dO stages as K-major and as MN-major operands
+#pragma unroll
+    for (int st = 0; st < NQ; ++st) {
+      qk_desc[st] = umma_smem_desc(sbase + Bwd2Smem::Q + st * TILE_BYTES, 16, 1024);
+      dk_desc[st] = umma_smem_desc(sbase + Bwd2Smem::DO + st * TILE_BYTES, 16, 1024);
+      qm_desc[st] = umma_smem_desc(sbase + Bwd2Smem::Q + st * TILE_BYTES, TILE_BYTES, 1024);
+      dm_desc[st] = umma_smem_desc(sbase + Bwd2Smem::DO + st * TILE_BYTES, TILE_BYTES, 1024);
+    }
+    const uint64_t k_mn_desc = umma_smem_desc(sbase + Bwd2Smem::K, TILE_BYTES, 1024);
+    const uint64_t ds_desc0 = umma_smem_desc(sbase + Bwd2Smem::DS, TILE_BYTES, 1024);
+    const uint64_t ds_desc1 = umma_smem_desc(sbase + Bwd2Smem::DS + 2 * TILE_BYTES, TILE_BYTES, 1024);
+    auto pick = [&](const uint64_t (&a)[NQ], int st) { return st == 0 ? a[0] : (st == 1 ? a[1] : a[2]); };
+    static_assert(NQ == 3, "pick() is written for three stages");
     auto issue_st = [&](int g) {  // S^T and dP^T of half tile g into TMEM buffer g & 1
-      if (lane == 0) {
-        const int i = g >> 1, hh = g & 1;
-        const uint32_t q = sbase + Bwd2Smem::Q + (i % NQ) * TILE_BYTES + hh * 64 * 128;
-        const uint32_t d = sbase + Bwd2Smem::DO + (i % NQ) * TILE_BYTES + hh * 64 * 128;
+      if (elect_one()) {
+        const int st = (g >> 1) % NQ, hh = g & 1;
+        const uint64_t q = umma_desc_adv(pick(qk_desc, st), hh * 64 * 128), d = umma_desc_adv(pick(dk_desc, st), hh * 64 * 128);
         const uint32_t ts = tmem + (g & 1) * 128, td = ts + 64;
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_ts(ts, tm_k + k * 8, umma_smem_desc(q + k * 32, 16, 1024), IDESC_ST, k > 0);
+        for (int k = 0; k < DH / 16; ++k) umma_ts(ts, tm_k + k * 8, umma_desc_adv(q, k * 32), IDESC_ST, k > 0);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_ts(td, tm_v + k * 8, umma_smem_desc(d + k * 32, 16, 1024), IDESC_ST, k > 0);
+        for (int k = 0; k < DH / 16; ++k) umma_ts(td, tm_v + k * 8, umma_desc_adv(d, k * 32), IDESC_ST, k > 0);
         umma_commit(bar_st_full + 8 * (g & 1));
       }
       __syncwarp();
@@ -932,18 +949,19 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
       mbar_wait(bar_pt_full + 8 * (g & 1), (g >> 1) & 1);   // P^T, dS^T of half g are in TMEM (+ dS^T half in smem)
       tc_fence_after();
       MT_TRACE(100 + g);
-      if (lane == 0) {
-        const uint32_t q = sbase + Bwd2Smem::Q + (i % NQ) * TILE_BYTES + hh * 64 * 128;
-        const uint32_t d = sbase + Bwd2Smem::DO + (i % NQ) * TILE_BYTES + hh * 64 * 128;
+      if (elect_one()) {
+        const int st = i % NQ;
+        const uint64_t q = umma_desc_adv(pick(qm_desc, st), hh * 64 * 128), d = umma_desc_adv(pick(dm_desc, st), hh * 64 * 128);
         const uint32_t ts = tmem + (g & 1) * 128, td = ts + 64;
-        // packed P^T / dS^T: query pair (2c, 2c+1) of 16-query quarter qq sits in column 16*qq + c of its buffer
+        // packed P^T / dS^T: query pair (2c, 2c+1) of 16-query quarter qq sits in column 16*qq + c of its buffer;
+        // 64 queries = 4 k-steps of 16 (rows of the dO / Q half tile: 2048 B each)
+        umma_ts(tm_dv, ts, d, IDESC_TS, g > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // 64 queries = 4 k-steps of 16 (rows of the dO / Q half tile: 2048 B each)
-          umma_ts(tm_dv, ts + k * 16, umma_smem_desc(d + k * 2048, TILE_BYTES, 1024), IDESC_TS, (g > 0) || (k > 0));
+        for (int k = 1; k < 4; ++k) umma_ts(tm_dv, ts + k * 16, umma_desc_adv(d, k * 2048), IDESC_TS, 1);
+        umma_ts(tm_dk, td, q, IDESC_TS, g > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ts(tm_dk, td + k * 16, umma_smem_desc(q + k * 2048, TILE_BYTES, 1024), IDESC_TS, (g > 0) || (k > 0));
-        if (hh == 1) umma_commit(bar_qdo_empty + 8 * (i % NQ));   // last readers of this Q / dO stage (dQ reads K, dS)
+        for (int k = 1; k < 4; ++k) umma_ts(tm_dk, td + k * 16, umma_desc_adv(q, k * 2048), IDESC_TS, 1);
+        if (hh == 1) umma_commit(bar_qdo_empty + 8 * st);   // last readers of this Q / dO stage (dQ reads K, dS)
       }
       __syncwarp();
       if (g + 2 < n_half) {          // the buffer is free once the MMAs above have consumed it (the pipe is in order)
@@ -956,18 +974,17 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
         if (i > 0) mbar_wait(bar_dq_free, (i - 1) & 1);
         tc_fence_after();
         MT_TRACE(300 + g);
-        if (lane == 0) {
-          const uint32_t ds = sbase + Bwd2Smem::DS + (i & 1) * 2 * TILE_BYTES;
+        if (elect_one()) {
+          const uint64_t ds = (i & 1) ? ds_desc1 : ds_desc0;
 #pragma unroll
           for (int k = 0; k < BT / 16; ++k)   // contraction over the 128 keys = rows of the dS^T tile and of K
-            umma_ss(tm_dq, umma_smem_desc(ds + k * 2048, TILE_BYTES, 1024), umma_smem_desc(sK + k * 2048, TILE_BYTES, 1024),
-                    IDESC_DQ, k > 0);
+            umma_ss(tm_dq, umma_desc_adv(ds, k * 2048), umma_desc_adv(k_mn_desc, k * 2048), IDESC_DQ, k > 0);
           umma_commit(bar_dq_full);
         }
         __syncwarp();
       }
     }
-    if (lane == 0) umma_commit(bar_done);
+    if (elect_one()) umma_commit(bar_done);
     __syncwarp();
     if (lane == 0) { MT_TRACE_DUMP("mma2"); }
   } else if (warp < W_EPI) {
@@ -1028,8 +1045,13 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
           const int q16 = sub * 2 + t;           // 16-query chunk of the half tile
           const uint32_t ts = tmem + (g & 1) * 128 + t_lane + q16 * 16, td = ts + 64;
           float sv[16], dp[16];
+#ifdef MT_DEBUG_NO_TMEM_LD
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { sv[c] = (float)(c + lane) * 0.01f; dp[c] = (float)(c - lane) * 0.01f; }
+#else
           tmem_ld16(ts, sv);
           tmem_ld16(td, dp);
+#endif
           float l2[16], nde[16];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -1049,11 +1071,17 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
             dk[c >> 1] = pack_bf16(p0 * fmaf(dp[c], sc, nde[c]), p1 * fmaf(dp[c + 1], sc, nde[c + 1]));
           }
           // packed results over the first 8 of the 16 columns this thread has just read (nobody else touches them)
+#ifndef MT_DEBUG_NO_TMEM_ST
           tmem_st8(ts, pk);
           tmem_st8(td, dk);
+#endif
+#ifndef MT_DEBUG_NO_DS_STS
           // dS^T half tile for dQ = dS K: [key row][64 queries] block hh, 16 queries = 2 swizzled 16-byte chunks
           *reinterpret_cast<uint4*>(drow + (((2 * q16) ^ sw) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
           *reinterpret_cast<uint4*>(drow + (((2 * q16 + 1) ^ sw) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+#else
+          if (pk[0] == 0x12345678u && dk[1] == 0x9abcdef0u) drow[0] = 1;
+#endif
         }
         MT_TRACE(1300 + g);
         tmem_st_wait();
@@ -1063,7 +1091,9 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
         MT_TRACE(1400 + g);
       }
     }
-    if ((cw == 0 || cw == 8) && lane == 0) { MT_TRACE_DUMP(cw == 0 ? "cmpA" : "cmpB"); }
+#ifdef MT_DEBUG_TRACE
+    if (lane == 0 && tron_) for (int q_ = 0; q_ + 1 < trn_; q_ += 2) printf("cmp%d %lld %lld\n", cw, tr_[q_], tr_[q_ + 1] & 0xffffffffll);
+#endif
     mbar_wait(bar_done, 0);                      // (a parity wait on dq_full would alias: these warps run 2 tiles ahead)
     tc_fence_after();
     // ---- dK / dV of this key tile (the last dq_full commit also covers the last dV / dK MMAs) --------------------------
