@@ -18,7 +18,17 @@ import torch
 _state = {
     "mode": os.environ.get("MODALTUNE_B200_MODE", "bf16"),
     "attn_impl": os.environ.get("MODALTUNE_B200_ATTN", "auto"),
+    "pass_streams": os.environ.get("MODALTUNE_B200_PASS_STREAMS", "1") != "0",
 }
+
+
+def pass_streams() -> bool:
+    """Run the independent task passes of ``forward_tasks`` on separate CUDA streams."""
+    return _state["pass_streams"]
+
+
+def set_pass_streams(on: bool) -> None:
+    _state["pass_streams"] = bool(on)
 
 
 def set_mode(mode: str) -> None:

@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import config
 from .adapter_modules import (CrossAttentionLayer, Identity_mod, InteractionBlockWithCls_LongNetViT,
                               SelfAttentionLayer)
 from .gene_encoder import GeneEncoder_Group
@@ -149,8 +150,33 @@ class LongNetGeneAdapter(LongNetViT):
             return torch.cat([self._adapter_forward(x, coords, genes, clinical, t, None, None, None)
                               for t in task_tokens], 0)
         shared = self._shared_inputs(x, coords, genes)
-        return torch.cat([self._adapter_forward(None, None, None, clinical, t, None, None, None, shared=shared)
-                          for t in task_tokens], 0)
+        if not (config.pass_streams() and shared[0].is_cuda and len(task_tokens) > 1):
+            return torch.cat([self._adapter_forward(None, None, None, clinical, t, None, None, None, shared=shared)
+                              for t in task_tokens], 0)
+        # The task passes are independent until the loss: each one runs on its own CUDA stream (autograd replays the
+        # backward of every node on the stream of its forward), so kernels of different passes overlap -- the tails of
+        # the attention launches and the hundreds of tiny modal-token kernels fill each other's gaps.  Under CUDA-graph
+        # capture the forks become parallel branches of the graph.
+        cur = torch.cuda.current_stream()
+        streams = self._task_streams(len(task_tokens) - 1)
+        outs = [None] * len(task_tokens)
+        for k, t in enumerate(task_tokens):
+            if k == 0:
+                continue
+            st = streams[k - 1]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                outs[k] = self._adapter_forward(None, None, None, clinical, t, None, None, None, shared=shared)
+        outs[0] = self._adapter_forward(None, None, None, clinical, task_tokens[0], None, None, None, shared=shared)
+        for st in streams[:len(task_tokens) - 1]:
+            cur.wait_stream(st)
+        return torch.cat(outs, 0)
+
+    def _task_streams(self, n):
+        pool = self.__dict__.setdefault("_streams", [])
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream())
+        return pool
 
     def _modal_tokens(self, gene_tokens, clinical, task_token):
         """[1, M, 768] modal tokens: (clinical) | (task) | (gene cls) | 64 pathway tokens  (:257-266, 568-584)."""
