@@ -18,7 +18,8 @@ import torch
 _state = {
     "mode": os.environ.get("MODALTUNE_B200_MODE", "bf16"),
     "attn_impl": os.environ.get("MODALTUNE_B200_ATTN", "auto"),
-    "pass_streams": os.environ.get("MODALTUNE_B200_PASS_STREAMS", "1") != "0",
+    # experimental (off): ~4 % faster at 10k tiles, but the eager/graph equivalence test is not yet green with it
+    "pass_streams": os.environ.get("MODALTUNE_B200_PASS_STREAMS", "0") != "0",
 }
 
 

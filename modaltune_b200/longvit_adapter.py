@@ -168,8 +168,9 @@ class LongNetGeneAdapter(LongNetViT):
             with torch.cuda.stream(st):
                 outs[k] = self._adapter_forward(None, None, None, clinical, t, None, None, None, shared=shared)
         outs[0] = self._adapter_forward(None, None, None, clinical, task_tokens[0], None, None, None, shared=shared)
-        for st in streams[:len(task_tokens) - 1]:
-            cur.wait_stream(st)
+        for k in range(1, len(task_tokens)):
+            cur.wait_stream(streams[k - 1])
+            outs[k].record_stream(cur)   # allocated on the side stream, read by the cat below on the calling stream
         return torch.cat(outs, 0)
 
     def _task_streams(self, n):
