@@ -195,7 +195,9 @@ def test_dilated_attention_linearity_in_v_at_full_size():
 # ---------------------------------------------------------------------------------------------------------------------
 # tcgen05 / TMA dilated attention (impl = 1) against the fp32-math SIMT kernels and the oracle
 # ---------------------------------------------------------------------------------------------------------------------
-SM100_GEOMS = GEOMS + [(5793, None), (10001, None), (300, [128, 256, 512, 1024, 2048])]
+SM100_GEOMS = GEOMS + [(5793, None), (10001, None), (300, [128, 256, 512, 1024, 2048]),
+                       (32769, None),   # C3: 33 x 1024, 6 x 5792 and the 2 x 32768 branch whose tail segment is all padding
+                       (40001, None)]   # C5 upper end
 
 
 @pytest.mark.parametrize("N,sl", SM100_GEOMS)

@@ -209,3 +209,26 @@ def test_graphed_step_equals_eager_step(model):
     # fp32 atomics in the attention backward reorder between runs: equality up to that noise
     assert _cos(g_graph, g_eager) > 0.999999
     assert helpers.relerr(g_graph, g_eager) < 1e-3
+
+
+def test_variable_length_slides_and_pancancer_task_tokens():
+    """C5-style use: one model instance steps slides of different tile counts back to back (geometry, workspaces and
+    tensor maps are per call), and a 4-way task one-hot (pan-cancer, train_modaltune_pancancer.py) drives the same path."""
+    m4 = helpers.build_model(helpers.SMALL_GROUPS, multi_task=4, device=DEV)
+    eye = torch.eye(4, device=DEV)
+    outs = {}
+    for L in (2000, 777, 5793, 2000):
+        slide = train_step.slide_to_device(synthetic.synthetic_slide(L, seed=L, group_sizes=helpers.SMALL_GROUPS), DEV)
+        with config.using(mode="bf16"):
+            y = m4(x=slide["x"], coords=slide["coords"], genes=slide["genes"], clinical=slide["clinical"], task_token=eye[3])
+            y.square().sum().backward()
+        assert y.shape == (1, 256) and bool(torch.isfinite(y).all())
+        assert all(bool(torch.isfinite(p.grad).all()) for p in m4.parameters() if p.requires_grad)
+        outs.setdefault(L, []).append(y.detach().clone())
+    assert helpers.relerr(outs[2000][1], outs[2000][0]) < 1e-3     # same slide, same answer after other shapes ran
+    # fp32 oracle on the smallest one
+    slide = synthetic.synthetic_slide(777, seed=777, group_sizes=helpers.SMALL_GROUPS)
+    sd = {k: v.detach().cpu() for k, v in m4.state_dict().items()}
+    genes = [slide["genes"][i] for i in range(len(helpers.SMALL_GROUPS))]
+    want = O.adapter_forward(sd, slide["x"][0], slide["coords"][0], genes, slide["clinical"], torch.eye(4)[3])
+    assert helpers.relerr(outs[777][0].float().cpu(), want) < 2e-2
