@@ -233,9 +233,6 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
       // pass 1: row maximum
       float mx = -INFINITY;
       float sv[32];
-#ifdef MT_DEBUG_FWD_NOMAX
-      mx = 4.f;
-#else
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         tmem_ld32(tmem_s + t_lane + c * 32, sv);
@@ -243,7 +240,6 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
 #pragma unroll
         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (!MASK || c * 32 + i < kvalid) ? sv[i] : -INFINITY);
       }
-#endif
       const float m_new = fmaxf(m_run, mx);
       const float alpha = ex2((m_run - m_new) * scale_log2);
       MT_TRACE(1200 + j);
@@ -596,7 +592,6 @@ dilated_bwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
       MT_TRACE(400 + i);
       if (lane == 0) {
         const uint32_t q = sbase + BwdSmem::Q + (i & 1) * TILE_BYTES, g = sbase + BwdSmem::DO + (i & 1) * TILE_BYTES;
-#ifndef MT_DEBUG_BWD_NO_T
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k)  // contraction over the 128 queries (tile rows): 16 rows = 2048 B per step
           umma_ss(tm_dv, umma_smem_desc(sP + k * 2048, TILE_BYTES, 1024), umma_smem_desc(g + k * 2048, TILE_BYTES, 1024),
@@ -605,13 +600,10 @@ dilated_bwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
         for (int k = 0; k < BT / 16; ++k)
           umma_ss(tm_dk, umma_smem_desc(sDS + k * 2048, TILE_BYTES, 1024), umma_smem_desc(q + k * 2048, TILE_BYTES, 1024),
                   IDESC_T, (i > 0) || (k > 0));
-#endif
-#ifndef MT_DEBUG_BWD_NO_DQ_MMA
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k)  // contraction over the 128 keys: dS K-major (two 64-key blocks)
           umma_ss(tm_dq + (i & 1) * 64, umma_smem_desc(sDS + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
                   umma_smem_desc(sK + k * 2048, TILE_BYTES, 1024), IDESC_DQ, k > 0);
-#endif
         umma_commit(bar_qdo_empty + 8 * (i & 1));
         umma_commit(bar_dq_full + 8 * (i & 1));
       }
@@ -654,9 +646,7 @@ dilated_bwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
       named_bar_sync(1, NCOMP);
       if (issuer) {
         // rows of slots >= m (next segment) and of padded positions are exact zeros (P = 0 there); rows >= n_alloc clip
-#ifndef MT_DEBUG_SKIP_DQ_REDUCE
         tma_reduce_add_3d(&dq_maps.m[b], sbase + BwdSmem::DQ + (i & 1) * BwdSmem::DQ_BYTES, h * DH, off, jseg + i * BT);
-#endif
         bulk_commit_group();
       }
     };
@@ -947,8 +937,8 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
     for (int g = 0; g < n_half; ++g) {
       const int i = g >> 1, hh = g & 1;
       mbar_wait(bar_pt_full + 8 * (g & 1), (g >> 1) & 1);   // P^T, dS^T of half g are in TMEM (+ dS^T half in smem)
-      tc_fence_after();
       MT_TRACE(100 + g);
+      tc_fence_after();
       if (elect_one()) {
         const int st = i % NQ;
         const uint64_t q = umma_desc_adv(pick(qm_desc, st), hh * 64 * 128), d = umma_desc_adv(pick(dm_desc, st), hh * 64 * 128);
@@ -1045,13 +1035,8 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
           const int q16 = sub * 2 + t;           // 16-query chunk of the half tile
           const uint32_t ts = tmem + (g & 1) * 128 + t_lane + q16 * 16, td = ts + 64;
           float sv[16], dp[16];
-#ifdef MT_DEBUG_NO_TMEM_LD
-#pragma unroll
-          for (int c = 0; c < 16; ++c) { sv[c] = (float)(c + lane) * 0.01f; dp[c] = (float)(c - lane) * 0.01f; }
-#else
           tmem_ld16(ts, sv);
           tmem_ld16(td, dp);
-#endif
           float l2[16], nde[16];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -1071,17 +1056,11 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
             dk[c >> 1] = pack_bf16(p0 * fmaf(dp[c], sc, nde[c]), p1 * fmaf(dp[c + 1], sc, nde[c + 1]));
           }
           // packed results over the first 8 of the 16 columns this thread has just read (nobody else touches them)
-#ifndef MT_DEBUG_NO_TMEM_ST
           tmem_st8(ts, pk);
           tmem_st8(td, dk);
-#endif
-#ifndef MT_DEBUG_NO_DS_STS
           // dS^T half tile for dQ = dS K: [key row][64 queries] block hh, 16 queries = 2 swizzled 16-byte chunks
           *reinterpret_cast<uint4*>(drow + (((2 * q16) ^ sw) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
           *reinterpret_cast<uint4*>(drow + (((2 * q16 + 1) ^ sw) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
-#else
-          if (pk[0] == 0x12345678u && dk[1] == 0x9abcdef0u) drow[0] = 1;
-#endif
         }
         MT_TRACE(1300 + g);
         tmem_st_wait();
@@ -1159,11 +1138,7 @@ dilated_bwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
       mbar_arrive(bar_dq_free);
       const int slot = i * BT + row;
       const int pos = s * bg.g + off + slot * bg.r;
-#ifdef MT_DEBUG_SKIP_DQ_RED
-      if (slot < 0) {
-#else
       if (slot < bg.m && pos < seg_end) {
-#endif
         float* dst = dqkv + (int64_t)pos * (3 * E) + h * DH;
 #pragma unroll
         for (int c = 0; c < 3; ++c)

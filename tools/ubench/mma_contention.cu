@@ -26,7 +26,29 @@ __global__ void __launch_bounds__(32 * 17, 1) k(int reps, long long* out, float*
     const uint64_t v0 = umma_smem_desc(sbase + 65536, 16384, 1024);
     const uint64_t q0 = umma_smem_desc(sbase + 98304, 16, 1024);
     long long t0 = clock64(), t1 = 0;
-    if (elect_one()) {
+    if (BG == 5) {   // dQ-type: SS, A MN-major [key rows][128 queries] smem, B MN-major K tile, N = 48
+      constexpr uint32_t iddq = umma_idesc_bf16(128, 48, 1, 1);
+      const uint64_t a0 = umma_smem_desc(sbase, 16384, 1024), b0 = umma_smem_desc(sbase + 65536, 16384, 1024);
+      if (elect_one()) {
+        for (int r = 0; r < reps; r += 8) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) umma_ss(tm + 384, umma_desc_adv(a0, kk * 2048), umma_desc_adv(b0, kk * 2048), iddq, 1);
+        }
+        t1 = clock64();
+        umma_commit(smem_u32(&bar));
+      }
+    } else if (BG == 6) {   // forward S-type: SS K-major N=128, three k-steps
+      constexpr uint32_t ids = umma_idesc_bf16(128, 128, 0, 0);
+      const uint64_t a0 = umma_smem_desc(sbase, 16, 1024), b0 = umma_smem_desc(sbase + 65536, 16, 1024);
+      if (elect_one()) {
+        for (int r = 0; r < reps; r += 3) {
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk) umma_ss(tm, umma_desc_adv(a0, kk * 32), umma_desc_adv(b0, kk * 32), ids, 1);
+        }
+        t1 = clock64();
+        umma_commit(smem_u32(&bar));
+      }
+    } else if (elect_one()) {
       for (int r = 0; r < reps; r += 14) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) umma_ts(tm + 256 + (kk >> 2) * 64, tm + (kk & 3) * 16, umma_desc_adv(v0, kk * 2048), id48, 1);
@@ -92,5 +114,7 @@ int main() {
   run(k<2>, "background: 16 warps of smem ld/st");
   run(k<3>, "background: 16 warps of tcgen05.ld");
   run(k<4>, "background: 16 warps polling an mbarrier");
+  run(k<5>, "dQ-type SS (A, B MN-major, N=48), idle background");
+  run(k<6>, "S-type SS (K-major, N=128), idle background");
   return 0;
 }
