@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmodaltune_b200.so")
+LIB_PATH = os.environ.get("MODALTUNE_B200_LIB") or os.path.join(HERE, "libmodaltune_b200.so")  # env: experiment builds
 
 MT_F32 = 0
 MT_BF16 = 1

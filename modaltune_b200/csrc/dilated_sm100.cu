@@ -354,8 +354,10 @@ static int encode_branch_map(CUtensorMap* map, const void* base, int64_t ld, int
   return 0;
 }
 
-// fp32 [n_alloc, ld] gradient buffer, same (column, residue, slot) view; dense [128][48] box for the TMA reduce-add
-static int encode_branch_map_f32(CUtensorMap* map, const void* base, int64_t ld, int64_t n_alloc, int r) {
+// fp32 [n_alloc, ld] gradient buffer, same (column, residue, slot) view, for the TMA reduce-add of dQ tiles:
+// box = [128 slots][cols] floats; cols = 48 unswizzled (dense staging tile), or 32 / 16 with the 128 B / 64 B swizzle
+// (row pitch = swizzle span, so that one-row-per-thread staging stores are bank-conflict free)
+static int encode_branch_map_f32(CUtensorMap* map, const void* base, int64_t ld, int64_t n_alloc, int r, int cols = DH) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -363,13 +365,15 @@ static int encode_branch_map_f32(CUtensorMap* map, const void* base, int64_t ld,
   }
   cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)r, (cuuint64_t)(n_alloc / r)};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)ld * 4 * (cuuint64_t)r};
-  cuuint32_t box[3] = {(cuuint32_t)DH, 1, (cuuint32_t)BT};
+  cuuint32_t box[3] = {(cuuint32_t)cols, 1, (cuuint32_t)BT};
   cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle swz = cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                            : (cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
   CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled (fp32) failed (%d) for dilation %d", (int)rc, r);
+    set_error("cuTensorMapEncodeTiled (fp32, %d columns) failed (%d) for dilation %d", cols, (int)rc, r);
     return MT_E_BADARG;
   }
   return 0;
@@ -1178,5 +1182,451 @@ int dilated_attn_bwd2_sm100(const mt_dilated_geometry* geom, const void* qkv, in
                                                                                           delta_br, dqkv, flag);
   return check_launch("dilated_bwd2_sm100_kernel");
 }
+
+// =====================================================================================================================
+// backward, third version: the per-query statistics ride on the tensor cores
+// =====================================================================================================================
+// Same transposed formulation as version 2 (keys on the TMEM lanes, K / V resident in TMEM, P^T / dS^T written back to
+// TMEM as the A operands of dV / dK), with two changes that take the element-wise work from ~6 to ~3.5 instructions per
+// score and the compute latency per half tile down by 2x:
+//   * the 64-column (128-byte) tile rows only carry 48 head columns, so columns 48..51 are used as an AUGMENTED
+//     contraction: the statistics warps overwrite them in every Q tile with the 3-way bf16 split of -lse/scale (and a
+//     -32768 mask column) and in every dO tile with the split of -delta, K' / V' in TMEM carry ones there.  The MMAs
+//     then deliver S^T - lse/scale and dP^T - delta directly (fp32 accumulation of exact 1 x bf16 products): no
+//     per-query statistics ring in shared memory, no broadcast loads, no subtraction per element.  Key rows past the
+//     segment's m get a one in the mask column (S = -32768 -> P = 0), queries that do not exist get -32768 as their lse.
+//   * all 16 compute warps work on the SAME 64-query half tile (16 scores per thread) while the MMAs of the other
+//     half run, instead of two groups of 8 warps ping-ponging over 32 scores per thread.
+// scale is applied to dQ and dK when they leave TMEM (dS is kept as P (dP - delta)).
+static constexpr int BWD3_THREADS = 64 + 512 + 128;
+struct Bwd3Smem {
+  static constexpr int K = 0;
+  static constexpr int V = K + TILE_BYTES;
+  static constexpr int NQ = 3;
+  static constexpr int Q = V + TILE_BYTES;                 // [NQ]
+  static constexpr int DO = Q + NQ * TILE_BYTES;           // [NQ]
+  static constexpr int DS = DO + NQ * TILE_BYTES;          // [2] dS^T tiles: [128 key rows][2 blocks of 64 queries]
+  static constexpr int DQ = DS + 4 * TILE_BYTES;           // fp32 dQ staging: [128][32] (128 B swizzle) + [128][16] (64 B)
+  static constexpr int DQ_BYTES = BT * DH * 4;
+  static constexpr int BAR = DQ + DQ_BYTES;
+  // kv_full, kvt_full, st_full[2], pt_full[2], dq_full, dq_free, done, qdo_full[NQ], qdo_empty[NQ], aug_full[NQ]
+  static constexpr int NBAR = 9 + 3 * NQ;
+  static constexpr int TMEM_PTR = BAR + NBAR * 8;
+  static constexpr int TOTAL = TMEM_PTR + 16;
+};
+
+__device__ __forceinline__ void split3_bf16(float a, uint32_t& w0, uint32_t& w1, float fourth) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(a);
+  const float r1 = a - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(mid);
+  w0 = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16);
+  w1 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(r2)) |
+       ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(fourth)) << 16);
+}
+
+__global__ void __launch_bounds__(BWD3_THREADS, 1)
+dilated_bwd3_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ TensorMaps do_maps,
+                          const __grid_constant__ TensorMaps dq32_maps, const __grid_constant__ TensorMaps dq16_maps,
+                          const Sm100Params P, const float* __restrict__ lse, const float* __restrict__ delta_br,
+                          float* __restrict__ dqkv, int* __restrict__ err_flag) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  // roles by warp id: compute 0-15, statistics / dQ drain 16-19, TMA 20, MMA 21
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int W_TMA = 20, W_MMA = 21, W_EPI = 16;
+  if ((sbase & 1023u) != 0) {
+    if (threadIdx.x == 0) atomicExch(err_flag, 1);
+    return;
+  }
+  int oi = 0;
+  while (oi + 1 < P.geo.nb && (int)blockIdx.x >= P.item_prefix[oi + 1]) ++oi;
+  const int b = P.order[oi];
+  const BranchGeom bg = P.geo.b[b];
+  int local = blockIdx.x - P.item_prefix[oi];
+  const int kt = local % P.tiles[b];
+  local /= P.tiles[b];
+  const int h = local % P.geo.H;
+  const int s = local / P.geo.H;
+  const int H = P.geo.H, N = P.geo.N, E = H * DH;
+  const int off = (h * bg.r) / H;
+  const int jseg = (s * bg.g) / bg.r;
+  const int n_q = P.tiles[b];
+  const int k0 = kt * BT;
+  const int seg_end = min(N, (s + 1) * bg.g);
+  const int slot_h = h - off * bg.hpb;
+
+  constexpr int NQ = Bwd3Smem::NQ;
+  const uint32_t bar_kv_full = sbase + Bwd3Smem::BAR + 0;
+  const uint32_t bar_kvt_full = sbase + Bwd3Smem::BAR + 8;
+  const uint32_t bar_st_full = sbase + Bwd3Smem::BAR + 16;     // [2]
+  const uint32_t bar_pt_full = sbase + Bwd3Smem::BAR + 32;     // [2]
+  const uint32_t bar_dq_full = sbase + Bwd3Smem::BAR + 48;
+  const uint32_t bar_dq_free = sbase + Bwd3Smem::BAR + 56;
+  const uint32_t bar_done = sbase + Bwd3Smem::BAR + 64;        // every MMA of the CTA has completed
+  const uint32_t bar_qdo_full = sbase + Bwd3Smem::BAR + 72;    // [NQ] TMA landed
+  const uint32_t bar_qdo_empty = bar_qdo_full + 8 * NQ;        // [NQ]
+  const uint32_t bar_aug_full = bar_qdo_empty + 8 * NQ;        // [NQ] statistics columns written into the stage
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Bwd3Smem::TMEM_PTR);
+  constexpr int NCOMP = 512;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_kv_full, 1);
+    mbar_init(bar_kvt_full, 256);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_st_full + 8 * i, 1);
+      mbar_init(bar_pt_full + 8 * i, NCOMP);
+    }
+    for (int i = 0; i < NQ; ++i) {
+      mbar_init(bar_qdo_full + 8 * i, 1);
+      mbar_init(bar_qdo_empty + 8 * i, 1);
+      mbar_init(bar_aug_full + 8 * i, 128);
+    }
+    mbar_init(bar_dq_full, 1);
+    mbar_init(bar_dq_free, 128);
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.m[b]);
+    tma_prefetch_desc(&do_maps.m[b]);
+    tma_prefetch_desc(&dq32_maps.m[b]);
+    tma_prefetch_desc(&dq16_maps.m[b]);
+  }
+  if (warp == W_MMA) {
+    tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // columns: [0,64) S^T buf0 | [64,128) dP^T buf0 | [128,192) S^T buf1 | [192,256) dP^T buf1 | dV 256 | dK 320 | dQ 384
+  //          K' (64 bf16 = 32 columns) 448 | V' 480
+  const uint32_t tm_dv = tmem + 256, tm_dk = tmem + 320, tm_dq = tmem + 384, tm_k = tmem + 448, tm_v = tmem + 480;
+
+  if (warp == W_TMA) {
+    // ===== TMA producer ===============================================================================================
+    if (lane == 0) {
+      const void* map = &maps.m[b];
+      const void* dmap = &do_maps.m[b];
+      mbar_expect_tx(bar_kv_full, 2 * TILE_BYTES);
+      tma_load_3d(sbase + Bwd3Smem::K, map, bar_kv_full, E + h * DH, off, jseg + k0);
+      tma_load_3d(sbase + Bwd3Smem::V, map, bar_kv_full, 2 * E + h * DH, off, jseg + k0);
+      for (int i = 0; i < n_q; ++i) {
+        const int st = i % NQ, use = i / NQ;
+        mbar_wait(bar_qdo_empty + 8 * st, (use & 1) ^ 1);
+        mbar_expect_tx(bar_qdo_full + 8 * st, 2 * TILE_BYTES);
+        tma_load_3d(sbase + Bwd3Smem::Q + st * TILE_BYTES, map, bar_qdo_full + 8 * st, h * DH, off, jseg + i * BT);
+        tma_load_3d(sbase + Bwd3Smem::DO + st * TILE_BYTES, dmap, bar_qdo_full + 8 * st, h * DH, off, jseg + i * BT);
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ===== MMA issuer =================================================================================================
+    constexpr uint32_t IDESC_ST = umma_idesc_bf16(BT, 64, 0, 0);    // A = K' / V' (TMEM), B = Q' / dO' half tile (K-major)
+    constexpr uint32_t IDESC_TS = umma_idesc_bf16(BT, DH, 0, 1);    // A = P^T / dS^T (TMEM), B = dO / Q (MN-major)
+    constexpr uint32_t IDESC_DQ = umma_idesc_bf16(BT, DH, 1, 1);    // A = dS^T tile (smem, MN-major), B = K (MN-major)
+    const int n_half = 2 * n_q;
+    const uint64_t qk_desc = umma_smem_desc(sbase + Bwd3Smem::Q, 16, 1024);          // K-major views (stage 0)
+    const uint64_t dk_desc = umma_smem_desc(sbase + Bwd3Smem::DO, 16, 1024);
+    const uint64_t qm_desc = umma_smem_desc(sbase + Bwd3Smem::Q, TILE_BYTES, 1024);  // MN-major views (stage 0)
+    const uint64_t dm_desc = umma_smem_desc(sbase + Bwd3Smem::DO, TILE_BYTES, 1024);
+    const uint64_t k_mn_desc = umma_smem_desc(sbase + Bwd3Smem::K, TILE_BYTES, 1024);
+    const uint64_t ds_desc0 = umma_smem_desc(sbase + Bwd3Smem::DS, TILE_BYTES, 1024);
+    const uint64_t ds_desc1 = umma_smem_desc(sbase + Bwd3Smem::DS + 2 * TILE_BYTES, TILE_BYTES, 1024);
+    // The issue loop is unrolled over the NQ stages x 2 halves so that every descriptor is a base plus a compile-time
+    // constant: the single issuing thread shares its scheduler with five busy warps, and every instruction it needs
+    // between a barrier flip and the UTCHMMA stream is latency on the critical path of the whole CTA.
+    auto issue_st = [&](auto U) {  // S'^T and dP'^T of a half tile (stage U / 2, half U & 1) into TMEM buffer U & 1
+      constexpr int u = decltype(U)::value;
+      if (elect_one()) {
+        constexpr uint32_t so = (uint32_t)((u >> 1) * TILE_BYTES + (u & 1) * 64 * 128);
+        const uint32_t ts = tmem + (u & 1) * 128, td = ts + 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ts(ts, tm_k + k * 8, umma_desc_adv(qk_desc, so + k * 32), IDESC_ST, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ts(td, tm_v + k * 8, umma_desc_adv(dk_desc, so + k * 32), IDESC_ST, k > 0);
+        umma_commit(bar_st_full + 8 * (u & 1));
+      }
+      __syncwarp();
+    };
+    MT_TRACE_DECL
+    mbar_wait(bar_kvt_full, 0);       // K' and V' are in TMEM
+    mbar_wait(bar_qdo_full, 0);
+    mbar_wait(bar_aug_full, 0);
+    tc_fence_after();
+    MT_TRACE(0);
+    issue_st(std::integral_constant<int, 0>{});
+    issue_st(std::integral_constant<int, 1>{});
+    // one half tile: t = trip of the unrolled loop (tile i = NQ * t + U / 2)
+    auto half = [&](int g, int t, auto U) {
+      constexpr int u = decltype(U)::value;
+      constexpr int st = u >> 1, hh = u & 1;
+      const int i = g >> 1;
+      mbar_wait(bar_pt_full + 8 * hh, i & 1);   // P^T, dS^T of half g are in TMEM (+ dS^T half in smem)
+      tc_fence_after();
+      MT_TRACE(100 + g);
+      if (elect_one()) {
+        constexpr uint32_t so = (uint32_t)(st * TILE_BYTES + hh * 64 * 128);
+        const uint32_t ts = tmem + hh * 128, td = ts + 64;
+        // packed P^T / dS^T: query pair (2c, 2c+1) of 16-query quarter qq sits in column 16*qq + c of its buffer;
+        // 64 queries = 4 k-steps of 16 (rows of the dO / Q half tile: 2048 B each)
+        umma_ts(tm_dv, ts, umma_desc_adv(dm_desc, so), IDESC_TS, g > 0);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) umma_ts(tm_dv, ts + k * 16, umma_desc_adv(dm_desc, so + k * 2048), IDESC_TS, 1);
+        umma_ts(tm_dk, td, umma_desc_adv(qm_desc, so), IDESC_TS, g > 0);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) umma_ts(tm_dk, td + k * 16, umma_desc_adv(qm_desc, so + k * 2048), IDESC_TS, 1);
+        if (hh == 1) umma_commit(bar_qdo_empty + 8 * st);   // last readers of this Q / dO stage (dQ reads K, dS)
+      }
+      __syncwarp();
+      if (g + 2 < n_half) {          // the buffer is free once the MMAs above have consumed it (the pipe is in order)
+        constexpr int st2 = (st + 1) % NQ;                  // stage of tile i + 1
+        if (hh == 0) {
+          const uint32_t par = (uint32_t)(t + (st2 == 0 ? 1 : 0)) & 1u;   // (i + 1) / NQ
+          mbar_wait(bar_qdo_full + 8 * st2, par);
+          mbar_wait(bar_aug_full + 8 * st2, par);
+        }
+        tc_fence_after();
+        MT_TRACE(200 + g);
+        issue_st(std::integral_constant<int, 2 * st2 + hh>{});
+      }
+      if (hh == 1) {                 // both halves of query tile i are done: dQ_i = dS_i K
+        if (i > 0) mbar_wait(bar_dq_free, (i - 1) & 1);
+        tc_fence_after();
+        MT_TRACE(300 + g);
+        if (elect_one()) {
+          const uint64_t ds = (i & 1) ? ds_desc1 : ds_desc0;
+#pragma unroll
+          for (int k = 0; k < BT / 16; ++k)   // contraction over the 128 keys = rows of the dS^T tile and of K
+            umma_ss(tm_dq, umma_desc_adv(ds, k * 2048), umma_desc_adv(k_mn_desc, k * 2048), IDESC_DQ, k > 0);
+          umma_commit(bar_dq_full);
+        }
+        __syncwarp();
+      }
+    };
+    static_assert(NQ == 3, "the issue loop is unrolled for three stages");
+    for (int g = 0, t = 0; g < n_half; g += 2 * NQ, ++t) {
+      half(g, t, std::integral_constant<int, 0>{});
+      half(g + 1, t, std::integral_constant<int, 1>{});
+      if (g + 2 < n_half) {
+        half(g + 2, t, std::integral_constant<int, 2>{});
+        half(g + 3, t, std::integral_constant<int, 3>{});
+      }
+      if (g + 4 < n_half) {
+        half(g + 4, t, std::integral_constant<int, 4>{});
+        half(g + 5, t, std::integral_constant<int, 5>{});
+      }
+    }
+    if (elect_one()) umma_commit(bar_done);
+    __syncwarp();
+    if (lane == 0) { MT_TRACE_DUMP("mma3"); }
+  } else if (warp < W_EPI) {
+    // ===== compute: 16 warps, thread = (key row, 16 queries of the current 64-query half tile) =======================
+    const int lane_grp = warp & 3;               // TMEM lanes of this warp
+    const int qq = warp >> 2;                    // 16-query quarter of every half tile; also the dK / dV column group
+    const int row = lane_grp * 32 + lane;        // key slot k0 + row
+    const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
+    const int sw = row & 7;
+    const bool key_ok = (k0 + row) < bg.m;       // rows past m belong to the next segment: mask column -> P = dS = 0
+    const float scale_log2 = P.scale_log2, sc = P.scale;
+
+    // ---- K' and V' -> TMEM (A operands of S^T / dP^T for the whole CTA): quarter 0 copies K, quarter 1 copies V.
+    // columns 48..50 = 1 (the three statistics columns), column 51 of K' = 1 for masked key rows, the rest 0
+    mbar_wait(bar_kv_full, 0);
+    if (qq < 2) {
+      const uint8_t* src = smem + (qq == 0 ? Bwd3Smem::K : Bwd3Smem::V) + row * 128;
+      uint32_t w[32];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const uint4 u = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));
+        w[4 * c] = u.x; w[4 * c + 1] = u.y; w[4 * c + 2] = u.z; w[4 * c + 3] = u.w;
+      }
+      w[24] = 0x3f803f80u;
+      w[25] = (qq == 0 && !key_ok) ? 0x3f803f80u : 0x00003f80u;
+#pragma unroll
+      for (int c = 26; c < 32; ++c) w[c] = 0u;
+      const uint32_t dst = (qq == 0 ? tm_k : tm_v) + t_lane;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r8[e] = w[8 * c + e];
+        tmem_st8(dst + c * 8, r8);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_kvt_full);
+    }
+
+    const int n_half = 2 * n_q;
+    MT_TRACE_DECL
+    for (int g = 0; g < n_half; ++g) {
+      const int i = g >> 1, hh = g & 1;
+      uint8_t* drow = smem + Bwd3Smem::DS + (i & 1) * 2 * TILE_BYTES + hh * TILE_BYTES + row * 128;
+      const uint32_t ts = tmem + (g & 1) * 128 + t_lane + qq * 16, td = ts + 64;
+      MT_TRACE(1000 + g);
+      mbar_wait(bar_st_full + 8 * (g & 1), (g >> 1) & 1);
+      tc_fence_after();
+      MT_TRACE(1100 + g);
+      float sv[16], dp[16];
+      tmem_ld16(ts, sv);
+      tmem_ld16(td, dp);
+      tmem_ld_wait();
+      MT_TRACE(1200 + g);
+      uint32_t pk[8], dk[8];
+#pragma unroll
+      for (int c = 0; c < 16; c += 2) {
+        const float p0 = ex2(sv[c] * scale_log2);
+        const float p1 = ex2(sv[c + 1] * scale_log2);
+        pk[c >> 1] = pack_bf16(p0, p1);
+        dk[c >> 1] = pack_bf16(p0 * dp[c], p1 * dp[c + 1]);
+      }
+      // packed results over the first 8 of the 16 columns this thread has just read (nobody else touches them)
+      tmem_st8(ts, pk);
+      tmem_st8(td, dk);
+      // dS^T half tile for dQ = dS K: [key row][64 queries] block hh, 16 queries = 2 swizzled 16-byte chunks
+      *reinterpret_cast<uint4*>(drow + (((2 * qq) ^ sw) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+      *reinterpret_cast<uint4*>(drow + (((2 * qq + 1) ^ sw) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_pt_full + 8 * (g & 1));
+    }
+    if (warp == 0 && lane == 0) { MT_TRACE_DUMP("cmp3"); }
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    // ---- dK / dV of this key tile ------------------------------------------------------------------------------------
+    {
+      float a[3][4], c2[3][4];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        tmem_ld4(tm_dk + t_lane + qq * 12 + c * 4, a[c]);
+        tmem_ld4(tm_dv + t_lane + qq * 12 + c * 4, c2[c]);
+      }
+      tmem_ld_wait();
+      const int slot = k0 + row;
+      const int pos = s * bg.g + off + slot * bg.r;
+      if (slot < bg.m && pos < seg_end) {
+        float* dst = dqkv + (int64_t)pos * (3 * E) + E + h * DH + qq * 12;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          red_add_v4(dst + c * 4, a[c][0] * sc, a[c][1] * sc, a[c][2] * sc, a[c][3] * sc);
+          red_add_v4(dst + E + c * 4, c2[c][0], c2[c][1], c2[c][2], c2[c][3]);
+        }
+      }
+    }
+  } else {
+    // ===== statistics + dQ drain (4 warps, one query row per thread) ==================================================
+    const int lane_grp = warp & 3;
+    const int row = lane_grp * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
+    const int sw = row & 7;
+    const float sc = P.scale, inv_sc = 1.f / P.scale;
+    // per-query statistics of tile i (strided 4-byte global loads, requested one iteration before their use)
+    auto load_stats = [&](int i, float& l, float& d) {
+      const int slot = i * BT + row;
+      const int pos = s * bg.g + off + slot * bg.r;
+      const bool qok = i < n_q && slot < bg.m && pos < seg_end;
+      l = qok ? -lse[(int64_t)pos * H + h] * inv_sc : -32768.f;    // -32768 -> P = 0 for rows that do not exist
+      d = qok ? -delta_br[bg.lse_off + (int64_t)pos * bg.hpb + slot_h] : 0.f;
+    };
+    // columns 48..55 (16-byte chunk 6) of this thread's row in the Q and dO tiles of stage i % NQ
+    auto write_aug = [&](int i, float l, float d) {
+      const int st = i % NQ;
+      mbar_wait(bar_qdo_full + 8 * st, (i / NQ) & 1);      // the TMA has written the stage
+      uint32_t w0, w1;
+      split3_bf16(l, w0, w1, -32768.f);
+      *reinterpret_cast<uint4*>(smem + Bwd3Smem::Q + st * TILE_BYTES + row * 128 + ((6 ^ sw) << 4)) = make_uint4(w0, w1, 0u, 0u);
+      split3_bf16(d, w0, w1, 0.f);
+      *reinterpret_cast<uint4*>(smem + Bwd3Smem::DO + st * TILE_BYTES + row * 128 + ((6 ^ sw) << 4)) = make_uint4(w0, w1, 0u, 0u);
+      fence_proxy_async_smem();
+      mbar_arrive(bar_aug_full + 8 * st);
+    };
+    float l_n, d_n;
+    MT_TRACE_DECL
+    load_stats(0, l_n, d_n);
+    write_aug(0, l_n, d_n);
+    if (n_q > 1) {
+      load_stats(1, l_n, d_n);
+      write_aug(1, l_n, d_n);
+    }
+    load_stats(2, l_n, d_n);
+    for (int i = 0; i < n_q; ++i) {
+      if (i + 2 < n_q) write_aug(i + 2, l_n, d_n);
+      load_stats(i + 3, l_n, d_n);   // requested now, consumed in the next iteration (hides the L2 latency)
+      // dQ of query tile i: TMEM -> registers -> fp32 staging tile in shared memory -> ONE TMA reduce-add per box
+      // (red.global from registers costs one L1 request per row and instruction: ~1500 LSU cycles per tile)
+      MT_TRACE(2000 + i);
+      mbar_wait(bar_dq_full, i & 1);
+      tc_fence_after();
+      MT_TRACE(2100 + i);
+      float v[3][16];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tmem_ld16(tm_dq + t_lane + c * 16, v[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_dq_free);
+      if (threadIdx.x == W_EPI * 32) bulk_wait_group_read<0>();   // the previous reduce has read the staging tile
+      named_bar_sync(1, 128);
+      uint8_t* s32 = smem + Bwd3Smem::DQ + row * 128;             // columns 0..31, 16-byte chunk c at c ^ (row & 7)
+      uint8_t* s16 = smem + Bwd3Smem::DQ + BT * 128 + row * 64;   // columns 32..47, chunk c at c ^ ((row >> 1) & 3)
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(s32 + ((c ^ sw) << 4)) =
+            make_float4(v[c >> 2][(c & 3) * 4] * sc, v[c >> 2][(c & 3) * 4 + 1] * sc, v[c >> 2][(c & 3) * 4 + 2] * sc,
+                        v[c >> 2][(c & 3) * 4 + 3] * sc);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4*>(s16 + ((c ^ ((row >> 1) & 3)) << 4)) =
+            make_float4(v[2][c * 4] * sc, v[2][c * 4 + 1] * sc, v[2][c * 4 + 2] * sc, v[2][c * 4 + 3] * sc);
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (threadIdx.x == W_EPI * 32) {
+        // rows past the segment's m (next segment / padding) carry dS = 0 -> they add zeros; rows >= n_alloc are clipped
+        tma_reduce_add_3d(&dq32_maps.m[b], sbase + Bwd3Smem::DQ, h * DH, off, jseg + i * BT);
+        tma_reduce_add_3d(&dq16_maps.m[b], sbase + Bwd3Smem::DQ + BT * 128, h * DH + 32, off, jseg + i * BT);
+        bulk_commit_group();
+      }
+      MT_TRACE(2200 + i);
+    }
+    if (threadIdx.x == W_EPI * 32) bulk_wait_group_all();
+    if (warp == W_EPI && lane == 0) { MT_TRACE_DUMP("sta3"); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc(tmem, 512);
+}
+
+int dilated_attn_bwd3_sm100(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,
+                            const void* dattn, const float* lse, const float* delta_br, float* dqkv, cudaStream_t st) {
+  Sm100Params P;
+  int rc = make_sm100_params(geom, &P);
+  if (rc) return rc;
+  MT_REQUIRE(n_alloc >= P.geo.N && n_alloc % 128 == 0, "dilated_attn_bwd: n_alloc must be a multiple of 128 >= n_tokens");
+  MT_REQUIRE(qkv_ld % 8 == 0 && ((uintptr_t)qkv & 15) == 0 && ((uintptr_t)dattn & 15) == 0 && ((uintptr_t)dqkv & 15) == 0,
+             "dilated_attn_bwd: buffers must be 16-byte aligned");
+  TensorMaps maps, do_maps, dq32_maps, dq16_maps;
+  memset(&maps, 0, sizeof(maps));
+  memset(&do_maps, 0, sizeof(do_maps));
+  memset(&dq32_maps, 0, sizeof(dq32_maps));
+  memset(&dq16_maps, 0, sizeof(dq16_maps));
+  const int64_t E = (int64_t)P.geo.H * DH;
+  for (int b = 0; b < P.geo.nb; ++b) {
+    rc = encode_branch_map(&maps.m[b], qkv, qkv_ld, n_alloc, P.geo.b[b].r);
+    if (rc) return rc;
+    rc = encode_branch_map(&do_maps.m[b], dattn, E, n_alloc, P.geo.b[b].r);
+    if (rc) return rc;
+    rc = encode_branch_map_f32(&dq32_maps.m[b], dqkv, 3 * E, n_alloc, P.geo.b[b].r, 32);
+    if (rc) return rc;
+    rc = encode_branch_map_f32(&dq16_maps.m[b], dqkv, 3 * E, n_alloc, P.geo.b[b].r, 16);
+    if (rc) return rc;
+  }
+  int* flag = error_flag();
+  MT_REQUIRE(flag != nullptr, "dilated_attn_bwd: cannot allocate the error flag");
+  MT_CUDA(cudaFuncSetAttribute(dilated_bwd3_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd3Smem::TOTAL));
+  dilated_bwd3_sm100_kernel<<<P.item_prefix[P.geo.nb], BWD3_THREADS, Bwd3Smem::TOTAL, st>>>(
+      maps, do_maps, dq32_maps, dq16_maps, P, lse, delta_br, dqkv, flag);
+  return check_launch("dilated_bwd3_sm100_kernel");
+}
+
 
 }  // namespace mt

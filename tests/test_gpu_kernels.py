@@ -229,7 +229,7 @@ def test_dilated_attention_tcgen05_backward(N, sl):
     y, _, lse, m, r = ops.dilated_merge_ln_fwd(geom, o, l, gamma, beta)
     dattn, delta = ops.dilated_merge_ln_bwd(geom, dy, o, l, gamma, m, r)
     dq_s = ops.dilated_attn_bwd(geom, qkv, dattn, lse, delta, 0)
-    for impl in (1, 2):   # 1: first tcgen05 version (operands through smem), 2: transposed, operands in TMEM
+    for impl in (1, 2, 3):   # 1: operands through smem, 2: transposed with operands in TMEM, 3: statistics on the MMAs
         dq_t = ops.dilated_attn_bwd(geom, qkv, dattn, lse, delta, impl)
         torch.cuda.synchronize()
         for name, sl_ in (("dq", slice(0, 768)), ("dk", slice(768, 1536)), ("dv", slice(1536, 2304))):
