@@ -36,6 +36,10 @@ def _stale(target: str, deps) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    global OUT, OBJ
+    if os.environ.get("MT_BUILD_OUT"):  # experiment builds (e.g. -DMT_DEBUG_TRACE) next to the product library
+        OUT = os.path.abspath(os.environ["MT_BUILD_OUT"])
+        OBJ = OUT + ".obj"
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "modaltune_b200.h"))

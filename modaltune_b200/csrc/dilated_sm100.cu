@@ -29,7 +29,10 @@ using namespace sm100;
 
 // experiment-only phase tracing (compile with -DMT_DEBUG_TRACE): block 0 prints clock64 stamps of its first iterations
 #ifdef MT_DEBUG_TRACE
-#define MT_TRACE_DECL long long tr_[96]; int trn_ = 0; const bool tron_ = (blockIdx.x == 0);
+#ifndef MT_TRACE_BLOCK
+#define MT_TRACE_BLOCK 0
+#endif
+#define MT_TRACE_DECL long long tr_[96]; int trn_ = 0; const bool tron_ = (blockIdx.x == MT_TRACE_BLOCK);
 #define MT_TRACE(tag) do { if (tron_ && trn_ < 94) { tr_[trn_++] = (long long)(tag); tr_[trn_++] = clock64(); } } while (0)
 #define MT_TRACE_DUMP(who) do { if (tron_) for (int q_ = 0; q_ + 1 < trn_; q_ += 2) printf("%s %lld %lld\n", who, tr_[q_], tr_[q_ + 1] & 0xffffffffll); } while (0)
 #else
@@ -1187,33 +1190,44 @@ int dilated_attn_bwd2_sm100(const mt_dilated_geometry* geom, const void* qkv, in
 // backward, third version: the per-query statistics ride on the tensor cores
 // =====================================================================================================================
 // Same transposed formulation as version 2 (keys on the TMEM lanes, K / V resident in TMEM, P^T / dS^T written back to
-// TMEM as the A operands of dV / dK), with two changes that take the element-wise work from ~6 to ~3.5 instructions per
-// score and the compute latency per half tile down by 2x:
+// TMEM as the A operands of dV / dK).  What changed, each item measured on B200 (tools/ubench, MT_DEBUG_TRACE):
 //   * the 64-column (128-byte) tile rows only carry 48 head columns, so columns 48..51 are used as an AUGMENTED
-//     contraction: the statistics warps overwrite them in every Q tile with the 3-way bf16 split of -lse/scale (and a
-//     -32768 mask column) and in every dO tile with the split of -delta, K' / V' in TMEM carry ones there.  The MMAs
+//     contraction: a dedicated warp overwrites them in every Q tile with the 3-way bf16 split of -lse/scale (and a
+//     -32768 mask column) and in every dO tile with the split of -delta; K' / V' in TMEM carry ones there.  The MMAs
 //     then deliver S^T - lse/scale and dP^T - delta directly (fp32 accumulation of exact 1 x bf16 products): no
 //     per-query statistics ring in shared memory, no broadcast loads, no subtraction per element.  Key rows past the
 //     segment's m get a one in the mask column (S = -32768 -> P = 0), queries that do not exist get -32768 as their lse.
 //   * all 16 compute warps work on the SAME 64-query half tile (16 scores per thread) while the MMAs of the other
 //     half run, instead of two groups of 8 warps ping-ponging over 32 scores per thread.
+//   * the MMA issue loop is unrolled over stages x halves: every descriptor is a base plus a compile-time constant
+//     (the single issuing thread shares its scheduler with busy warps; its instructions are critical-path latency).
+//   * dQ, dK and dV leave through swizzled fp32 staging tiles and TMA reduce-adds (cp.reduce.async.bulk.tensor)
+//     instead of red.global from registers, which costs one L1 request per row and instruction (~1500 LSU cycles per
+//     dQ tile).  fp32 reduce-adds saturate at ~5.3 TB/s chip-wide (tools/ubench/red_rate.cu): ~1300 cycles per dQ tile
+//     and SM, so the staging tile is a buffer of its own and nobody but the drain warps ever waits for it.
+//   * separate warps for the TMA issue, the statistics columns and the dQ drain; the first loads are issued before
+//     the CTA-wide setup barrier.
 // scale is applied to dQ and dK when they leave TMEM (dS is kept as P (dP - delta)).
-static constexpr int BWD3_THREADS = 64 + 512 + 128;
+static constexpr int BWD3_THREADS = 32 * 23;   // 16 compute, 4 dQ drain, TMA, statistics, MMA
 struct Bwd3Smem {
+  static constexpr int NQ = 3;
   static constexpr int K = 0;
   static constexpr int V = K + TILE_BYTES;
-  static constexpr int NQ = 3;
   static constexpr int Q = V + TILE_BYTES;                 // [NQ]
   static constexpr int DO = Q + NQ * TILE_BYTES;           // [NQ]
   static constexpr int DS = DO + NQ * TILE_BYTES;          // [2] dS^T tiles: [128 key rows][2 blocks of 64 queries]
-  static constexpr int DQ = DS + 4 * TILE_BYTES;           // fp32 dQ staging: [128][32] (128 B swizzle) + [128][16] (64 B)
-  static constexpr int DQ_BYTES = BT * DH * 4;
-  static constexpr int BAR = DQ + DQ_BYTES;
+  static constexpr int STG = DS + 4 * TILE_BYTES;          // fp32 staging tile of the dQ reduce-add (24 KB)
+  static constexpr int BAR = STG + BT * DH * 4;
   // kv_full, kvt_full, st_full[2], pt_full[2], dq_full, dq_free, done, qdo_full[NQ], qdo_empty[NQ], aug_full[NQ]
   static constexpr int NBAR = 9 + 3 * NQ;
   static constexpr int TMEM_PTR = BAR + NBAR * 8;
   static constexpr int TOTAL = TMEM_PTR + 16;
+  // fp32 staging of a [128][48] gradient tile: columns 0..31 as [128][32] with the 128 B
+  // swizzle, columns 32..47 as [128][16] with the 64 B swizzle (row pitch = swizzle span: one-row-per-thread stores are
+  // bank-conflict free); each part is the box of one TMA reduce-add
+  static constexpr int STG16 = BT * 128;
 };
+static_assert(Bwd3Smem::TOTAL <= 232448, "shared memory of the backward kernel");
 
 __device__ __forceinline__ void split3_bf16(float a, uint32_t& w0, uint32_t& w1, float fourth) {
   const __nv_bfloat16 hi = __float2bfloat16_rn(a);
@@ -1225,16 +1239,24 @@ __device__ __forceinline__ void split3_bf16(float a, uint32_t& w0, uint32_t& w1,
        ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(fourth)) << 16);
 }
 
+// 16-byte chunk c (4 floats, columns 4c..4c+3 of 48) of row `row` of a staged fp32 gradient tile
+__device__ __forceinline__ void stage_chunk(uint8_t* stg, int row, int c, float4 v) {
+  uint8_t* dst = c < 8 ? stg + row * 128 + ((c ^ (row & 7)) << 4)
+                       : stg + Bwd3Smem::STG16 + row * 64 + (((c - 8) ^ ((row >> 1) & 3)) << 4);
+  *reinterpret_cast<float4*>(dst) = v;
+}
+
 __global__ void __launch_bounds__(BWD3_THREADS, 1)
 dilated_bwd3_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ TensorMaps do_maps,
                           const __grid_constant__ TensorMaps dq32_maps, const __grid_constant__ TensorMaps dq16_maps,
                           const Sm100Params P, const float* __restrict__ lse, const float* __restrict__ delta_br,
-                          float* __restrict__ dqkv, int* __restrict__ err_flag) {
+                          int* __restrict__ err_flag) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  // roles by warp id: compute 0-15, statistics / dQ drain 16-19, TMA 20, MMA 21
+  // roles by warp id: compute 0-15, dQ drain 16-19, TMA 20, statistics columns 21, MMA 22 (last: the scheduler
+  // favours high warp ids and the single-thread issuer must never starve)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int W_TMA = 20, W_MMA = 21, W_EPI = 16;
+  constexpr int W_DRAIN = 16, W_TMA = 20, W_AUG = 21, W_MMA = 22;
   if ((sbase & 1023u) != 0) {
     if (threadIdx.x == 0) atomicExch(err_flag, 1);
     return;
@@ -1270,7 +1292,9 @@ dilated_bwd3_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Bwd3Smem::TMEM_PTR);
   constexpr int NCOMP = 512;
 
-  if (threadIdx.x == 0) {
+  if (warp == W_TMA && lane == 0) {
+    // barrier setup and the first loads by the producer itself, ahead of the CTA-wide sync: the first tiles are on
+    // the critical path of every CTA (one CTA per SM, nothing overlaps its prologue)
     mbar_init(bar_kv_full, 1);
     mbar_init(bar_kvt_full, 256);
     for (int i = 0; i < 2; ++i) {
@@ -1280,14 +1304,22 @@ dilated_bwd3_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
     for (int i = 0; i < NQ; ++i) {
       mbar_init(bar_qdo_full + 8 * i, 1);
       mbar_init(bar_qdo_empty + 8 * i, 1);
-      mbar_init(bar_aug_full + 8 * i, 128);
+      mbar_init(bar_aug_full + 8 * i, 32);
     }
     mbar_init(bar_dq_full, 1);
     mbar_init(bar_dq_free, 128);
     mbar_init(bar_done, 1);
     fence_barrier_init();
-    tma_prefetch_desc(&maps.m[b]);
-    tma_prefetch_desc(&do_maps.m[b]);
+    const void* map = &maps.m[b];
+    const void* dmap = &do_maps.m[b];
+    mbar_expect_tx(bar_kv_full, 2 * TILE_BYTES);
+    tma_load_3d(sbase + Bwd3Smem::K, map, bar_kv_full, E + h * DH, off, jseg + k0);
+    tma_load_3d(sbase + Bwd3Smem::V, map, bar_kv_full, 2 * E + h * DH, off, jseg + k0);
+    for (int i = 0; i < NQ && i < n_q; ++i) {
+      mbar_expect_tx(bar_qdo_full + 8 * i, 2 * TILE_BYTES);
+      tma_load_3d(sbase + Bwd3Smem::Q + i * TILE_BYTES, map, bar_qdo_full + 8 * i, h * DH, off, jseg + i * BT);
+      tma_load_3d(sbase + Bwd3Smem::DO + i * TILE_BYTES, dmap, bar_qdo_full + 8 * i, h * DH, off, jseg + i * BT);
+    }
     tma_prefetch_desc(&dq32_maps.m[b]);
     tma_prefetch_desc(&dq16_maps.m[b]);
   }
@@ -1304,20 +1336,58 @@ dilated_bwd3_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
   const uint32_t tm_dv = tmem + 256, tm_dk = tmem + 320, tm_dq = tmem + 384, tm_k = tmem + 448, tm_v = tmem + 480;
 
   if (warp == W_TMA) {
-    // ===== TMA producer ===============================================================================================
+    // ===== TMA producer (tiles >= NQ; the first NQ were issued above) ================================================
     if (lane == 0) {
       const void* map = &maps.m[b];
       const void* dmap = &do_maps.m[b];
-      mbar_expect_tx(bar_kv_full, 2 * TILE_BYTES);
-      tma_load_3d(sbase + Bwd3Smem::K, map, bar_kv_full, E + h * DH, off, jseg + k0);
-      tma_load_3d(sbase + Bwd3Smem::V, map, bar_kv_full, 2 * E + h * DH, off, jseg + k0);
-      for (int i = 0; i < n_q; ++i) {
+      for (int i = NQ; i < n_q; ++i) {
         const int st = i % NQ, use = i / NQ;
         mbar_wait(bar_qdo_empty + 8 * st, (use & 1) ^ 1);
         mbar_expect_tx(bar_qdo_full + 8 * st, 2 * TILE_BYTES);
         tma_load_3d(sbase + Bwd3Smem::Q + st * TILE_BYTES, map, bar_qdo_full + 8 * st, h * DH, off, jseg + i * BT);
         tma_load_3d(sbase + Bwd3Smem::DO + st * TILE_BYTES, dmap, bar_qdo_full + 8 * st, h * DH, off, jseg + i * BT);
       }
+    }
+  } else if (warp == W_AUG) {
+    // ===== statistics columns: lane owns rows lane + 32 j of every Q / dO tile ==========================================
+    const float inv_sc = 1.f / P.scale;
+    float lr[4], dr[4], ln[4], dn[4];
+    // raw per-query statistics of tile i: strided 4-byte loads issued one tile ahead; consumed (and masked) at use
+    auto load_raw = [&](int i, float (&l)[4], float (&d)[4]) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int slot = i * BT + lane + 32 * j;
+        const int pos = s * bg.g + off + slot * bg.r;
+        const bool qok = i < n_q && slot < bg.m && pos < seg_end;
+        const int pc = qok ? pos : 0;
+        l[j] = lse[(int64_t)pc * H + h];
+        d[j] = delta_br[bg.lse_off + (int64_t)pc * bg.hpb + slot_h];
+      }
+    };
+    load_raw(0, lr, dr);
+    for (int i = 0; i < n_q; ++i) {
+      load_raw(i + 1, ln, dn);
+      const int st = i % NQ;
+      mbar_wait(bar_qdo_full + 8 * st, (i / NQ) & 1);      // the TMA has written the stage
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int row = lane + 32 * j;
+        const int slot = i * BT + row;
+        const int pos = s * bg.g + off + slot * bg.r;
+        const bool qok = slot < bg.m && pos < seg_end;
+        uint32_t w0, w1;
+        // columns 48..55 (16-byte chunk 6) of the row: [hi, mid, lo, mask, 0, 0, 0, 0]
+        split3_bf16(qok ? -lr[j] * inv_sc : -32768.f, w0, w1, -32768.f);   // -32768 -> P = 0 for rows that do not exist
+        *reinterpret_cast<uint4*>(smem + Bwd3Smem::Q + st * TILE_BYTES + row * 128 + ((6 ^ (row & 7)) << 4)) =
+            make_uint4(w0, w1, 0u, 0u);
+        split3_bf16(qok ? -dr[j] : 0.f, w0, w1, 0.f);
+        *reinterpret_cast<uint4*>(smem + Bwd3Smem::DO + st * TILE_BYTES + row * 128 + ((6 ^ (row & 7)) << 4)) =
+            make_uint4(w0, w1, 0u, 0u);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_aug_full + 8 * st);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { lr[j] = ln[j]; dr[j] = dn[j]; }
     }
   } else if (warp == W_MMA) {
     // ===== MMA issuer =================================================================================================
@@ -1332,9 +1402,6 @@ dilated_bwd3_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
     const uint64_t k_mn_desc = umma_smem_desc(sbase + Bwd3Smem::K, TILE_BYTES, 1024);
     const uint64_t ds_desc0 = umma_smem_desc(sbase + Bwd3Smem::DS, TILE_BYTES, 1024);
     const uint64_t ds_desc1 = umma_smem_desc(sbase + Bwd3Smem::DS + 2 * TILE_BYTES, TILE_BYTES, 1024);
-    // The issue loop is unrolled over the NQ stages x 2 halves so that every descriptor is a base plus a compile-time
-    // constant: the single issuing thread shares its scheduler with five busy warps, and every instruction it needs
-    // between a barrier flip and the UTCHMMA stream is latency on the critical path of the whole CTA.
     auto issue_st = [&](auto U) {  // S'^T and dP'^T of a half tile (stage U / 2, half U & 1) into TMEM buffer U & 1
       constexpr int u = decltype(U)::value;
       if (elect_one()) {
@@ -1403,23 +1470,17 @@ dilated_bwd3_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
         __syncwarp();
       }
     };
+    auto trip = [&](int g0, int t, auto... Us) {
+      ((g0 + decltype(Us)::value < n_half ? (half(g0 + decltype(Us)::value, t, Us), 0) : 0), ...);
+    };
     static_assert(NQ == 3, "the issue loop is unrolled for three stages");
-    for (int g = 0, t = 0; g < n_half; g += 2 * NQ, ++t) {
-      half(g, t, std::integral_constant<int, 0>{});
-      half(g + 1, t, std::integral_constant<int, 1>{});
-      if (g + 2 < n_half) {
-        half(g + 2, t, std::integral_constant<int, 2>{});
-        half(g + 3, t, std::integral_constant<int, 3>{});
-      }
-      if (g + 4 < n_half) {
-        half(g + 4, t, std::integral_constant<int, 4>{});
-        half(g + 5, t, std::integral_constant<int, 5>{});
-      }
-    }
+    for (int g = 0, t = 0; g < n_half; g += 2 * NQ, ++t)
+      trip(g, t, std::integral_constant<int, 0>{}, std::integral_constant<int, 1>{}, std::integral_constant<int, 2>{},
+           std::integral_constant<int, 3>{}, std::integral_constant<int, 4>{}, std::integral_constant<int, 5>{});
     if (elect_one()) umma_commit(bar_done);
     __syncwarp();
     if (lane == 0) { MT_TRACE_DUMP("mma3"); }
-  } else if (warp < W_EPI) {
+  } else if (warp < W_DRAIN) {
     // ===== compute: 16 warps, thread = (key row, 16 queries of the current 64-query half tile) =======================
     const int lane_grp = warp & 3;               // TMEM lanes of this warp
     const int qq = warp >> 2;                    // 16-query quarter of every half tile; also the dK / dV column group
@@ -1428,10 +1489,13 @@ dilated_bwd3_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
     const int sw = row & 7;
     const bool key_ok = (k0 + row) < bg.m;       // rows past m belong to the next segment: mask column -> P = dS = 0
     const float scale_log2 = P.scale_log2, sc = P.scale;
+    MT_TRACE_DECL
+    MT_TRACE(1);
 
     // ---- K' and V' -> TMEM (A operands of S^T / dP^T for the whole CTA): quarter 0 copies K, quarter 1 copies V.
     // columns 48..50 = 1 (the three statistics columns), column 51 of K' = 1 for masked key rows, the rest 0
     mbar_wait(bar_kv_full, 0);
+    MT_TRACE(2);
     if (qq < 2) {
       const uint8_t* src = smem + (qq == 0 ? Bwd3Smem::K : Bwd3Smem::V) + row * 128;
       uint32_t w[32];
@@ -1458,20 +1522,17 @@ dilated_bwd3_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
     }
 
     const int n_half = 2 * n_q;
-    MT_TRACE_DECL
+    MT_TRACE(3);
     for (int g = 0; g < n_half; ++g) {
       const int i = g >> 1, hh = g & 1;
       uint8_t* drow = smem + Bwd3Smem::DS + (i & 1) * 2 * TILE_BYTES + hh * TILE_BYTES + row * 128;
-      const uint32_t ts = tmem + (g & 1) * 128 + t_lane + qq * 16, td = ts + 64;
-      MT_TRACE(1000 + g);
-      mbar_wait(bar_st_full + 8 * (g & 1), (g >> 1) & 1);
+      const uint32_t ts = tmem + hh * 128 + t_lane + qq * 16, td = ts + 64;
+      mbar_wait(bar_st_full + 8 * hh, i & 1);
       tc_fence_after();
-      MT_TRACE(1100 + g);
       float sv[16], dp[16];
       tmem_ld16(ts, sv);
       tmem_ld16(td, dp);
       tmem_ld_wait();
-      MT_TRACE(1200 + g);
       uint32_t pk[8], dk[8];
 #pragma unroll
       for (int c = 0; c < 16; c += 2) {
@@ -1489,12 +1550,14 @@ dilated_bwd3_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
       tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_pt_full + 8 * (g & 1));
+      mbar_arrive(bar_pt_full + 8 * hh);
     }
-    if (warp == 0 && lane == 0) { MT_TRACE_DUMP("cmp3"); }
+    MT_TRACE(4);
     mbar_wait(bar_done, 0);
     tc_fence_after();
-    // ---- dK / dV of this key tile ------------------------------------------------------------------------------------
+    MT_TRACE(5);
+    // ---- dK / dV of this key tile: TMEM -> fp32 staging (dK in dS^T buffer 0, dV in buffer 1) -> TMA reduce-adds.
+    // Rows past the segment's m carry zeros (mask column); zero-key rows (position >= N) land in the scratch rows of dqkv.
     {
       float a[3][4], c2[3][4];
 #pragma unroll
@@ -1503,58 +1566,37 @@ dilated_bwd3_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
         tmem_ld4(tm_dv + t_lane + qq * 12 + c * 4, c2[c]);
       }
       tmem_ld_wait();
-      const int slot = k0 + row;
-      const int pos = s * bg.g + off + slot * bg.r;
-      if (slot < bg.m && pos < seg_end) {
-        float* dst = dqkv + (int64_t)pos * (3 * E) + E + h * DH + qq * 12;
+      uint8_t* stg_k = smem + Bwd3Smem::DS;
+      uint8_t* stg_v = smem + Bwd3Smem::DS + 2 * TILE_BYTES;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          red_add_v4(dst + c * 4, a[c][0] * sc, a[c][1] * sc, a[c][2] * sc, a[c][3] * sc);
-          red_add_v4(dst + E + c * 4, c2[c][0], c2[c][1], c2[c][2], c2[c][3]);
-        }
+      for (int c = 0; c < 3; ++c) {
+        stage_chunk(stg_k, row, qq * 3 + c, make_float4(a[c][0] * sc, a[c][1] * sc, a[c][2] * sc, a[c][3] * sc));
+        stage_chunk(stg_v, row, qq * 3 + c, make_float4(c2[c][0], c2[c][1], c2[c][2], c2[c][3]));
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2, NCOMP);
+      if (threadIdx.x == 0) {
+        const uint32_t sk = sbase + Bwd3Smem::DS, sv_ = sbase + Bwd3Smem::DS + 2 * TILE_BYTES;
+        tma_reduce_add_3d(&dq32_maps.m[b], sk, E + h * DH, off, jseg + k0);
+        tma_reduce_add_3d(&dq16_maps.m[b], sk + Bwd3Smem::STG16, E + h * DH + 32, off, jseg + k0);
+        tma_reduce_add_3d(&dq32_maps.m[b], sv_, 2 * E + h * DH, off, jseg + k0);
+        tma_reduce_add_3d(&dq16_maps.m[b], sv_ + Bwd3Smem::STG16, 2 * E + h * DH + 32, off, jseg + k0);
+        bulk_commit_group();
+        bulk_wait_group_read<0>();          // the staging must outlive the reads; the adds complete with the kernel
       }
     }
+    MT_TRACE(6);
+    if (warp == 0 && lane == 0) { MT_TRACE_DUMP("cmp3"); }
   } else {
-    // ===== statistics + dQ drain (4 warps, one query row per thread) ==================================================
+    // ===== dQ drain (4 warps, one query row per thread) ================================================================
     const int lane_grp = warp & 3;
     const int row = lane_grp * 32 + lane;
     const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
-    const int sw = row & 7;
-    const float sc = P.scale, inv_sc = 1.f / P.scale;
-    // per-query statistics of tile i (strided 4-byte global loads, requested one iteration before their use)
-    auto load_stats = [&](int i, float& l, float& d) {
-      const int slot = i * BT + row;
-      const int pos = s * bg.g + off + slot * bg.r;
-      const bool qok = i < n_q && slot < bg.m && pos < seg_end;
-      l = qok ? -lse[(int64_t)pos * H + h] * inv_sc : -32768.f;    // -32768 -> P = 0 for rows that do not exist
-      d = qok ? -delta_br[bg.lse_off + (int64_t)pos * bg.hpb + slot_h] : 0.f;
-    };
-    // columns 48..55 (16-byte chunk 6) of this thread's row in the Q and dO tiles of stage i % NQ
-    auto write_aug = [&](int i, float l, float d) {
-      const int st = i % NQ;
-      mbar_wait(bar_qdo_full + 8 * st, (i / NQ) & 1);      // the TMA has written the stage
-      uint32_t w0, w1;
-      split3_bf16(l, w0, w1, -32768.f);
-      *reinterpret_cast<uint4*>(smem + Bwd3Smem::Q + st * TILE_BYTES + row * 128 + ((6 ^ sw) << 4)) = make_uint4(w0, w1, 0u, 0u);
-      split3_bf16(d, w0, w1, 0.f);
-      *reinterpret_cast<uint4*>(smem + Bwd3Smem::DO + st * TILE_BYTES + row * 128 + ((6 ^ sw) << 4)) = make_uint4(w0, w1, 0u, 0u);
-      fence_proxy_async_smem();
-      mbar_arrive(bar_aug_full + 8 * st);
-    };
-    float l_n, d_n;
+    const float sc = P.scale;
+    const bool leader = threadIdx.x == W_DRAIN * 32;
     MT_TRACE_DECL
-    load_stats(0, l_n, d_n);
-    write_aug(0, l_n, d_n);
-    if (n_q > 1) {
-      load_stats(1, l_n, d_n);
-      write_aug(1, l_n, d_n);
-    }
-    load_stats(2, l_n, d_n);
     for (int i = 0; i < n_q; ++i) {
-      if (i + 2 < n_q) write_aug(i + 2, l_n, d_n);
-      load_stats(i + 3, l_n, d_n);   // requested now, consumed in the next iteration (hides the L2 latency)
-      // dQ of query tile i: TMEM -> registers -> fp32 staging tile in shared memory -> ONE TMA reduce-add per box
-      // (red.global from registers costs one L1 request per row and instruction: ~1500 LSU cycles per tile)
+      // dQ of query tile i: TMEM -> registers -> fp32 staging tile -> one TMA reduce-add per box
       MT_TRACE(2000 + i);
       mbar_wait(bar_dq_full, i & 1);
       tc_fence_after();
@@ -1565,31 +1607,25 @@ dilated_bwd3_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(bar_dq_free);
-      if (threadIdx.x == W_EPI * 32) bulk_wait_group_read<0>();   // the previous reduce has read the staging tile
+      if (leader) bulk_wait_group_read<0>();   // the previous reduce-add has read the staging tile
       named_bar_sync(1, 128);
-      uint8_t* s32 = smem + Bwd3Smem::DQ + row * 128;             // columns 0..31, 16-byte chunk c at c ^ (row & 7)
-      uint8_t* s16 = smem + Bwd3Smem::DQ + BT * 128 + row * 64;   // columns 32..47, chunk c at c ^ ((row >> 1) & 3)
+      uint8_t* stg = smem + Bwd3Smem::STG;
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<float4*>(s32 + ((c ^ sw) << 4)) =
-            make_float4(v[c >> 2][(c & 3) * 4] * sc, v[c >> 2][(c & 3) * 4 + 1] * sc, v[c >> 2][(c & 3) * 4 + 2] * sc,
-                        v[c >> 2][(c & 3) * 4 + 3] * sc);
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<float4*>(s16 + ((c ^ ((row >> 1) & 3)) << 4)) =
-            make_float4(v[2][c * 4] * sc, v[2][c * 4 + 1] * sc, v[2][c * 4 + 2] * sc, v[2][c * 4 + 3] * sc);
+      for (int c = 0; c < 12; ++c)
+        stage_chunk(stg, row, c, make_float4(v[c >> 2][(c & 3) * 4] * sc, v[c >> 2][(c & 3) * 4 + 1] * sc,
+                                             v[c >> 2][(c & 3) * 4 + 2] * sc, v[c >> 2][(c & 3) * 4 + 3] * sc));
       fence_proxy_async_smem();
       named_bar_sync(1, 128);
-      if (threadIdx.x == W_EPI * 32) {
+      if (leader) {
         // rows past the segment's m (next segment / padding) carry dS = 0 -> they add zeros; rows >= n_alloc are clipped
-        tma_reduce_add_3d(&dq32_maps.m[b], sbase + Bwd3Smem::DQ, h * DH, off, jseg + i * BT);
-        tma_reduce_add_3d(&dq16_maps.m[b], sbase + Bwd3Smem::DQ + BT * 128, h * DH + 32, off, jseg + i * BT);
+        tma_reduce_add_3d(&dq32_maps.m[b], sbase + Bwd3Smem::STG, h * DH, off, jseg + i * BT);
+        tma_reduce_add_3d(&dq16_maps.m[b], sbase + Bwd3Smem::STG + Bwd3Smem::STG16, h * DH + 32, off, jseg + i * BT);
         bulk_commit_group();
       }
       MT_TRACE(2200 + i);
     }
-    if (threadIdx.x == W_EPI * 32) bulk_wait_group_all();
-    if (warp == W_EPI && lane == 0) { MT_TRACE_DUMP("sta3"); }
+    if (leader) bulk_wait_group_read<0>();
+    if (leader) { MT_TRACE_DUMP("drn3"); }
   }
   tc_fence_before();
   __syncthreads();
@@ -1624,9 +1660,8 @@ int dilated_attn_bwd3_sm100(const mt_dilated_geometry* geom, const void* qkv, in
   MT_REQUIRE(flag != nullptr, "dilated_attn_bwd: cannot allocate the error flag");
   MT_CUDA(cudaFuncSetAttribute(dilated_bwd3_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd3Smem::TOTAL));
   dilated_bwd3_sm100_kernel<<<P.item_prefix[P.geo.nb], BWD3_THREADS, Bwd3Smem::TOTAL, st>>>(
-      maps, do_maps, dq32_maps, dq16_maps, P, lse, delta_br, dqkv, flag);
+      maps, do_maps, dq32_maps, dq16_maps, P, lse, delta_br, flag);
   return check_launch("dilated_bwd3_sm100_kernel");
 }
-
 
 }  // namespace mt
