@@ -284,7 +284,7 @@ def main():
     t_fwd, n_fwd = avg_ms("dilated_attn_fwd")
     ach_bwd = f_bwd / (t_bwd * 1e-3) / 1e12 if t_bwd > 0 else 0.0
     ach_fwd = f_fwd / (t_fwd * 1e-3) / 1e12 if t_fwd > 0 else 0.0
-    impl_names = {0: "simt", 1: "tcgen05", 2: "tcgen05-tmem"}
+    impl_names = {0: "simt", 1: "tcgen05", 2: "tcgen05-tmem", 3: "tcgen05-tmem-aug"}
     roofline = {
         "bound": "tensor", "kernel": f"dilated_attn_bwd[{impl_names[config.attn_impl('bwd')]}]", "achieved": ach_bwd,
         "peak": peak, "peak_source": peak_src, "unit": "TFLOP/s", "frac": ach_bwd / peak, "traffic": None,
