@@ -515,7 +515,7 @@ int dilated_attn_bwd_simt(const mt_dilated_geometry* geom, const void* qkv, int6
 
 // implemented in dilated_sm100.cu
 int dilated_attn_fwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,
-                           void* o_br, float* lse_br, cudaStream_t st);
+                           void* o_br, float* lse_br, int impl, cudaStream_t st);
 int dilated_attn_bwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,
                            const void* dattn, const float* lse, const float* delta_br, float* dqkv, cudaStream_t st);
 int dilated_attn_bwd2_sm100(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,
@@ -533,7 +533,7 @@ extern "C" int mt_dilated_attn_fwd(const mt_dilated_geometry* geom, const void* 
   MT_REQUIRE(qkv_ld % 8 == 0, "dilated_attn_fwd: qkv row stride must be a multiple of 8 elements");
   if (impl == 0) return dilated_attn_fwd_simt(geom, qkv, qkv_ld, dtype, o_br, lse_br, (cudaStream_t)stream);
   MT_REQUIRE(dtype == MT_BF16, "dilated_attn_fwd: the tcgen05 path computes in bf16");
-  return dilated_attn_fwd_sm100(geom, qkv, qkv_ld, n_alloc, o_br, lse_br, (cudaStream_t)stream);
+  return dilated_attn_fwd_sm100(geom, qkv, qkv_ld, n_alloc, o_br, lse_br, impl, (cudaStream_t)stream);
 }
 
 extern "C" int mt_dilated_attn_bwd(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,

@@ -316,6 +316,263 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// forward, second version: O accumulated in TMEM with a lazily raised row maximum (no per-tile fold / rescale in
+// registers), the whole 128-column score row loaded once, 3-input maxima
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FWD_THREADS, 2)
+dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Params P, __nv_bfloat16* __restrict__ o_br,
+                         float* __restrict__ lse_br, int* __restrict__ err_flag) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  // roles by warp id: the scheduler favours high warp ids, so the latency-critical single-thread roles sit last
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int W_TMA = 4, W_MMA = 5;
+  if ((sbase & 1023u) != 0) {  // SWIZZLE_128B tiles need 1024-byte alignment; never expected, but fail loudly
+    if (threadIdx.x == 0) atomicExch(err_flag, 1);
+    return;
+  }
+  // ---- which tile -------------------------------------------------------------------------------------------------
+  int oi = 0;
+  while (oi + 1 < P.geo.nb && (int)blockIdx.x >= P.item_prefix[oi + 1]) ++oi;
+  const int b = P.order[oi];
+  const BranchGeom bg = P.geo.b[b];
+  int local = blockIdx.x - P.item_prefix[oi];
+  const int qt = local % P.tiles[b];
+  local /= P.tiles[b];
+  const int h = local % P.geo.H;
+  const int s = local / P.geo.H;
+  const int H = P.geo.H, N = P.geo.N, E = H * DH;
+  const int off = (h * bg.r) / H;                    // residue of the positions this head owns
+  const int jseg = (s * bg.g) / bg.r;                // first slot of the segment in the branch's j axis
+  const int n_kv = P.tiles[b];
+  const int q0 = qt * BT;
+
+  const uint32_t bar_q_full = sbase + FwdSmem::BAR + 0;
+  const uint32_t bar_kv_full = sbase + FwdSmem::BAR + 8;    // [2]
+  const uint32_t bar_kv_empty = sbase + FwdSmem::BAR + 24;  // [2]
+  const uint32_t bar_s_full = sbase + FwdSmem::BAR + 40;
+  const uint32_t bar_s_free = sbase + FwdSmem::BAR + 48;
+  const uint32_t bar_p_full = sbase + FwdSmem::BAR + 56;
+  const uint32_t bar_o_full = sbase + FwdSmem::BAR + 64;    // [2]
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + FwdSmem::TMEM_PTR);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q_full, 1);
+    for (int i = 0; i < KV_STAGES; ++i) {
+      mbar_init(bar_kv_full + 8 * i, 1);
+      mbar_init(bar_kv_empty + 8 * i, 1);
+      mbar_init(bar_o_full + 8 * i, 1);
+    }
+    mbar_init(bar_s_full, 1);
+    mbar_init(bar_s_free, 128);
+    mbar_init(bar_p_full, 128);
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.m[b]);
+  }
+  if (warp == W_MMA) {
+    tmem_alloc(smem_u32((const void*)tmem_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_s = tmem;
+  const uint32_t tmem_p = tmem + 128;  // P as the A operand of P V: lane = query row, column k/2 holds keys (k, k+1)
+  const uint32_t tmem_o = tmem + 192;
+
+  if (warp == W_TMA) {
+    // ===== TMA producer ===============================================================================================
+    if (lane == 0) {
+      const void* map = &maps.m[b];
+      mbar_expect_tx(bar_q_full, TILE_BYTES);
+      tma_load_3d(sbase + FwdSmem::Q, map, bar_q_full, h * DH, off, jseg + q0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1, use = j >> 1;
+        mbar_wait(bar_kv_empty + 8 * st, (use & 1) ^ 1);
+        mbar_expect_tx(bar_kv_full + 8 * st, 2 * TILE_BYTES);
+        tma_load_3d(sbase + FwdSmem::K + st * TILE_BYTES, map, bar_kv_full + 8 * st, E + h * DH, off, jseg + j * BT);
+        tma_load_3d(sbase + FwdSmem::V + st * TILE_BYTES, map, bar_kv_full + 8 * st, 2 * E + h * DH, off, jseg + j * BT);
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ===== MMA issuer =================================================================================================
+    constexpr uint32_t IDESC_QK = umma_idesc_bf16(BT, BT, 0, 0);
+    constexpr uint32_t IDESC_PV = umma_idesc_bf16(BT, DH, 0, 1);
+    // descriptors are built once; inside the loops an MMA costs one UTCHMMA (+ a constant descriptor advance)
+    const uint64_t q_desc = umma_smem_desc(sbase + FwdSmem::Q, 16, 1024);
+    const uint64_t k_desc0 = umma_smem_desc(sbase + FwdSmem::K, 16, 1024);
+    const uint64_t k_desc1 = umma_smem_desc(sbase + FwdSmem::K + TILE_BYTES, 16, 1024);
+    const uint64_t v_desc0 = umma_smem_desc(sbase + FwdSmem::V, TILE_BYTES, 1024);
+    const uint64_t v_desc1 = umma_smem_desc(sbase + FwdSmem::V + TILE_BYTES, TILE_BYTES, 1024);
+    auto issue_qk = [&](int j) {  // S = Q K_j^T : three k-steps of 16 inside the 128-byte swizzle atom
+      if (elect_one()) {
+        const uint64_t kd = (j & 1) ? k_desc1 : k_desc0;
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_ss(tmem_s, umma_desc_adv(q_desc, k * 32), umma_desc_adv(kd, k * 32), IDESC_QK, k > 0);
+        umma_commit(bar_s_full);
+      }
+      __syncwarp();
+    };
+    MT_TRACE_DECL
+    mbar_wait(bar_q_full, 0);
+    mbar_wait(bar_kv_full, 0);
+    tc_fence_after();
+    MT_TRACE(0);
+    issue_qk(0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) {
+        mbar_wait(bar_kv_full + 8 * ((j + 1) & 1), ((j + 1) >> 1) & 1);
+        MT_TRACE(100 + j);
+        mbar_wait(bar_s_free, j & 1);  // the softmax threads have read S_j out of TMEM
+        tc_fence_after();
+        MT_TRACE(200 + j);
+        issue_qk(j + 1);
+      }
+      mbar_wait(bar_p_full, j & 1);    // P_j is in TMEM (and the O tile of P_{j-1} V_{j-1} has been folded)
+      tc_fence_after();
+      MT_TRACE(300 + j);
+      if (elect_one()) {
+        // O_tile = P_j V_j : A = P straight from TMEM (16 keys = 8 packed columns per k-step), B = V in place as an
+        // MN-major operand (keys are the rows of the tile: 16 rows = 2048 B per k-step)
+        const uint64_t vd = (j & 1) ? v_desc1 : v_desc0;
+#pragma unroll
+        for (int k = 0; k < BT / 16; ++k)
+          umma_ts(tmem_o, tmem_p + k * 8, umma_desc_adv(vd, k * 2048), IDESC_PV, (j > 0) || (k > 0));
+        umma_commit(bar_kv_empty + 8 * (j & 1));
+        umma_commit(bar_o_full);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) { MT_TRACE_DUMP("mma"); }
+  } else {
+    // ===== softmax: one query row per thread; O accumulates in TMEM over the whole key loop =========================
+    // The row maximum used for the exponentials is only raised when the new maximum exceeds it by more than 8 in the
+    // log2 domain (P <= 2^8 stays exact enough in bf16, l is fp32): the O accumulator then never needs the per-tile
+    // rescale, and in the rare tile where a row does move, its warp rescales its 32 rows of O in TMEM in place.
+    const int lane_grp = warp & 3;                    // TMEM lanes this warp may touch: [32*lane_grp, +32)
+    const int row = lane_grp * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
+    float m_used = -INFINITY, l_run = 0.f;
+    const float scale_log2 = P.scale_log2;
+    MT_TRACE_DECL
+    auto tile = [&](int j, auto mask_tag) {
+      constexpr bool MASK = decltype(mask_tag)::value;
+      const int kvalid = bg.m - j * BT;  // key slots of this tile that belong to the segment (>= 1)
+      MT_TRACE(1000 + j);
+      mbar_wait(bar_s_full, j & 1);
+      tc_fence_after();
+      MT_TRACE(1100 + j);
+      float sv[128];
+      tmem_ld64(tmem_s + t_lane, sv);
+      tmem_ld64(tmem_s + t_lane + 64, sv + 64);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_s_free);          // S_j is in registers: the MMA warp may overwrite it with S_{j+1}
+      if (MASK) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) sv[i] = (i < kvalid) ? sv[i] : -INFINITY;
+      }
+      float mx = fmax3(sv[0], sv[1], sv[2]);
+#pragma unroll
+      for (int i = 3; i + 1 < 128; i += 2) mx = fmax3(mx, sv[i], sv[i + 1]);
+      mx = fmaxf(mx, sv[127]);
+      MT_TRACE(1200 + j);
+      bool waited = false;
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool need = (mx - m_used) * scale_log2 > 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(bar_o_full, (j - 1) & 1);   // P V of tile j-1 has completed: O may be touched
+          tc_fence_after();
+          waited = true;
+          const float alpha = need ? ex2((m_used - mx) * scale_log2) : 1.f;
+          float t[16];
+#pragma unroll
+          for (int c = 0; c < DH / 16; ++c) {
+            tmem_ld16(tmem_o + t_lane + c * 16, t);
+            tmem_ld_wait();
+            uint32_t u[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) u[i] = __float_as_uint(t[i] * alpha);
+            tmem_st16(tmem_o + t_lane + c * 16, u);
+          }
+          if (need) {
+            l_run *= alpha;
+            m_used = mx;
+          }
+        }
+      }
+      const float mb = m_used * scale_log2;
+      if (j > 0 && !waited) {             // P_j overwrites P_{j-1}: its P V must have read it
+        mbar_wait(bar_o_full, (j - 1) & 1);
+        tc_fence_after();
+      }
+      MT_TRACE(1300 + j);
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2(fmaf(sv[c * 32 + i], scale_log2, -mb));       // masked slots: ex2(-inf) = 0
+          const float p1 = ex2(fmaf(sv[c * 32 + i + 1], scale_log2, -mb));
+          rs += p0 + p1;
+          pk[i >> 1] = pack_bf16(p0, p1);
+        }
+        tmem_st16(tmem_p + t_lane + c * 16, pk);  // 32 keys = 16 packed columns
+      }
+      l_run += rs;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_p_full);
+      MT_TRACE(1400 + j);
+    };
+    for (int j = 0; j < n_kv; ++j) {
+      if (bg.m - j * BT >= BT) tile(j, std::false_type{});
+      else tile(j, std::true_type{});
+    }
+    mbar_wait(bar_o_full, (n_kv - 1) & 1);
+    tc_fence_after();
+    if (warp == 0 && lane == 0) { MT_TRACE_DUMP("smx"); }
+    // ---- epilogue: normalise and write the compact per-branch output ---------------------------------------------
+    const int slot = q0 + row;
+    const int pos = s * bg.g + off + slot * bg.r;
+    const int seg_end = min(N, (s + 1) * bg.g);
+    float o_acc[DH];
+#pragma unroll
+    for (int c = 0; c < DH / 16; ++c) {
+      float t[16];
+      tmem_ld16(tmem_o + t_lane + c * 16, t);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] = t[i];
+    }
+    if (slot < bg.m && pos < seg_end) {
+      const float inv = 1.f / l_run;
+      const int slot_h = h - off * bg.hpb;
+      __nv_bfloat16* dst = o_br + bg.o_off + ((int64_t)pos * bg.hpb + slot_h) * DH;
+#pragma unroll
+      for (int c = 0; c < DH / 8; ++c) {
+        uint4 u;
+        u.x = pack_bf16(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
+        u.y = pack_bf16(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
+        u.z = pack_bf16(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv);
+        u.w = pack_bf16(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + c * 8) = u;
+      }
+      lse_br[bg.lse_off + (int64_t)pos * bg.hpb + slot_h] = m_used * P.scale + logf(l_run);
+    }
+  }
+  // ---- teardown ------------------------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -423,7 +680,7 @@ static int* error_flag() {  // one device word, allocated once (reported through
 }
 
 int dilated_attn_fwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,
-                           void* o_br, float* lse_br, cudaStream_t st) {
+                           void* o_br, float* lse_br, int impl, cudaStream_t st) {
   Sm100Params P;
   int rc = make_sm100_params(geom, &P);
   if (rc) return rc;
@@ -437,6 +694,12 @@ int dilated_attn_fwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int
   }
   int* flag = error_flag();
   MT_REQUIRE(flag != nullptr, "dilated_attn_fwd: cannot allocate the error flag");
+  if (impl == 2) {
+    MT_CUDA(cudaFuncSetAttribute(dilated_fwd2_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
+    dilated_fwd2_sm100_kernel<<<P.item_prefix[P.geo.nb], FWD_THREADS, FwdSmem::TOTAL, st>>>(
+        maps, P, (__nv_bfloat16*)o_br, lse_br, flag);
+    return check_launch("dilated_fwd2_sm100_kernel");
+  }
   MT_CUDA(cudaFuncSetAttribute(dilated_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
   dilated_fwd_sm100_kernel<<<P.item_prefix[P.geo.nb], FWD_THREADS, FwdSmem::TOTAL, st>>>(
       maps, P, (__nv_bfloat16*)o_br, lse_br, flag);

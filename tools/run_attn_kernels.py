@@ -6,7 +6,8 @@ from modaltune_b200 import ops
 from modaltune_b200.slide_encoder import DILATED_RATIO, optimal_segment_lengths
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 10001
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-bwd_impl = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+bwd_impl = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+fwd_impl = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 dev = "cuda"
 geom = ops.Geometry.get(N, optimal_segment_lengths(), DILATED_RATIO)
 g = torch.Generator().manual_seed(0)
@@ -18,7 +19,7 @@ dy = torch.randn(N, 768, generator=g).to(dev)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 for i in range(reps):
     ev[0].record()
-    o, l = ops.dilated_attn_fwd(geom, qkv, 1)
+    o, l = ops.dilated_attn_fwd(geom, qkv, fwd_impl)
     ev[1].record()
     y, _, lse, m, r = ops.dilated_merge_ln_fwd(geom, o, l, gamma, beta)
     dattn, delta = ops.dilated_merge_ln_bwd(geom, dy, o, l, gamma, m, r)
