@@ -284,14 +284,22 @@ def main():
     t_fwd, n_fwd = avg_ms("dilated_attn_fwd")
     ach_bwd = f_bwd / (t_bwd * 1e-3) / 1e12 if t_bwd > 0 else 0.0
     ach_fwd = f_fwd / (t_fwd * 1e-3) / 1e12 if t_fwd > 0 else 0.0
-    impl_names = {0: "simt", 1: "tcgen05", 2: "tcgen05-tmem", 3: "tcgen05-tmem-aug"}
+    # DRAM bytes per launch of the backward kernel from the committed `ncu --set full` capture (read + write); only valid
+    # for the configuration that capture was taken on
+    traffic, traffic_src = None, None
+    if args.tiles == 10000 and config.attn_impl("bwd") == 3:
+        traffic = 243.451648e6 + 100.084480e6
+        traffic_src = "profiles/r1_ncu_attention_v3.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+    bwd_names = {0: "simt", 1: "tcgen05", 2: "tcgen05-tmem", 3: "tcgen05-tmem-aug"}
+    fwd_names = {0: "simt", 1: "tcgen05", 2: "tcgen05-tmem-acc"}
     roofline = {
-        "bound": "tensor", "kernel": f"dilated_attn_bwd[{impl_names[config.attn_impl('bwd')]}]", "achieved": ach_bwd,
-        "peak": peak, "peak_source": peak_src, "unit": "TFLOP/s", "frac": ach_bwd / peak, "traffic": None,
+        "bound": "tensor", "kernel": f"dilated_attn_bwd[{bwd_names[config.attn_impl('bwd')]}]", "achieved": ach_bwd,
+        "peak": peak, "peak_source": peak_src, "unit": "TFLOP/s", "frac": ach_bwd / peak, "traffic": traffic,
+        "traffic_source": traffic_src,
         "launch_ms": t_bwd, "launches_timed": n_bwd, "algorithmic_gflop_per_launch": f_bwd / 1e9,
         "share_of_step": t_bwd * n_bwd / args.steps / (ms / args.steps),
         "timing": "CUDA events on the launching stream, eager pass of the same step inside this run",
-        "fwd": {"kernel": f"dilated_attn_fwd[{impl_names[config.attn_impl('fwd')]}]", "achieved": ach_fwd,
+        "fwd": {"kernel": f"dilated_attn_fwd[{fwd_names[config.attn_impl('fwd')]}]", "achieved": ach_fwd,
                 "frac": ach_fwd / peak, "launch_ms": t_fwd, "launches_timed": n_fwd,
                 "algorithmic_gflop_per_launch": f_fwd / 1e9, "share_of_step": t_fwd * n_fwd / args.steps / (ms / args.steps)},
     }

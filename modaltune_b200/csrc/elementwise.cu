@@ -25,11 +25,17 @@ __device__ __forceinline__ float row_sum(float v, float* red, int row_in_block, 
   }
 }
 
+// 768 columns: one warp per row, 3 chunks of 8 elements per thread, 8 rows per 256-thread block.
+// 3072 columns: 384 threads per row with ONE chunk per thread: the GELU kernels need ~100 registers per thread with three
+// chunks, which caps them at 512 resident threads per SM -- too few loads in flight to hide the erf arithmetic behind
+// HBM; with one chunk they run three 384-thread blocks per SM.
 template <int COLS> struct RowCfg {
-  static constexpr int TPR = COLS / 24;          // threads per row, 3 chunks of 8 elements each
-  static constexpr int THREADS = 256;
-  static constexpr int RPB = THREADS / TPR;      // rows per block iteration
-  static_assert(COLS % 24 == 0 && (TPR == 32 || TPR == 128), "supported widths: 768, 3072");
+  static constexpr int NCH = COLS == 3072 ? 1 : 3;   // 8-element chunks per thread
+  static constexpr int TPR = COLS / (8 * NCH);       // threads per row
+  static constexpr int THREADS = COLS == 3072 ? 384 : 256;
+  static constexpr int MINB = COLS == 3072 ? 3 : 2;  // resident blocks per SM the register budget is set for
+  static constexpr int RPB = THREADS / TPR;          // rows per block iteration
+  static_assert(COLS % (8 * NCH) == 0 && TPR % 32 == 0 && THREADS % TPR == 0, "supported widths: 768, 3072");
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -41,7 +47,7 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 
 // y = LN(f(x)) * gamma + beta (+ add[row % add_rows]);  f = identity or GELU
 template <int COLS, typename TX, typename TY, typename TA, bool GELU>
-__global__ void __launch_bounds__(256, 2) ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ xbias,
+__global__ void __launch_bounds__(RowCfg<COLS>::THREADS, RowCfg<COLS>::MINB) ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ xbias,
                                                      const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, const TA* __restrict__ add,
                                                      int64_t add_rows, TY* __restrict__ y, float* __restrict__ mean,
@@ -52,10 +58,10 @@ __global__ void __launch_bounds__(256, 2) ln_fwd_kernel(const TX* __restrict__ x
   for (int64_t row0 = (int64_t)blockIdx.x * C::RPB; row0 < rows; row0 += (int64_t)gridDim.x * C::RPB) {
     const int64_t row = row0 + rib;
     const bool live = row < rows;
-    float v[3][8];
+    float v[C::NCH][8];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < C::NCH; ++i) {
       if (live) {
         load8(x + row * COLS + (i * C::TPR + t) * 8, v[i]);
         if (xbias != nullptr) {  // bias of the producing GEMM, folded in here (the GEMM keeps a plain fp32 output)
@@ -77,7 +83,7 @@ __global__ void __launch_bounds__(256, 2) ln_fwd_kernel(const TX* __restrict__ x
     const float mu = row_sum<C::TPR>(s, red, rib, t) * (1.f / COLS);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < C::NCH; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float d = v[i][j] - mu;
@@ -91,7 +97,7 @@ __global__ void __launch_bounds__(256, 2) ln_fwd_kernel(const TX* __restrict__ x
         if (rstd) rstd[row] = rs;
       }
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
+      for (int i = 0; i < C::NCH; ++i) {
         const int c = (i * C::TPR + t) * 8;
         float g[8], b[8], o[8];
         load8(gamma + c, g);
@@ -112,7 +118,7 @@ __global__ void __launch_bounds__(256, 2) ln_fwd_kernel(const TX* __restrict__ x
 
 // dx = [gelu'(x)] * rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ residual), g = dy * gamma, xhat = (f(x) - mean) * rstd
 template <int COLS, typename TDY, typename TX, typename TR, typename TDX, bool GELU, bool WGRAD>
-__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
+__global__ void __launch_bounds__(RowCfg<COLS>::THREADS, RowCfg<COLS>::MINB) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
                                                      const float* __restrict__ xbias,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const TR* __restrict__ residual,
@@ -121,10 +127,10 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const TDY* __restrict__ 
   using C = RowCfg<COLS>;
   __shared__ float red[C::RPB * (C::TPR / 32) + 1];
   const int t = threadIdx.x % C::TPR, rib = threadIdx.x / C::TPR;
-  float gam[3][8];
-  float dg_acc[WGRAD ? 3 : 1][8], db_acc[WGRAD ? 3 : 1][8];
+  float gam[C::NCH][8];
+  float dg_acc[WGRAD ? C::NCH : 1][8], db_acc[WGRAD ? C::NCH : 1][8];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < C::NCH; ++i) {
     load8(gamma + (i * C::TPR + t) * 8, gam[i]);
     if constexpr (WGRAD) {
 #pragma unroll
@@ -134,11 +140,11 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const TDY* __restrict__ 
   for (int64_t row0 = (int64_t)blockIdx.x * C::RPB; row0 < rows; row0 += (int64_t)gridDim.x * C::RPB) {
     const int64_t row = row0 + rib;
     const bool live = row < rows;
-    float xh[3][8], g[3][8], raw[3][8];  // raw holds x, or gelu'(x) when GELU
+    float xh[C::NCH][8], g[C::NCH][8], raw[C::NCH][8];  // raw holds x, or gelu'(x) when GELU
     const float mu = live ? mean[row] : 0.f, rs = live ? rstd[row] : 0.f;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < C::NCH; ++i) {
       const int c = (i * C::TPR + t) * 8;
       float d[8];
       if (live) {
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const TDY* __restrict__ 
     const float m2 = row_sum<C::TPR>(s2, red, rib, t) * (1.f / COLS);
     if (live) {
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
+      for (int i = 0; i < C::NCH; ++i) {
         const int c = (i * C::TPR + t) * 8;
         float o[8];
 #pragma unroll
@@ -202,7 +208,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const TDY* __restrict__ 
     for (int c = threadIdx.x; c < 2 * COLS; c += blockDim.x) wsum[c] = 0.f;
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < C::NCH; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = (i * C::TPR + t) * 8 + j;
@@ -285,10 +291,10 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict
   for (int64_t row0 = (int64_t)blockIdx.x * C::RPB; row0 < rows; row0 += (int64_t)gridDim.x * C::RPB) {
     const int64_t row = row0 + rib;
     const bool live = row < rows;
-    float v[3][8];
+    float v[C::NCH][8];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < C::NCH; ++i) {
       if (live) {
         float av[8];
         load8(x + row * COLS + (i * C::TPR + t) * 8, v[i]);
@@ -311,7 +317,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict
     const float mu = row_sum<C::TPR>(s, red, rib, t) * (1.f / COLS);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < C::NCH; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float d = v[i][j] - mu;
@@ -325,7 +331,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict
         rstd[row] = rs;
       }
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
+      for (int i = 0; i < C::NCH; ++i) {
         const int c = (i * C::TPR + t) * 8;
         float g[8], b[8], o[8];
         load8(gamma + c, g);
@@ -420,11 +426,11 @@ static int launch_ln_fwd(const void* x, const float* xbias, const float* gamma, 
   using C = RowCfg<COLS>;
   const int grid = grid_for(rows, C::RPB);
   if (add == nullptr || add_dtype == MT_F32)
-    ln_fwd_kernel<COLS, TX, TY, float, GELU><<<grid, 256, 0, st>>>((const TX*)x, xbias, gamma, beta, (const float*)add,
+    ln_fwd_kernel<COLS, TX, TY, float, GELU><<<grid, C::THREADS, 0, st>>>((const TX*)x, xbias, gamma, beta, (const float*)add,
                                                                    add_rows > 0 ? add_rows : 1, (TY*)y, mean, rstd,
                                                                    rows, eps);
   else
-    ln_fwd_kernel<COLS, TX, TY, __nv_bfloat16, GELU><<<grid, 256, 0, st>>>(
+    ln_fwd_kernel<COLS, TX, TY, __nv_bfloat16, GELU><<<grid, C::THREADS, 0, st>>>(
         (const TX*)x, xbias, gamma, beta, (const __nv_bfloat16*)add, add_rows > 0 ? add_rows : 1, (TY*)y, mean, rstd, rows, eps);
   return check_launch("ln_fwd_kernel");
 }
@@ -458,14 +464,14 @@ static int launch_ln_bwd(const void* dy, const void* x, const float* xbias, cons
         set_error("layernorm bwd with weight grads: residual must be f32");
         return MT_E_UNSUPPORTED;
       }
-      ln_bwd_kernel<COLS, TDY, TX, float, TDX, GELU, true><<<grid, 256, 0, st>>>(
+      ln_bwd_kernel<COLS, TDY, TX, float, TDX, GELU, true><<<grid, C::THREADS, 0, st>>>(
           (const TDY*)dy, (const TX*)x, xbias, gamma, mean, rstd, (const float*)residual, (TDX*)dx, dgamma, dbeta, rows);
     }
   } else if (residual == nullptr || rd == MT_F32)
-    ln_bwd_kernel<COLS, TDY, TX, float, TDX, GELU, false><<<grid, 256, 0, st>>>(
+    ln_bwd_kernel<COLS, TDY, TX, float, TDX, GELU, false><<<grid, C::THREADS, 0, st>>>(
         (const TDY*)dy, (const TX*)x, xbias, gamma, mean, rstd, (const float*)residual, (TDX*)dx, dgamma, dbeta, rows);
   else
-    ln_bwd_kernel<COLS, TDY, TX, __nv_bfloat16, TDX, GELU, false><<<grid, 256, 0, st>>>(
+    ln_bwd_kernel<COLS, TDY, TX, __nv_bfloat16, TDX, GELU, false><<<grid, C::THREADS, 0, st>>>(
         (const TDY*)dy, (const TX*)x, xbias, gamma, mean, rstd, (const __nv_bfloat16*)residual, (TDX*)dx, dgamma, dbeta, rows);
   return check_launch("ln_bwd_kernel");
 }
