@@ -44,6 +44,18 @@ typedef struct {
   int32_t ratio[MT_MAX_BRANCHES];
 } mt_dilated_geometry;
 
+/* Train-mode stochastic ops of the frozen encoder (torchscale/architecture/encoder.py:149-152,169-170:
+ * Dropout(p) then DropPath on each residual branch; feedforward_network.py:142).  A Philox4x32-10 counter RNG keyed by
+ * *seed generates the keep mask of element i of the tensor from (seed, stream_id, i): nothing is stored, the backward
+ * regenerates the same mask.  seed and path_scale are DEVICE pointers so that a CUDA graph replays fresh masks when
+ * the caller redraws them inside the graph.  A NULL mt_dropout* means eval mode (identity). */
+typedef struct {
+  float p;                 /* drop probability, 0 <= p < 1; kept elements are scaled by 1 / (1 - p)              */
+  const int64_t* seed;     /* device pointer to the 64-bit seed of this step                                      */
+  int64_t stream_id;       /* distinct per call site (layer, branch) so that masks are independent               */
+  const float* path_scale; /* device pointer to the DropPath factor of the branch (0 or 1 / keep), NULL = 1      */
+} mt_dropout;
+
 const char* mt_last_error(void);
 int mt_version(void);
 /* 1 when the running device is sm_100 (tcgen05 / TMA kernels usable), 0 otherwise, <0 on error */
@@ -71,11 +83,11 @@ int mt_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, c
                      float* dbeta, int64_t rows, int64_t cols, void* stream);
 
 /* residual add fused with the next pre-LN (torchscale/architecture/encoder.py:152-166):
- * x_out = x + a [+ abias] (f32 residual stream, a in a_dtype, abias [cols] f32 or NULL = bias of the GEMM that
- * produced a), y = LN(x_out).  cols = 768. */
+ * x_out = x + D(a [+ abias]) (f32 residual stream, a in a_dtype, abias [cols] f32 or NULL = bias of the GEMM that
+ * produced a; D = train-mode dropout + DropPath of the branch, identity when drop is NULL), y = LN(x_out).  cols = 768. */
 int mt_add_layernorm_fwd(const float* x, const void* a, int a_dtype, const float* abias, const float* gamma,
                          const float* beta, float* x_out, void* y, int y_dtype, float* mean, float* rstd, int64_t rows, int64_t cols,
-                         float eps, void* stream);
+                         float eps, const mt_dropout* drop, void* stream);
 
 /* ---- A6: GELU(fp32) + LayerNorm(3072) between fc1 and fc2 ---------------------------------------------------------
  * replaces: `activation_fn(x.float()).type_as(x)` + ffn_layernorm (torchscale/component/feedforward_network.py:135-140)
@@ -146,10 +158,15 @@ int mt_gated_residual(const float* a, const void* b, int b_dtype, const float* g
  * (dgate is zeroed by the call and accumulated with atomics). */
 int mt_gated_residual_bwd(const float* dy, const float* a, const void* b, int b_dtype, const float* gate, float* da,
                           void* db, int db_dtype, float* dgate, int64_t rows, int64_t cols, void* stream);
-/* y = x + a + bias: residual add after fc2 (torchscale/architecture/encoder.py:169-175), bias [cols] f32 or NULL. */
+/* y = x + D(a + bias): residual add after fc2 (torchscale/architecture/encoder.py:169-175), bias [cols] f32 or NULL,
+ * D = dropout + DropPath of the branch (drop NULL = identity). */
 int mt_residual_bias_add(const float* x, const void* a, int a_dtype, const float* bias, float* y, int64_t rows,
-                         int64_t cols, void* stream);
+                         int64_t cols, const mt_dropout* drop, void* stream);
 int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* backward of D: dst[i] = src[i] * keep_mask(i) / (1 - p) * path_scale, converted to dst_dtype (the gradient that
+ * enters the dX GEMM of the branch).  drop must not be NULL. */
+int mt_dropout_bwd_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, const mt_dropout* drop,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,14 @@ class DilatedGeometry(Structure):
     ]
 
 
+class Dropout(Structure):
+    """``mt_dropout`` (include/modaltune_b200.h): train-mode dropout + DropPath of one residual branch."""
+
+    _fields_ = [("p", c_float), ("seed", c_void_p), ("stream_id", c_int64), ("path_scale", c_void_p)]
+
+
 _G = POINTER(DilatedGeometry)
+_D = POINTER(Dropout)
 _P = c_void_p
 _I64 = c_int64
 
@@ -42,7 +49,7 @@ SIGNATURES = {
     "mt_embed_assemble": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_float, _P]),
     "mt_layernorm_fwd": (c_int, [_P, c_int, _P, _P, _P, c_int, _I64, _P, c_int, _P, _P, _I64, _I64, c_float, _P]),
     "mt_layernorm_bwd": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, c_int, _P, c_int, _P, _P, _I64, _I64, _P]),
-    "mt_add_layernorm_fwd": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _I64, _I64, c_float, _P]),
+    "mt_add_layernorm_fwd": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _I64, _I64, c_float, _D, _P]),
     "mt_gelu_ln_fwd": (c_int, [_P, c_int, _P, _P, _P, _P, c_int, _P, _P, _I64, _I64, c_float, _P]),
     "mt_gelu_ln_bwd": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, _P, c_int, _I64, _I64, _P]),
     "mt_dilated_attn_fwd": (c_int, [_G, _P, _I64, _I64, c_int, _P, _P, c_int, _P]),
@@ -54,7 +61,8 @@ SIGNATURES = {
     "mt_cross_attn_workspace_floats": (_I64, [_I64, _I64, c_int, c_int]),
     "mt_gated_residual": (c_int, [_P, _P, c_int, _P, _P, _I64, _I64, _P]),
     "mt_gated_residual_bwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, _P, _I64, _I64, _P]),
-    "mt_residual_bias_add": (c_int, [_P, _P, c_int, _P, _P, _I64, _I64, _P]),
+    "mt_residual_bias_add": (c_int, [_P, _P, c_int, _P, _P, _I64, _I64, _D, _P]),
+    "mt_dropout_bwd_cast": (c_int, [_P, c_int, _P, c_int, _I64, _D, _P]),
     "mt_cast": (c_int, [_P, c_int, _P, c_int, _I64, _P]),
 }
 

@@ -38,6 +38,67 @@ template <int COLS> struct RowCfg {
   static_assert(COLS % (8 * NCH) == 0 && TPR % 32 == 0 && THREADS % TPR == 0, "supported widths: 768, 3072");
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// train-mode dropout + DropPath: Philox4x32-10 keyed by the step seed, counter = (8-element chunk, stream id, half)
+// ---------------------------------------------------------------------------------------------------------------------
+struct DropArgs {
+  int on;                  // 0 = eval mode
+  uint32_t threshold;      // keep iff random u32 >= threshold (threshold = p * 2^32)
+  float inv_keep;          // 1 / (1 - p)
+  const int64_t* seed;
+  int64_t stream_id;
+  const float* path_scale;
+};
+
+static int make_drop_args(const mt_dropout* d, DropArgs* out) {
+  out->on = 0;
+  out->threshold = 0;
+  out->inv_keep = 1.f;
+  out->seed = nullptr;
+  out->stream_id = 0;
+  out->path_scale = nullptr;
+  if (d == nullptr) return 0;
+  if (!(d->p >= 0.f && d->p < 1.f) || d->seed == nullptr) {
+    set_error("dropout: p must be in [0, 1) and seed a device pointer");
+    return MT_E_BADARG;
+  }
+  out->on = 1;
+  out->threshold = (uint32_t)((double)d->p * 4294967296.0);
+  out->inv_keep = 1.f / (1.f - d->p);
+  out->seed = d->seed;
+  out->stream_id = d->stream_id;
+  out->path_scale = d->path_scale;
+  return 0;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 ctr) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+// multiplicative factors (0 or inv_keep * path_scale) of the 8 elements of chunk `chunk` (element index = 8 chunk + j)
+__device__ __forceinline__ void drop_factors8(const DropArgs& d, int64_t chunk, float (&m)[8]) {
+  const uint64_t seed = (uint64_t)__ldg(d.seed);
+  const float sc = d.inv_keep * (d.path_scale != nullptr ? __ldg(d.path_scale) : 1.f);
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint4 r = philox4x32_10(key, make_uint4((uint32_t)chunk, (uint32_t)((uint64_t)chunk >> 32),
+                                                  (uint32_t)d.stream_id, (uint32_t)(2 * (d.stream_id >> 32) + half)));
+    m[4 * half + 0] = r.x >= d.threshold ? sc : 0.f;
+    m[4 * half + 1] = r.y >= d.threshold ? sc : 0.f;
+    m[4 * half + 2] = r.z >= d.threshold ? sc : 0.f;
+    m[4 * half + 3] = r.w >= d.threshold ? sc : 0.f;
+  }
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
@@ -284,7 +345,8 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict
                                                          const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ x_out,
                                                          TY* __restrict__ y, float* __restrict__ mean,
-                                                         float* __restrict__ rstd, int64_t rows, float eps) {
+                                                         float* __restrict__ rstd, int64_t rows, float eps,
+                                                         const DropArgs drop) {
   using C = RowCfg<COLS>;
   __shared__ float red[C::RPB * (C::TPR / 32) + 1];
   const int t = threadIdx.x % C::TPR, rib = threadIdx.x / C::TPR;
@@ -299,13 +361,20 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict
         float av[8];
         load8(x + row * COLS + (i * C::TPR + t) * 8, v[i]);
         load8(a + row * COLS + (i * C::TPR + t) * 8, av);
+        if (abias != nullptr) {
+          float bv[8];
+          load8(abias + (i * C::TPR + t) * 8, bv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) av[j] += bv[j];
+        }
+        if (drop.on) {   // train mode: Dropout then DropPath on the branch, before the residual add (encoder.py:149-155)
+          float m[8];
+          drop_factors8(drop, row * (COLS / 8) + i * C::TPR + t, m);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) av[j] *= m[j];
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[i][j] += av[j];
-        if (abias != nullptr) {
-          load8(abias + (i * C::TPR + t) * 8, av);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[i][j] += av[j];
-        }
         store8(x_out + row * COLS + (i * C::TPR + t) * 8, v[i]);
       } else {
 #pragma unroll
@@ -383,7 +452,7 @@ __global__ void __launch_bounds__(256) gated_residual_bwd_kernel(const float* __
 template <typename TA>
 __global__ void __launch_bounds__(256) residual_bias_add_kernel(const float* __restrict__ x, const TA* __restrict__ a,
                                                                 const float* __restrict__ bias, float* __restrict__ y,
-                                                                int64_t rows, int cols) {
+                                                                int64_t rows, int cols, const DropArgs drop) {
   const int chunks = cols / 8;
   const int64_t total = rows * chunks;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -394,8 +463,30 @@ __global__ void __launch_bounds__(256) residual_bias_add_kernel(const float* __r
     load8(a + idx * 8, av);
     if (bias != nullptr) load8(bias + c, bv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = xv[j] + av[j] + (bias != nullptr ? bv[j] : 0.f);
+    for (int j = 0; j < 8; ++j) av[j] += (bias != nullptr ? bv[j] : 0.f);
+    if (drop.on) {
+      float m[8];
+      drop_factors8(drop, idx, m);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) av[j] *= m[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = xv[j] + av[j];
     store8(y + idx * 8, o);
+  }
+}
+
+// dst = src * keep_mask / (1 - p) * path_scale: the gradient of a dropped residual branch, converted for the dX GEMM
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) dropout_bwd_cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n8,
+                                                               const DropArgs drop) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n8; idx += (int64_t)gridDim.x * blockDim.x) {
+    float v[8], m[8];
+    load8(s + idx * 8, v);
+    drop_factors8(drop, idx, m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= m[j];
+    store8(d + idx * 8, v);
   }
 }
 
@@ -585,21 +676,23 @@ extern "C" int mt_gated_residual(const float* a, const void* b, int b_dtype, con
 extern "C" int mt_add_layernorm_fwd(const float* x, const void* a, int a_dtype, const float* abias, const float* gamma,
                                     const float* beta,
                                     float* x_out, void* y, int y_dtype, float* mean, float* rstd, int64_t rows,
-                                    int64_t cols, float eps, void* stream) {
+                                    int64_t cols, float eps, const mt_dropout* drop, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (rows == 0) return 0;
   MT_REQUIRE(cols == 768, "add_layernorm: width %lld not supported (768)", (long long)cols);
+  DropArgs D;
+  if (int rc = make_drop_args(drop, &D)) return rc;
   using C = RowCfg<768>;
   using bf = __nv_bfloat16;
   const int grid = grid_for(rows, C::RPB);
   if (a_dtype == MT_F32 && y_dtype == MT_F32)
-    add_ln_fwd_kernel<768, float, float><<<grid, 256, 0, st>>>(x, (const float*)a, abias, gamma, beta, x_out, (float*)y, mean, rstd, rows, eps);
+    add_ln_fwd_kernel<768, float, float><<<grid, 256, 0, st>>>(x, (const float*)a, abias, gamma, beta, x_out, (float*)y, mean, rstd, rows, eps, D);
   else if (a_dtype == MT_BF16 && y_dtype == MT_BF16)
-    add_ln_fwd_kernel<768, bf, bf><<<grid, 256, 0, st>>>(x, (const bf*)a, abias, gamma, beta, x_out, (bf*)y, mean, rstd, rows, eps);
+    add_ln_fwd_kernel<768, bf, bf><<<grid, 256, 0, st>>>(x, (const bf*)a, abias, gamma, beta, x_out, (bf*)y, mean, rstd, rows, eps, D);
   else if (a_dtype == MT_F32 && y_dtype == MT_BF16)
-    add_ln_fwd_kernel<768, float, bf><<<grid, 256, 0, st>>>(x, (const float*)a, abias, gamma, beta, x_out, (bf*)y, mean, rstd, rows, eps);
+    add_ln_fwd_kernel<768, float, bf><<<grid, 256, 0, st>>>(x, (const float*)a, abias, gamma, beta, x_out, (bf*)y, mean, rstd, rows, eps, D);
   else
-    add_ln_fwd_kernel<768, bf, float><<<grid, 256, 0, st>>>(x, (const bf*)a, abias, gamma, beta, x_out, (float*)y, mean, rstd, rows, eps);
+    add_ln_fwd_kernel<768, bf, float><<<grid, 256, 0, st>>>(x, (const bf*)a, abias, gamma, beta, x_out, (float*)y, mean, rstd, rows, eps, D);
   return check_launch("add_ln_fwd_kernel");
 }
 
@@ -623,16 +716,40 @@ extern "C" int mt_gated_residual_bwd(const float* dy, const float* a, const void
 }
 
 extern "C" int mt_residual_bias_add(const float* x, const void* a, int a_dtype, const float* bias, float* y,
-                                    int64_t rows, int64_t cols, void* stream) {
+                                    int64_t rows, int64_t cols, const mt_dropout* drop, void* stream) {
   MT_REQUIRE(cols % 8 == 0, "residual_bias_add: cols must be a multiple of 8");
   cudaStream_t st = (cudaStream_t)stream;
   if (rows == 0) return 0;
+  DropArgs D;
+  if (int rc = make_drop_args(drop, &D)) return rc;
   const int grid = grid_for(rows * (cols / 8), 256);
   if (a_dtype == MT_F32)
-    residual_bias_add_kernel<float><<<grid, 256, 0, st>>>(x, (const float*)a, bias, y, rows, (int)cols);
+    residual_bias_add_kernel<float><<<grid, 256, 0, st>>>(x, (const float*)a, bias, y, rows, (int)cols, D);
   else
-    residual_bias_add_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, (const __nv_bfloat16*)a, bias, y, rows, (int)cols);
+    residual_bias_add_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, (const __nv_bfloat16*)a, bias, y, rows, (int)cols, D);
   return check_launch("residual_bias_add_kernel");
+}
+
+extern "C" int mt_dropout_bwd_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,
+                                   const mt_dropout* drop, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MT_REQUIRE(drop != nullptr, "dropout_bwd_cast: drop must not be NULL (use mt_cast in eval mode)");
+  MT_REQUIRE(n % 8 == 0, "dropout_bwd_cast: element count must be a multiple of 8");
+  if (n == 0) return 0;
+  DropArgs D;
+  if (int rc = make_drop_args(drop, &D)) return rc;
+  const int64_t n8 = n / 8;
+  const int grid = grid_for(n8, 256);
+  using bf = __nv_bfloat16;
+  if (src_dtype == MT_F32 && dst_dtype == MT_BF16)
+    dropout_bwd_cast_kernel<float, bf><<<grid, 256, 0, st>>>((const float*)src, (bf*)dst, n8, D);
+  else if (src_dtype == MT_F32 && dst_dtype == MT_F32)
+    dropout_bwd_cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, n8, D);
+  else if (src_dtype == MT_BF16 && dst_dtype == MT_BF16)
+    dropout_bwd_cast_kernel<bf, bf><<<grid, 256, 0, st>>>((const bf*)src, (bf*)dst, n8, D);
+  else
+    dropout_bwd_cast_kernel<bf, float><<<grid, 256, 0, st>>>((const bf*)src, (float*)dst, n8, D);
+  return check_launch("dropout_bwd_cast_kernel");
 }
 
 extern "C" int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream) {

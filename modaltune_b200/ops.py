@@ -158,8 +158,28 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx_dtype, residual=None, want_wgrad:
     return dx, dgamma, dbeta
 
 
-def add_layernorm_fwd(x, a, gamma, beta, out_dtype, eps: float = LN_EPS, abias=None):
-    """x_out = x + a [+ abias] (fp32), y = LN(x_out)."""
+class DropSpec:
+    """Train-mode Dropout(p) + DropPath of one residual branch of the frozen encoder (``mt_dropout``): the keep mask of
+    element i comes from a counter RNG keyed by ``seed`` (device int64 [1]) and ``stream_id``; ``path_scale`` is the
+    device fp32 [1] DropPath factor (0 or 1 / keep) or None.  Nothing is stored: the backward regenerates the mask."""
+
+    def __init__(self, p: float, seed: torch.Tensor, stream_id: int, path_scale: Optional[torch.Tensor] = None):
+        assert 0.0 <= p < 1.0 and seed.dtype == torch.int64 and seed.is_cuda and seed.numel() == 1
+        assert path_scale is None or (path_scale.dtype == torch.float32 and path_scale.is_cuda and path_scale.numel() == 1)
+        self.p, self.seed, self.stream_id, self.path_scale = float(p), seed, int(stream_id), path_scale
+        self.c_struct = _lib.Dropout(self.p, seed.data_ptr(), self.stream_id,
+                                     path_scale.data_ptr() if path_scale is not None else None)
+
+    def ref(self):
+        return ctypes.byref(self.c_struct)
+
+
+def _drop(d: Optional[DropSpec]):
+    return d.ref() if d is not None else None
+
+
+def add_layernorm_fwd(x, a, gamma, beta, out_dtype, eps: float = LN_EPS, abias=None, drop: Optional[DropSpec] = None):
+    """x_out = x + D(a [+ abias]) (fp32), y = LN(x_out); D = train-mode dropout / DropPath (identity when drop is None)."""
     rows, cols = x.shape
     assert x.dtype == torch.float32
     x_out = torch.empty_like(x)
@@ -167,7 +187,7 @@ def add_layernorm_fwd(x, a, gamma, beta, out_dtype, eps: float = LN_EPS, abias=N
     mean = torch.empty(rows, device=x.device, dtype=torch.float32)
     rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
     rc = _lib.load().mt_add_layernorm_fwd(_p(x), _p(a), _dt(a), _p(abias), _p(gamma), _p(beta), _p(x_out), _p(y), _dt(y),
-                                          _p(mean), _p(rstd), rows, cols, eps, _stream())
+                                          _p(mean), _p(rstd), rows, cols, eps, _drop(drop), _stream())
     _check(rc, "mt_add_layernorm_fwd")
     return x_out, y, mean, rstd
 
@@ -192,13 +212,21 @@ def gelu_ln_bwd(dy, h, gamma, mean, rstd, out_dtype, hbias=None):
     return dh
 
 
-def residual_bias_add(x, a, bias):
-    """y = x + a + bias (fp32 residual stream)."""
+def residual_bias_add(x, a, bias, drop: Optional[DropSpec] = None):
+    """y = x + D(a + bias) (fp32 residual stream)."""
     rows, cols = x.shape
     y = torch.empty_like(x)
-    rc = _lib.load().mt_residual_bias_add(_p(x), _p(a), _dt(a), _p(bias), _p(y), rows, cols, _stream())
+    rc = _lib.load().mt_residual_bias_add(_p(x), _p(a), _dt(a), _p(bias), _p(y), rows, cols, _drop(drop), _stream())
     _check(rc, "mt_residual_bias_add")
     return y
+
+
+def dropout_bwd_cast(src: torch.Tensor, dtype: torch.dtype, drop: DropSpec) -> torch.Tensor:
+    """Gradient of a dropped branch: src * keep_mask / (1 - p) * path_scale in ``dtype`` (same mask as the forward)."""
+    dst = torch.empty(src.shape, device=src.device, dtype=dtype)
+    rc = _lib.load().mt_dropout_bwd_cast(_p(src), _dt(src), _p(dst), _dt(dst), src.numel(), drop.ref(), _stream())
+    _check(rc, "mt_dropout_bwd_cast")
+    return dst
 
 
 def dilated_attn_fwd(geom: Geometry, qkv: torch.Tensor, impl: int):
@@ -521,8 +549,10 @@ def _qkv_project(h1: torch.Tensor, W: FrozenLayerWeights, geom: Geometry) -> tor
     return qkv
 
 
-def encoder_layer_forward(x: torch.Tensor, W: FrozenLayerWeights, geom: Geometry, cdt: torch.dtype, impl):
-    """x [N, 768] fp32 -> (y fp32, saved tensors); ``impl`` = (forward, backward) attention kernel selectors.  Eval-mode EncoderLayer (encoder.py:121-175)."""
+def encoder_layer_forward(x: torch.Tensor, W: FrozenLayerWeights, geom: Geometry, cdt: torch.dtype, impl, rng=None):
+    """x [N, 768] fp32 -> (y fp32, saved tensors); ``impl`` = (forward, backward) attention kernel selectors.
+    EncoderLayer.forward (encoder.py:121-175); ``rng`` = (DropSpec of the attention branch, DropSpec of the FFN branch)
+    in train mode, None in eval mode."""
     h1, mean1, rstd1 = layernorm_fwd(x, W.ln1[0], W.ln1[1], cdt)
     qkv = _qkv_project(h1, W, geom)
     del h1
@@ -530,24 +560,29 @@ def encoder_layer_forward(x: torch.Tensor, W: FrozenLayerWeights, geom: Geometry
     a_ln, _, lse, mean_a, rstd_a = dilated_merge_ln_fwd(geom, o_br, lse_br, W.ln_in[0], W.ln_in[1])
     attn_out = _linear_f32out(a_ln, W.w_o)                   # fp32 [N, 768], bias added by the consumer
     del a_ln
-    x1, h2, mean2, rstd2 = add_layernorm_fwd(x, attn_out, W.ln2[0], W.ln2[1], cdt, abias=W.b_o)
+    x1, h2, mean2, rstd2 = add_layernorm_fwd(x, attn_out, W.ln2[0], W.ln2[1], cdt, abias=W.b_o,
+                                             drop=rng[0] if rng else None)
     del attn_out
     f1 = _linear_f32out(h2, W.w_1)                           # fp32 [N, 3072] WITHOUT fc1's bias, kept for the backward
     del h2
     g, mean_f, rstd_f = gelu_ln_fwd(f1, W.ln_ffn[0], W.ln_ffn[1], cdt, hbias=W.b_1)
     f2 = _linear_f32out(g, W.w_2)
     del g
-    y = residual_bias_add(x1, f2, W.b_2)
+    y = residual_bias_add(x1, f2, W.b_2, drop=rng[1] if rng else None)
     saved = (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f)
     return y, saved
 
 
-def encoder_layer_backward(dy: torch.Tensor, saved, W: FrozenLayerWeights, geom: Geometry, cdt: torch.dtype, impl):
+def encoder_layer_backward(dy: torch.Tensor, saved, W: FrozenLayerWeights, geom: Geometry, cdt: torch.dtype, impl,
+                           rng=None):
     """dX of the frozen layer (no weight gradients: every parameter of the slide encoder is frozen,
-    longvit_adapter.py:78-80)."""
+    longvit_adapter.py:78-80).  ``rng``: the DropSpecs of the forward (the masks are regenerated, not stored)."""
     (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f) = saved
     dy = dy.contiguous()
-    d_f2 = dy if cdt == torch.float32 else cast(dy, cdt)
+    if rng:
+        d_f2 = dropout_bwd_cast(dy, cdt, rng[1])
+    else:
+        d_f2 = dy if cdt == torch.float32 else cast(dy, cdt)
     dg = _matmul_f32out(d_f2, W.w_2)                                 # fp32 [N, 3072]
     d_f1 = gelu_ln_bwd(dg, f1, W.ln_ffn[0], mean_f, rstd_f, cdt, hbias=W.b_1)
     del dg
@@ -555,7 +590,10 @@ def encoder_layer_backward(dy: torch.Tensor, saved, W: FrozenLayerWeights, geom:
     del d_f1
     dx1, _, _ = layernorm_bwd(dh2, x1, W.ln2[0], mean2, rstd2, torch.float32, residual=dy)
     del dh2
-    d_out = dx1 if cdt == torch.float32 else cast(dx1, cdt)
+    if rng:
+        d_out = dropout_bwd_cast(dx1, cdt, rng[0])
+    else:
+        d_out = dx1 if cdt == torch.float32 else cast(dx1, cdt)
     d_aln = _matmul_f32out(d_out, W.w_o)                             # fp32 [N, 768]
     dattn, delta_br = dilated_merge_ln_bwd(geom, d_aln, o_br, lse_br, W.ln_in[0], mean_a, rstd_a)
     del d_aln
@@ -568,23 +606,37 @@ def encoder_layer_backward(dy: torch.Tensor, saved, W: FrozenLayerWeights, geom:
 
 class FrozenEncoderLayerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, W, geom, cdt, impl):
-        y, saved = encoder_layer_forward(x.contiguous(), W, geom, cdt, impl)
+    def forward(ctx, x, W, geom, cdt, impl, rng):
+        y, saved = encoder_layer_forward(x.contiguous(), W, geom, cdt, impl, rng)
         ctx.save_for_backward(*saved)
-        ctx.W, ctx.geom, ctx.cdt, ctx.impl = W, geom, cdt, impl
+        ctx.W, ctx.geom, ctx.cdt, ctx.impl, ctx.rng = W, geom, cdt, impl, rng
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        dx = encoder_layer_backward(dy, ctx.saved_tensors, ctx.W, ctx.geom, ctx.cdt, ctx.impl)
-        return dx, None, None, None, None
+        dx = encoder_layer_backward(dy, ctx.saved_tensors, ctx.W, ctx.geom, ctx.cdt, ctx.impl, ctx.rng)
+        return dx, None, None, None, None, None
 
 
-def frozen_encoder_layer(x, W, geom, cdt, impl):
+def frozen_encoder_layer(x, W, geom, cdt, impl, rng=None):
     if torch.is_grad_enabled() and x.requires_grad:
-        return FrozenEncoderLayerFn.apply(x, W, geom, cdt, impl)
-    y, _ = encoder_layer_forward(x.contiguous(), W, geom, cdt, impl)
+        return FrozenEncoderLayerFn.apply(x, W, geom, cdt, impl, rng)
+    y, _ = encoder_layer_forward(x.contiguous(), W, geom, cdt, impl, rng)
     return y
+
+
+def train_rng(device, dropout: float, drop_path: float, stream_base: int):
+    """The two DropSpecs of one encoder-layer call in train mode: a fresh 64-bit seed and the DropPath factors of the
+    attention and FFN branches drawn on the device with torch's generator (graph-capture safe: a captured step redraws
+    them on every replay).  timm's drop_path (per sample, scaled by 1 / keep) with batch 1 is one Bernoulli per branch."""
+    seed = torch.randint(0, 2 ** 62, (1,), device=device, dtype=torch.int64)
+    if drop_path > 0.0:
+        keep = 1.0 - drop_path
+        scales = (torch.rand(2, device=device) < keep).float() / keep
+        ps = (scales[0:1], scales[1:2])
+    else:
+        ps = (None, None)
+    return DropSpec(dropout, seed, stream_base, ps[0]), DropSpec(dropout, seed, stream_base + 1, ps[1])
 
 
 def attention_flops(geom: Geometry) -> Tuple[float, float]:

@@ -13,7 +13,9 @@ Differences by design:
 * ``pos_embed`` is not materialised as the reference's [1, 1_000_001, 768] fp32 buffer (3 GB, ``slide_encoder.py:118``).
   The 2-D sincos table is separable (``pos_embed.py:34-81``): ``pos_embed[1 + i*G + j] = [T[j] | T[i]]`` with one
   [G, 384] factor ``pos_table``; the embedding kernel adds it on the fly.  ``pos_embed_rows(pos)`` reproduces any rows.
-* the encoder runs the eval-mode arithmetic (dropout / droppath of the frozen encoder are identity), see DESIGN.md.
+* in ``train()`` mode the frozen encoder applies its Dropout(0.25) / DropPath like the reference (encoder.py:149-152,
+  169-170, 339; feedforward_network.py:142), fused into the residual kernels with counter-based masks that the backward
+  regenerates; parity against the reference is defined in ``eval()`` mode (masks cannot be bit-matched), see DESIGN.md.
 """
 from __future__ import annotations
 
@@ -83,9 +85,12 @@ class _FeedForward(nn.Module):
 class LongNetEncoderLayer(nn.Module):
     """One pre-LN / sub-LN LongNet block (TS/architecture/encoder.py:24-175 with DilatedAttention)."""
 
-    def __init__(self, embed_dim: int, num_heads: int, ffn_dim: int, segment_lengths, ratios, eps: float = 1e-5):
+    def __init__(self, embed_dim: int, num_heads: int, ffn_dim: int, segment_lengths, ratios, eps: float = 1e-5,
+                 dropout: float = 0.0, drop_path: float = 0.0, layer_index: int = 0):
         super().__init__()
         self.embed_dim = embed_dim
+        # train-mode stochastic ops of the frozen layer (encoder.py:69-75,149-152,169-170; feedforward_network.py:142)
+        self.dropout, self.drop_path_prob, self.layer_index = float(dropout), float(drop_path), int(layer_index)
         self.self_attn = _SelfAttention(embed_dim, num_heads, eps)
         self.self_attn_layer_norm = nn.LayerNorm(embed_dim, eps=eps)
         self.ffn = _FeedForward(embed_dim, ffn_dim, eps)
@@ -106,7 +111,11 @@ class LongNetEncoderLayer(nn.Module):
         W = self._weights.refresh(self, cdt)
         geom = ops.Geometry.get(N, self.segment_lengths, self.ratios)
         impl = (config.attn_impl("fwd"), config.attn_impl("bwd"))
-        outs = [ops.frozen_encoder_layer(x[b].float(), W, geom, cdt, impl) for b in range(B)]
+        rng = None
+        if self.training and (self.dropout > 0.0 or self.drop_path_prob > 0.0):
+            assert B == 1, "train-mode DropPath is drawn per sample; the ModalTune path runs one slide per step"
+            rng = ops.train_rng(x.device, self.dropout, self.drop_path_prob, 2 * self.layer_index)
+        outs = [ops.frozen_encoder_layer(x[b].float(), W, geom, cdt, impl, rng) for b in range(B)]
         y = outs[0].unsqueeze(0) if B == 1 else torch.stack(outs, 0)
         return y, None
 
@@ -115,22 +124,28 @@ class LongNetEncoder(nn.Module):
     """``encoder`` attribute of LongNetViT (TS/architecture/encoder.py:178-436, TS/model/LongNet.py:53-82)."""
 
     def __init__(self, embed_dim: int, depth: int, num_heads: int, ffn_dim: int, segment_lengths, ratios,
-                 eps: float = 1e-5):
+                 eps: float = 1e-5, dropout: float = 0.0, drop_path_rate: float = 0.0):
         super().__init__()
+        # DropPath probability grows linearly with depth (encoder.py:37-41: np.linspace(0, rate, layers)[depth])
+        dp = [drop_path_rate * l / max(depth - 1, 1) for l in range(depth)] if drop_path_rate > 0 else [0.0] * depth
         self.layers = nn.ModuleList([
-            LongNetEncoderLayer(embed_dim, num_heads, ffn_dim, segment_lengths, ratios, eps) for _ in range(depth)])
+            LongNetEncoderLayer(embed_dim, num_heads, ffn_dim, segment_lengths, ratios, eps, dropout=dropout,
+                                drop_path=dp[l], layer_index=l) for l in range(depth)])
+        self.dropout = float(dropout)
         self.layer_norm = nn.LayerNorm(embed_dim, eps=eps)  # encoder_normalize_before; unused by the adapter
         self.embed_scale = 1.0  # no_scale_embedding=True
         self.num_layers = depth
 
     def prepare_forward(self, src_tokens, encoder_padding_mask=None, token_embeddings=None,
                         multiway_split_position=None, positions=None, **kwargs):
-        """encoder.py:342-385: scale (1), mask multiply (all ones) and dropout (eval: identity)."""
+        """encoder.py:342-385: scale (1), dropout on the embedded tokens (:339, train mode only), mask multiply (ones)."""
         assert token_embeddings is not None, "the slide encoder is driven by token embeddings"
-        x = token_embeddings
+        emb = x = token_embeddings
+        if self.training and self.dropout > 0.0:
+            x = torch.nn.functional.dropout(emb, self.dropout, True)
         if encoder_padding_mask is None:
             encoder_padding_mask = torch.zeros(x.shape[:2], device=x.device, dtype=torch.bool)
-        return x, x, encoder_padding_mask, None
+        return x, emb, encoder_padding_mask, None
 
     def layer_forward(self, x, rel_pos_bias=None, encoder_padding_mask=None, attn_mask=None, return_all_hiddens=False,
                       multiway_split_position=None, features_only=False, incremental_state=None, **kwargs):
@@ -166,7 +181,7 @@ class LongNetViT(nn.Module):
         assert embed_dim == ops.EMBED, "the kernels are built for the 768-d / 16-head GigaPath slide encoder"
         self.segment_lengths = optimal_segment_lengths(max_wsi_size, tile_size)
         self.encoder = LongNetEncoder(embed_dim, depth, ops.HEADS, int(embed_dim * mlp_ratio), self.segment_lengths,
-                                      DILATED_RATIO)
+                                      DILATED_RATIO, dropout=dropout, drop_path_rate=drop_path_rate)
         self.norm = nn.LayerNorm(embed_dim, eps=1e-6)  # unused by the adapter (longvit_adapter.py:309-312)
         self.global_pool = global_pool
         self.initialize_vit_weights()

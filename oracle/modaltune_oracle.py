@@ -227,13 +227,18 @@ def feed_forward(sd: Dict[str, Tensor], prefix: str, x: Tensor) -> Tensor:
     return F.linear(h, sd[f"{prefix}.fc2.weight"].to(dt), sd[f"{prefix}.fc2.bias"].to(dt))
 
 
-def encoder_layer(sd: Dict[str, Tensor], l: int, x: Tensor, segment_lengths, ratios) -> Tensor:
-    """Pre-LN block with sub-LN, alpha = 1 (encoder.py:137-175).  Dropout / DropPath are identity in eval."""
+def encoder_layer(sd: Dict[str, Tensor], l: int, x: Tensor, segment_lengths, ratios, masks=None) -> Tensor:
+    """Pre-LN block with sub-LN, alpha = 1 (encoder.py:137-175).  Dropout / DropPath are identity in eval; in train mode
+    the reference applies Dropout(p) then DropPath to each residual branch before the add (encoder.py:149-155, 169-172;
+    the FFN's own output dropout, feedforward_network.py:142, multiplies the same tensor): ``masks`` = the two
+    multiplicative factors (keep / (1 - p) * path_scale, [N, 768]) of the attention and FFN branches."""
     p = f"encoder.layers.{l}"
     h = layer_norm(x, sd[f"{p}.self_attn_layer_norm.weight"], sd[f"{p}.self_attn_layer_norm.bias"])
-    x = x + dilated_self_attention(sd, f"{p}.self_attn", h, segment_lengths, ratios)
+    a = dilated_self_attention(sd, f"{p}.self_attn", h, segment_lengths, ratios)
+    x = x + (a if masks is None else a * masks[0].to(a.dtype))
     h = layer_norm(x, sd[f"{p}.final_layer_norm.weight"], sd[f"{p}.final_layer_norm.bias"])
-    return x + feed_forward(sd, f"{p}.ffn", h)
+    f = feed_forward(sd, f"{p}.ffn", h)
+    return x + (f if masks is None else f * masks[1].to(f.dtype))
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -49,7 +49,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx_dtype, residual=None, want_wgrad=
     return dx, dg, db
 
 
-def add_layernorm_fwd(x, a, gamma, beta, out_dtype, eps=1e-5, abias=None):
+def add_layernorm_fwd(x, a, gamma, beta, out_dtype, eps=1e-5, abias=None, drop=None):
+    assert drop is None, "the CPU stand-ins cover the eval-mode host logic only"
     x_out = x + a.float() + (abias if abias is not None else 0.0)
     y, mean, rstd = layernorm_fwd(x_out, gamma, beta, out_dtype, eps=eps)
     return x_out, y, mean, rstd
@@ -60,7 +61,8 @@ def gelu_ln_fwd(h, gamma, beta, out_dtype, eps=1e-5, hbias=None):
     return layernorm_fwd(F.gelu(hb), gamma, beta, out_dtype, eps=eps)
 
 
-def residual_bias_add(x, a, bias):
+def residual_bias_add(x, a, bias, drop=None):
+    assert drop is None, "the CPU stand-ins cover the eval-mode host logic only"
     return x + a.float() + (bias if bias is not None else 0.0)
 
 
