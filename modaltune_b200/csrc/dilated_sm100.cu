@@ -344,8 +344,16 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
   const int H = P.geo.H, N = P.geo.N, E = H * DH;
   const int off = (h * bg.r) / H;                    // residue of the positions this head owns
   const int jseg = (s * bg.g) / bg.r;                // first slot of the segment in the branch's j axis
-  const int n_kv = P.tiles[b];
   const int q0 = qt * BT;
+  // Zero padding (positions >= N in the last segment, dilated_attention.py:82-111) in whole tiles is never computed:
+  // a query tile without a real position writes nothing, and key tiles without a real position are all zero keys
+  // (score 0, value 0), whose only effect -- n_zero_tail * exp(0 - max) in the softmax denominator -- is added in
+  // closed form in the epilogue.  At 32k tiles 30 % of the padded tile pairs of the reference disappear this way.
+  const int seg_lo = s * bg.g + off;
+  const int c_real = min(N, (s + 1) * bg.g) > seg_lo ? (min(N, (s + 1) * bg.g) - seg_lo + bg.r - 1) / bg.r : 0;
+  if (q0 >= c_real) return;
+  const int n_kv = min(P.tiles[b], (c_real + BT - 1) / BT);
+  const int n_zero_tail = max(0, bg.m - n_kv * BT);
 
   const uint32_t bar_q_full = sbase + FwdSmem::BAR + 0;
   const uint32_t bar_kv_full = sbase + FwdSmem::BAR + 8;    // [2]
@@ -549,6 +557,14 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] = t[i];
+    }
+    if (n_zero_tail > 0) {   // the zero keys of the tiles that were skipped
+      const float m_fin = fmaxf(m_used, 0.f);
+      const float alpha = ex2((m_used - m_fin) * scale_log2);
+      l_run = l_run * alpha + (float)n_zero_tail * ex2(-m_fin * scale_log2);
+#pragma unroll
+      for (int i = 0; i < DH; ++i) o_acc[i] *= alpha;
+      m_used = m_fin;
     }
     if (slot < bg.m && pos < seg_end) {
       const float inv = 1.f / l_run;
@@ -1536,10 +1552,15 @@ dilated_bwd3_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_
   const int H = P.geo.H, N = P.geo.N, E = H * DH;
   const int off = (h * bg.r) / H;
   const int jseg = (s * bg.g) / bg.r;
-  const int n_q = P.tiles[b];
   const int k0 = kt * BT;
   const int seg_end = min(N, (s + 1) * bg.g);
   const int slot_h = h - off * bg.hpb;
+  // Whole tiles of zero padding (positions >= N in the last segment) are skipped: a zero key tile has K = V = 0, so it
+  // adds nothing to dQ and its own dK / dV rows are scratch; a padding query tile has P = 0.
+  const int seg_lo = s * bg.g + off;
+  const int c_real = seg_end > seg_lo ? (seg_end - seg_lo + bg.r - 1) / bg.r : 0;   // real slots of this (segment, head)
+  if (k0 >= c_real) return;
+  const int n_q = min(P.tiles[b], (c_real + BT - 1) / BT);
 
   constexpr int NQ = Bwd3Smem::NQ;
   const uint32_t bar_kv_full = sbase + Bwd3Smem::BAR + 0;
