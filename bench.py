@@ -288,7 +288,7 @@ def main():
     # for the configuration that capture was taken on
     traffic, traffic_src = None, None
     if args.tiles == 10000 and config.attn_impl("bwd") == 3:
-        traffic = 243.451648e6 + 100.084480e6
+        traffic = 242.375936e6 + 97.083392e6
         traffic_src = "profiles/r1_ncu_attention_v3.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
     bwd_names = {0: "simt", 1: "tcgen05", 2: "tcgen05-tmem", 3: "tcgen05-tmem-aug"}
     fwd_names = {0: "simt", 1: "tcgen05", 2: "tcgen05-tmem-acc"}
