@@ -165,6 +165,13 @@ class LongNetGeneAdapter(LongNetViT):
                 continue
             st = streams[k - 1]
             st.wait_stream(cur)
+            # Everything allocated on the calling stream that this pass reads (forward AND backward, through autograd's
+            # saved tensors) must be known to the allocator as in use on the side stream: otherwise its block can be
+            # handed out again on the calling stream while a side-stream kernel is still queued to read it (seen as a
+            # wrong task_weight gradient: the 12-byte one-hot task token was recycled during the backward).
+            for tns in (*shared, clinical, t):
+                if torch.is_tensor(tns) and tns.is_cuda:
+                    tns.record_stream(st)
             with torch.cuda.stream(st):
                 outs[k] = self._adapter_forward(None, None, None, clinical, t, None, None, None, shared=shared)
         outs[0] = self._adapter_forward(None, None, None, clinical, task_tokens[0], None, None, None, shared=shared)
@@ -172,6 +179,15 @@ class LongNetGeneAdapter(LongNetViT):
             cur.wait_stream(streams[k - 1])
             outs[k].record_stream(cur)   # allocated on the side stream, read by the cat below on the calling stream
         return torch.cat(outs, 0)
+
+    def join_pass_streams(self):
+        """Make the current stream wait for everything queued on the task-pass streams (call after a backward)."""
+        streams = self.__dict__.get("_streams", [])
+        if not streams:
+            return
+        cur = torch.cuda.current_stream()
+        for st in streams:
+            cur.wait_stream(st)
 
     def _task_streams(self, n):
         pool = self.__dict__.setdefault("_streams", [])

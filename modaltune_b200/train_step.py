@@ -58,10 +58,20 @@ def distill_loss(logits: torch.Tensor, text_proj: torch.Tensor) -> torch.Tensor:
 
 
 def forward_backward(model, projector, slide: Dict):
-    """One slide step: returns (loss, logits).  Gradients are left in ``p.grad`` of the trainable parameters."""
+    """One slide step: returns (loss, logits).  Gradients are left in ``p.grad`` of the trainable parameters.
+
+    The gradients are taken with ``torch.autograd.grad`` and assigned, not accumulated by ``loss.backward()``: an
+    AccumulateGrad node remembers the CUDA stream of the step that created it, and a node kept alive from an earlier
+    (eager, default-stream) step silently breaks a later multi-stream CUDA-graph capture of the same model."""
     logits = multitask_forward(model, slide)
     loss = distill_loss(logits, text_targets(projector, slide["text"]))
-    loss.backward()
+    params = [p for p in model.parameters() if p.requires_grad]
+    grads = torch.autograd.grad(loss, params, allow_unused=True)
+    if hasattr(model, "join_pass_streams"):
+        model.join_pass_streams()     # the backward of a task pass runs on the stream of its forward
+    for p, g in zip(params, grads):
+        if g is not None:
+            p.grad = g if p.grad is None else p.grad + g
     return loss.detach(), logits.detach()
 
 
