@@ -196,6 +196,10 @@ def test_dilated_attention_linearity_in_v_at_full_size():
 # tcgen05 / TMA dilated attention (impl = 1) against the fp32-math SIMT kernels and the oracle
 # ---------------------------------------------------------------------------------------------------------------------
 SM100_GEOMS = GEOMS + [(5793, None), (10001, None), (300, [128, 256, 512, 1024, 2048]),
+                       # whole-tile padding skip: last segments with 1 / 128 / 129 real slots, real counts that are
+                       # exact multiples of the 128-slot tile, tails of several all-padding tiles in every branch
+                       (1153, None), (2177, [1024, 2048, 4096, 8192, 16384]), (8193, None), (16385, None),
+                       (4224, [512, 1024, 2048, 4096, 8192]), (12289, [4096, 4096, 8192, 8192, 16384]),
                        (32769, None),   # C3: 33 x 1024, 6 x 5792 and the 2 x 32768 branch whose tail segment is all padding
                        (40001, None)]   # C5 upper end
 
