@@ -25,15 +25,16 @@ __device__ __forceinline__ float row_sum(float v, float* red, int row_in_block, 
   }
 }
 
-// 768 columns: one warp per row, 3 chunks of 8 elements per thread, 8 rows per 256-thread block.
-// 3072 columns: 384 threads per row with ONE chunk per thread: the GELU kernels need ~100 registers per thread with three
-// chunks, which caps them at 512 resident threads per SM -- too few loads in flight to hide the erf arithmetic behind
-// HBM; with one chunk they run three 384-thread blocks per SM.
+// One 8-element chunk per thread: 96 threads per row for 768 columns (4 rows per 384-thread block), 384 threads per row
+// for 3072 columns.  With three chunks per thread the backward kernels need ~100-128 registers, which caps them at 512
+// resident threads per SM -- too few loads in flight to hide the arithmetic (erf, reductions) behind HBM; with one chunk
+// they fit in 56 registers and run three 384-thread blocks per SM (measured: LN backward 768 -25 %, GELU+LN(3072)
+// forward -18 %, backward -10 %).
 template <int COLS> struct RowCfg {
-  static constexpr int NCH = COLS == 3072 ? 1 : 3;   // 8-element chunks per thread
-  static constexpr int TPR = COLS / (8 * NCH);       // threads per row
-  static constexpr int THREADS = COLS == 3072 ? 384 : 256;
-  static constexpr int MINB = COLS == 3072 ? 3 : 2;  // resident blocks per SM the register budget is set for
+  static constexpr int NCH = 1;                      // 8-element chunks per thread
+  static constexpr int TPR = COLS / (8 * NCH);       // threads per row: 96 (768 columns) or 384 (3072 columns)
+  static constexpr int THREADS = 384;
+  static constexpr int MINB = 3;                     // resident blocks per SM the register budget is set for
   static constexpr int RPB = THREADS / TPR;          // rows per block iteration
   static_assert(COLS % (8 * NCH) == 0 && TPR % 32 == 0 && THREADS % TPR == 0, "supported widths: 768, 3072");
 };
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(256) gated_residual_kernel(const float* __rest
 // x_out = x + a (fp32 residual stream), y = LN(x_out) * gamma + beta: the residual add after the attention / FFN branch
 // fused with the next block's pre-LN (encoder.py:152-166), one pass over HBM.
 template <int COLS, typename TA, typename TY>
-__global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict__ x, const TA* __restrict__ a,
+__global__ void __launch_bounds__(RowCfg<COLS>::THREADS, RowCfg<COLS>::MINB) add_ln_fwd_kernel(const float* __restrict__ x, const TA* __restrict__ a,
                                                          const float* __restrict__ abias,
                                                          const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ x_out,
@@ -686,13 +687,13 @@ extern "C" int mt_add_layernorm_fwd(const float* x, const void* a, int a_dtype, 
   using bf = __nv_bfloat16;
   const int grid = grid_for(rows, C::RPB);
   if (a_dtype == MT_F32 && y_dtype == MT_F32)
-    add_ln_fwd_kernel<768, float, float><<<grid, 256, 0, st>>>(x, (const float*)a, abias, gamma, beta, x_out, (float*)y, mean, rstd, rows, eps, D);
+    add_ln_fwd_kernel<768, float, float><<<grid, C::THREADS, 0, st>>>(x, (const float*)a, abias, gamma, beta, x_out, (float*)y, mean, rstd, rows, eps, D);
   else if (a_dtype == MT_BF16 && y_dtype == MT_BF16)
-    add_ln_fwd_kernel<768, bf, bf><<<grid, 256, 0, st>>>(x, (const bf*)a, abias, gamma, beta, x_out, (bf*)y, mean, rstd, rows, eps, D);
+    add_ln_fwd_kernel<768, bf, bf><<<grid, C::THREADS, 0, st>>>(x, (const bf*)a, abias, gamma, beta, x_out, (bf*)y, mean, rstd, rows, eps, D);
   else if (a_dtype == MT_F32 && y_dtype == MT_BF16)
-    add_ln_fwd_kernel<768, float, bf><<<grid, 256, 0, st>>>(x, (const float*)a, abias, gamma, beta, x_out, (bf*)y, mean, rstd, rows, eps, D);
+    add_ln_fwd_kernel<768, float, bf><<<grid, C::THREADS, 0, st>>>(x, (const float*)a, abias, gamma, beta, x_out, (bf*)y, mean, rstd, rows, eps, D);
   else
-    add_ln_fwd_kernel<768, bf, float><<<grid, 256, 0, st>>>(x, (const bf*)a, abias, gamma, beta, x_out, (float*)y, mean, rstd, rows, eps, D);
+    add_ln_fwd_kernel<768, bf, float><<<grid, C::THREADS, 0, st>>>(x, (const bf*)a, abias, gamma, beta, x_out, (float*)y, mean, rstd, rows, eps, D);
   return check_launch("add_ln_fwd_kernel");
 }
 
