@@ -1,12 +1,12 @@
 // HBM-bound fused kernels of the path: embedding assembly (A0), LayerNorm fwd/bwd (A1), GELU+LayerNorm(3072) fwd/bwd
-// (A6), gated residual (A7 tail), casts.  All accesses are 128-bit vectorised; one row is owned by COLS/24 threads and
-// every thread keeps its 24 elements in registers between the statistics pass and the write (single HBM pass).
+// (A6), gated residual (A7 tail), casts.  All accesses are 128-bit vectorised; one row is owned by COLS/8 threads and
+// every thread keeps its 8 elements in registers between the statistics pass and the write (single HBM pass).
 #include "mt_common.cuh"
 
 namespace mt {
 
 // ---------------------------------------------------------------------------------------------------------------------
-// row reductions: TPR threads per row (32 -> one warp, 128 -> four warps through shared memory)
+// row reductions: TPR threads per row (32 -> one warp, otherwise TPR / 32 warps through shared memory)
 // ---------------------------------------------------------------------------------------------------------------------
 template <int TPR>
 __device__ __forceinline__ float row_sum(float v, float* red, int row_in_block, int t) {
