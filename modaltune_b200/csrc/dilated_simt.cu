@@ -307,54 +307,86 @@ __global__ void __launch_bounds__(256) dilated_bwd_simt_kernel(const SimtParams 
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Branch merge + inner_attn_ln.  One warp per position; lane l owns head l/2, half l%2 (24 contiguous channels).
+// Ownership of (position, head) by a branch is pure index arithmetic, so every load of a row -- the lse AND the 24
+// output channels of all owning branches -- is issued before the first one is consumed (one memory latency per row),
+// and the branch outputs stay in registers for the per-branch delta of the backward (o_br is read once).
+// NB = compile-time bound on the number of branches (5 for the GigaPath configuration, MT_MAX_BRANCHES otherwise).
 // ---------------------------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T> struct Raw24;
+template <> struct Raw24<__nv_bfloat16> {
+  uint4 u[3];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    u[0] = s[0]; u[1] = s[1]; u[2] = s[2];
+  }
+  __device__ __forceinline__ float get(int j) const {
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(u)[j]);
+  }
+};
+template <> struct Raw24<float> {
+  float4 u[6];
+  __device__ __forceinline__ void load(const float* p) {
+    const float4* s = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) u[i] = s[i];
+  }
+  __device__ __forceinline__ float get(int j) const { return reinterpret_cast<const float*>(u)[j]; }
+};
+
+template <typename T, int NB>
+struct MergedRow {
+  Raw24<T> o[NB];     // the 24 channels of every owning branch
+  float w[NB];        // merge weight softmax_b(lse_b) (0 where the branch does not own the position)
+  int slot[NB];       // compact head slot of the (position, head) in branch b
+  bool own[NB];
+};
+
+template <typename T, int NB>
 __device__ __forceinline__ void merge_row(const DilatedGeom& G, const T* __restrict__ o_br,
                                           const float* __restrict__ lse_br, int p, int lane, float (&acc)[24],
-                                          float* lse_out) {
+                                          float* lse_out, MergedRow<T, NB>& R) {
   const int h = lane >> 1, half = lane & 1;
-  float l[MT_MAX_BRANCHES];
-  int slot[MT_MAX_BRANCHES];
-  float mx = -INFINITY;
+  float l[NB];
 #pragma unroll
-  for (int b = 0; b < MT_MAX_BRANCHES; ++b) {
+  for (int b = 0; b < NB; ++b) {
     l[b] = -INFINITY;
-    slot[b] = 0;
+    R.own[b] = false;
+    R.slot[b] = 0;
     if (b < G.nb) {
       int sl;
-      if (branch_owns(G.b[b], G.H, p, h, &sl)) {
+      R.own[b] = branch_owns(G.b[b], G.H, p, h, &sl);
+      R.slot[b] = sl;
+      if (R.own[b]) {
         l[b] = lse_br[G.b[b].lse_off + (int64_t)p * G.b[b].hpb + sl];
-        slot[b] = sl;
+        R.o[b].load(o_br + G.b[b].o_off + ((int64_t)p * G.b[b].hpb + sl) * D + half * 24);
       }
-      mx = fmaxf(mx, l[b]);
     }
   }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) mx = fmaxf(mx, l[b]);
   float den = 0.f;
 #pragma unroll
-  for (int b = 0; b < MT_MAX_BRANCHES; ++b)
-    if (b < G.nb && l[b] != -INFINITY) den += expf(l[b] - mx);
+  for (int b = 0; b < NB; ++b) {
+    R.w[b] = R.own[b] ? expf(l[b] - mx) : 0.f;
+    den += R.w[b];
+  }
   const float inv = den > 0.f ? 1.f / den : 0.f;  // no owning branch (needs a config without r = 1): output 0
 #pragma unroll
   for (int j = 0; j < 24; ++j) acc[j] = 0.f;
 #pragma unroll
-  for (int b = 0; b < MT_MAX_BRANCHES; ++b) {
-    if (b < G.nb && l[b] != -INFINITY) {
-      const float w = expf(l[b] - mx) * inv;
-      const T* src = o_br + G.b[b].o_off + ((int64_t)p * G.b[b].hpb + slot[b]) * D + half * 24;
+  for (int b = 0; b < NB; ++b) {
+    R.w[b] *= inv;
+    if (R.own[b]) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float v[8];
-        load8(src + c * 8, v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[c * 8 + j] = fmaf(w, v[j], acc[c * 8 + j]);
-      }
+      for (int j = 0; j < 24; ++j) acc[j] = fmaf(R.w[b], R.o[b].get(j), acc[j]);
     }
   }
   *lse_out = mx + logf(den);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) merge_ln_fwd_kernel(const DilatedGeom G, const T* __restrict__ o_br,
+template <typename T, int NB>
+__global__ void __launch_bounds__(256, 2) merge_ln_fwd_kernel(const DilatedGeom G, const T* __restrict__ o_br,
                                                            const float* __restrict__ lse_br, T* __restrict__ attn,
                                                            float* __restrict__ lse, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float eps,
@@ -364,7 +396,8 @@ __global__ void __launch_bounds__(256) merge_ln_fwd_kernel(const DilatedGeom G, 
   const int E = G.H * D;
   for (int p = blockIdx.x * 8 + (threadIdx.x >> 5); p < G.N; p += gridDim.x * 8) {
     float acc[24], L;
-    merge_row(G, o_br, lse_br, p, lane, acc, &L);
+    MergedRow<T, NB> R;
+    merge_row<T, NB>(G, o_br, lse_br, p, lane, acc, &L, R);
     if ((lane & 1) == 0) lse[(int64_t)p * G.H + (lane >> 1)] = L;
     float s = 0.f;
 #pragma unroll
@@ -396,8 +429,8 @@ __global__ void __launch_bounds__(256) merge_ln_fwd_kernel(const DilatedGeom G, 
 }
 
 // dattn = LN'(dy) with attn recomputed from the branch outputs; delta_b[p, h] = dattn[p, h, :] . o_b[p, h, :]
-template <typename T, typename TDY>
-__global__ void __launch_bounds__(256) merge_ln_bwd_kernel(const DilatedGeom G, const TDY* __restrict__ dy,
+template <typename T, typename TDY, int NB>
+__global__ void __launch_bounds__(256, 2) merge_ln_bwd_kernel(const DilatedGeom G, const TDY* __restrict__ dy,
                                                            const T* __restrict__ o_br,
                                                            const float* __restrict__ lse_br,
                                                            const float* __restrict__ gamma,
@@ -406,22 +439,25 @@ __global__ void __launch_bounds__(256) merge_ln_bwd_kernel(const DilatedGeom G, 
                                                            float* __restrict__ delta_br) {
   const int lane = threadIdx.x & 31;
   const int E = G.H * D;
-  const int h = lane >> 1, half = lane & 1;
+  const int half = lane & 1;
   for (int p = blockIdx.x * 8 + (threadIdx.x >> 5); p < G.N; p += gridDim.x * 8) {
-    float acc[24], L;
-    merge_row(G, o_br, lse_br, p, lane, acc, &L);
+    // the row of dy and the statistics do not depend on the merge: request them first
+    float d[3][8];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) load8(dy + (int64_t)p * E + lane * 24 + c * 8, d[c]);
     const float mu = mean[p], rs = rstd[p];
+    float acc[24], L;
+    MergedRow<T, NB> R;
+    merge_row<T, NB>(G, o_br, lse_br, p, lane, acc, &L, R);
     float g[24], s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const int col = lane * 24 + c * 8;
-      float d[8], gm[8];
-      load8(dy + (int64_t)p * E + col, d);
-      load8(gamma + col, gm);
+      float gm[8];
+      load8(gamma + lane * 24 + c * 8, gm);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         acc[c * 8 + j] = (acc[c * 8 + j] - mu) * rs;  // xhat
-        g[c * 8 + j] = d[j] * gm[j];
+        g[c * 8 + j] = d[c][j] * gm[j];
         s1 += g[c * 8 + j];
         s2 += g[c * 8 + j] * acc[c * 8 + j];
       }
@@ -437,25 +473,19 @@ __global__ void __launch_bounds__(256) merge_ln_bwd_kernel(const DilatedGeom G, 
       }
       store8(dattn + (int64_t)p * E + lane * 24 + c * 8, o);
     }
-    // per-branch delta against the same (rounded) dattn the attention backward will read
+    // per-branch delta against the same (rounded) dattn the attention backward will read; o_b is still in registers
 #pragma unroll
-    for (int b = 0; b < MT_MAX_BRANCHES; ++b) {
+    for (int j = 0; j < 24; ++j) g[j] = to_float(from_float<T>(g[j]));
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
       if (b < G.nb) {
-        int sl;
-        const bool own = branch_owns(G.b[b], G.H, p, h, &sl);
         float dsum = 0.f;
-        if (own) {
-          const T* src = o_br + G.b[b].o_off + ((int64_t)p * G.b[b].hpb + sl) * D + half * 24;
+        if (R.own[b]) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float v[8];
-            load8(src + c * 8, v);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dsum = fmaf(to_float(from_float<T>(g[c * 8 + j])), v[j], dsum);
-          }
+          for (int j = 0; j < 24; ++j) dsum = fmaf(g[j], R.o[b].get(j), dsum);
         }
         dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
-        if (own && half == 0) delta_br[G.b[b].lse_off + (int64_t)p * G.b[b].hpb + sl] = dsum;
+        if (R.own[b] && half == 0) delta_br[G.b[b].lse_off + (int64_t)p * G.b[b].hpb + R.slot[b]] = dsum;
       }
     }
   }
@@ -561,13 +591,15 @@ extern "C" int mt_dilated_merge_ln_fwd(const mt_dilated_geometry* geom, const vo
   cudaStream_t st = (cudaStream_t)stream;
   int grid = (G.N + 7) / 8;
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-  if (dtype == MT_F32)
-    merge_ln_fwd_kernel<float><<<grid, 256, 0, st>>>(G, (const float*)o_br, lse_br, (float*)attn, lse, gamma, beta, eps,
-                                                     (float*)y, mean, rstd);
-  else
-    merge_ln_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(G, (const __nv_bfloat16*)o_br, lse_br,
-                                                             (__nv_bfloat16*)attn, lse, gamma, beta, eps,
-                                                             (__nv_bfloat16*)y, mean, rstd);
+  using bf = __nv_bfloat16;
+#define MT_MERGE_FWD(T, NB) \
+  merge_ln_fwd_kernel<T, NB><<<grid, 256, 0, st>>>(G, (const T*)o_br, lse_br, (T*)attn, lse, gamma, beta, eps, (T*)y, mean, rstd)
+  if (dtype == MT_F32) {
+    if (G.nb <= 5) MT_MERGE_FWD(float, 5); else MT_MERGE_FWD(float, MT_MAX_BRANCHES);
+  } else {
+    if (G.nb <= 5) MT_MERGE_FWD(bf, 5); else MT_MERGE_FWD(bf, MT_MAX_BRANCHES);
+  }
+#undef MT_MERGE_FWD
   return check_launch("merge_ln_fwd_kernel");
 }
 
@@ -582,18 +614,19 @@ extern "C" int mt_dilated_merge_ln_bwd(const mt_dilated_geometry* geom, const vo
   int grid = (G.N + 7) / 8;
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
   using bf = __nv_bfloat16;
-  if (dtype == MT_F32 && dy_dtype == MT_F32)
-    merge_ln_bwd_kernel<float, float><<<grid, 256, 0, st>>>(G, (const float*)dy, (const float*)o_br, lse_br, gamma, mean,
-                                                            rstd, (float*)dattn, delta_br);
-  else if (dtype == MT_BF16 && dy_dtype == MT_BF16)
-    merge_ln_bwd_kernel<bf, bf><<<grid, 256, 0, st>>>(G, (const bf*)dy, (const bf*)o_br, lse_br, gamma, mean, rstd,
-                                                      (bf*)dattn, delta_br);
-  else if (dtype == MT_BF16 && dy_dtype == MT_F32)
-    merge_ln_bwd_kernel<bf, float><<<grid, 256, 0, st>>>(G, (const float*)dy, (const bf*)o_br, lse_br, gamma, mean, rstd,
-                                                         (bf*)dattn, delta_br);
-  else {
+#define MT_MERGE_BWD(T, TDY, NB)                                                                                   \
+  merge_ln_bwd_kernel<T, TDY, NB><<<grid, 256, 0, st>>>(G, (const TDY*)dy, (const T*)o_br, lse_br, gamma, mean, rstd, \
+                                                        (T*)dattn, delta_br)
+  if (dtype == MT_F32 && dy_dtype == MT_F32) {
+    if (G.nb <= 5) MT_MERGE_BWD(float, float, 5); else MT_MERGE_BWD(float, float, MT_MAX_BRANCHES);
+  } else if (dtype == MT_BF16 && dy_dtype == MT_BF16) {
+    if (G.nb <= 5) MT_MERGE_BWD(bf, bf, 5); else MT_MERGE_BWD(bf, bf, MT_MAX_BRANCHES);
+  } else if (dtype == MT_BF16 && dy_dtype == MT_F32) {
+    if (G.nb <= 5) MT_MERGE_BWD(bf, float, 5); else MT_MERGE_BWD(bf, float, MT_MAX_BRANCHES);
+  } else {
     set_error("merge_ln_bwd: unsupported dtype combination (%d, dy %d)", dtype, dy_dtype);
     return MT_E_UNSUPPORTED;
   }
+#undef MT_MERGE_BWD
   return check_launch("merge_ln_bwd_kernel");
 }
