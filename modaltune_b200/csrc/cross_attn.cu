@@ -4,7 +4,8 @@
 //
 //   Injector  (Lq = tiles ~1e4, Lk = modal tokens ~66): one thread per query, K/V tiles broadcast from shared memory.
 //   Extractor (Lq ~66, Lk = tiles ~1e4): split-K over the keys (grid.z), partial (m, l, acc) per split, LSE combine.
-// Backward is two kernels, each accumulating in registers along its own loop and flushing with fp32 atomics:
+// Backward is two kernels, each accumulating in registers along its own loop (plain stores when the loop is not split,
+// 16-byte fp32 reduce-adds when it is):
 //   dq-kernel (thread per query, loop over keys) and dkv-kernel (thread per key, loop over queries).
 #include "mt_common.cuh"
 
@@ -190,8 +191,16 @@ __global__ void __launch_bounds__(XT) cross_bwd_dq_kernel(const T* __restrict__ 
     }
   }
   if (live) {
+    float* dst = dq + qi * ld + h * HD;
+    if (gridDim.z == 1) {   // the only contribution to this row: plain 16-byte stores, no zero fill needed
 #pragma unroll
-    for (int e = 0; e < HD; ++e) atomicAdd(dq + qi * ld + h * HD + e, acc[e]);
+      for (int e = 0; e < HD; e += 4)
+        *reinterpret_cast<float4*>(dst + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < HD; e += 4)
+        atomicAdd(reinterpret_cast<float4*>(dst + e), make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]));
+    }
   }
 }
 
@@ -258,10 +267,20 @@ __global__ void __launch_bounds__(XT) cross_bwd_dkv_kernel(const T* __restrict__
     }
   }
   if (live) {
+    float* dstk = dk + ki * ld + h * HD;
+    float* dstv = dv + ki * ld + h * HD;
+    if (gridDim.z == 1) {
 #pragma unroll
-    for (int e = 0; e < HD; ++e) {
-      atomicAdd(dk + ki * ld + h * HD + e, dka[e]);
-      atomicAdd(dv + ki * ld + h * HD + e, dva[e]);
+      for (int e = 0; e < HD; e += 4) {
+        *reinterpret_cast<float4*>(dstk + e) = make_float4(dka[e], dka[e + 1], dka[e + 2], dka[e + 3]);
+        *reinterpret_cast<float4*>(dstv + e) = make_float4(dva[e], dva[e + 1], dva[e + 2], dva[e + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < HD; e += 4) {
+        atomicAdd(reinterpret_cast<float4*>(dstk + e), make_float4(dka[e], dka[e + 1], dka[e + 2], dka[e + 3]));
+        atomicAdd(reinterpret_cast<float4*>(dstv + e), make_float4(dva[e], dva[e + 1], dva[e + 2], dva[e + 3]));
+      }
     }
   }
 }
@@ -322,10 +341,15 @@ extern "C" int mt_cross_attn_bwd(const void* q, const void* k, const void* v, co
   MT_REQUIRE(lq > 0 && lk > 0 && heads > 0 && heads <= 65535, "cross_attn: bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t ld = (size_t)heads * HD;
-  MT_CUDA(cudaMemsetAsync(dq_f32, 0, sizeof(float) * lq * ld, st));
-  MT_CUDA(cudaMemsetAsync(dk_f32, 0, sizeof(float) * lk * ld, st));
-  MT_CUDA(cudaMemsetAsync(dv_f32, 0, sizeof(float) * lk * ld, st));
   const int nsk = pick_splits(lq, lk, heads), nsq = pick_splits(lk, lq, heads);
+  MT_REQUIRE(((reinterpret_cast<uintptr_t>(dq_f32) | reinterpret_cast<uintptr_t>(dk_f32) |
+               reinterpret_cast<uintptr_t>(dv_f32)) & 15) == 0, "cross_attn_bwd: gradients must be 16-byte aligned");
+  // split loops accumulate with 16-byte reduce-adds into zero-filled gradients; an unsplit loop owns its rows and stores
+  if (nsk > 1) MT_CUDA(cudaMemsetAsync(dq_f32, 0, sizeof(float) * lq * ld, st));
+  if (nsq > 1) {
+    MT_CUDA(cudaMemsetAsync(dk_f32, 0, sizeof(float) * lk * ld, st));
+    MT_CUDA(cudaMemsetAsync(dv_f32, 0, sizeof(float) * lk * ld, st));
+  }
   const int64_t kps = ((lk + nsk - 1) / nsk + XC - 1) / XC * XC;
   const int64_t qps = ((lq + nsq - 1) / nsq + XC - 1) / XC * XC;
   dim3 gq((unsigned)((lq + XT - 1) / XT), (unsigned)heads, (unsigned)nsk);

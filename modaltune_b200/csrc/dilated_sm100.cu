@@ -41,6 +41,12 @@ using namespace sm100;
 #define MT_TRACE_DUMP(who)
 #endif
 
+#ifndef MT_FWD_POLY
+#define MT_FWD_POLY 0                     // exponentials per 8 computed on the FMA pipes in the forward (ex2_poly)
+#endif
+#ifndef MT_FWD_STAGGER
+#define MT_FWD_STAGGER 0                  // start delay (cycles) of the second forward CTA of each SM in the first wave
+#endif
 static constexpr int DH = 48;            // head dim
 static constexpr int BT = 128;           // slots per tile (queries and keys)
 static constexpr int TILE_BYTES = BT * 128;  // [128 rows][128 B]: 64 bf16 columns per row, SWIZZLE_128B
@@ -67,10 +73,12 @@ struct FwdSmem {
   static constexpr int K = Q + TILE_BYTES;
   static constexpr int V = K + KV_STAGES * TILE_BYTES;
   static constexpr int BAR = V + KV_STAGES * TILE_BYTES;
-  // barriers (8 B each): q_full, kv_full[2], kv_empty[2], s_full, s_free, p_full, o_full[2]; then the TMEM pointer
-  static constexpr int NBAR = 10;
+  // barriers (8 B each): q_full, kv_full[2], kv_empty[2], s_full, s_free, p_full, o_full[2], (forward v2: v_full[2],
+  // v_empty[2], the first two pairs then serve K alone); then the TMEM pointer
+  static constexpr int NBAR = 14;
   static constexpr int TMEM_PTR = BAR + NBAR * 8;
-  static constexpr int TOTAL = TMEM_PTR + 16;
+  static constexpr int XCH = TMEM_PTR + 16;          // forward with two threads per row: 3 x [2][128] floats
+  static constexpr int TOTAL = XCH + 3 * 2 * 128 * 4;
 };
 
 __global__ void __launch_bounds__(FWD_THREADS, 2)
@@ -317,16 +325,32 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
 
 // ---------------------------------------------------------------------------------------------------------------------
 // forward, second version: O accumulated in TMEM with a lazily raised row maximum (no per-tile fold / rescale in
-// registers), the whole 128-column score row loaded once, 3-input maxima
+// registers), the whole 128-column score row loaded once, 3-input maxima.
+// TPR = threads per query row: 1 (impl 2) or 2 (impl 3: eight softmax warps, warps w and w + 4 share the 32 TMEM lanes of
+// their rows and each own 64 of the 128 score columns and 24 of the 48 output columns; the row maximum is exchanged
+// through shared memory once per tile, the row sums once per CTA).  With four softmax warps the kernel is bound by the
+// latency of each warp's dependent instruction stream (issue slots 44 %, MUFU 63 % busy, and moving exponentials to the
+// FMA pipes did not help, MT_FWD_POLY); eight warps give every scheduler four streams to interleave.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FWD_THREADS, 2)
+// 64-thread named barrier of the two softmax warps that share TMEM lane group g (compile-time ids 1..4)
+__device__ __forceinline__ void pair_bar_sync(int g) {
+  switch (g) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
+
+template <int TPR>
+__global__ void __launch_bounds__(64 + 128 * TPR, 2)
 dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Params P, __nv_bfloat16* __restrict__ o_br,
                          float* __restrict__ lse_br, int* __restrict__ err_flag) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   // roles by warp id: the scheduler favours high warp ids, so the latency-critical single-thread roles sit last
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int W_TMA = 4, W_MMA = 5;
+  constexpr int W_TMA = 4 * TPR, W_MMA = 4 * TPR + 1;
   if ((sbase & 1023u) != 0) {  // SWIZZLE_128B tiles need 1024-byte alignment; never expected, but fail loudly
     if (threadIdx.x == 0) atomicExch(err_flag, 1);
     return;
@@ -356,8 +380,12 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
   const int n_zero_tail = max(0, bg.m - n_kv * BT);
 
   const uint32_t bar_q_full = sbase + FwdSmem::BAR + 0;
-  const uint32_t bar_kv_full = sbase + FwdSmem::BAR + 8;    // [2]
-  const uint32_t bar_kv_empty = sbase + FwdSmem::BAR + 24;  // [2]
+  // K and V have their own 2-stage rings: a K stage is free as soon as its Q K^T has completed, a full tile time before
+  // the P V that frees the V stage, so the load of K_{j+1} (which gates S_{j+1}) starts a tile earlier
+  const uint32_t bar_k_full = sbase + FwdSmem::BAR + 8;     // [2]
+  const uint32_t bar_k_empty = sbase + FwdSmem::BAR + 24;   // [2]
+  const uint32_t bar_v_full = sbase + FwdSmem::BAR + 80;    // [2]
+  const uint32_t bar_v_empty = sbase + FwdSmem::BAR + 96;   // [2]
   const uint32_t bar_s_full = sbase + FwdSmem::BAR + 40;
   const uint32_t bar_s_free = sbase + FwdSmem::BAR + 48;
   const uint32_t bar_p_full = sbase + FwdSmem::BAR + 56;
@@ -367,13 +395,15 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
   if (threadIdx.x == 0) {
     mbar_init(bar_q_full, 1);
     for (int i = 0; i < KV_STAGES; ++i) {
-      mbar_init(bar_kv_full + 8 * i, 1);
-      mbar_init(bar_kv_empty + 8 * i, 1);
+      mbar_init(bar_k_full + 8 * i, 1);
+      mbar_init(bar_k_empty + 8 * i, 1);
+      mbar_init(bar_v_full + 8 * i, 1);
+      mbar_init(bar_v_empty + 8 * i, 1);
       mbar_init(bar_o_full + 8 * i, 1);
     }
     mbar_init(bar_s_full, 1);
-    mbar_init(bar_s_free, 128);
-    mbar_init(bar_p_full, 128);
+    mbar_init(bar_s_free, 128 * TPR);
+    mbar_init(bar_p_full, 128 * TPR);
     fence_barrier_init();
     tma_prefetch_desc(&maps.m[b]);
   }
@@ -397,10 +427,12 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
       tma_load_3d(sbase + FwdSmem::Q, map, bar_q_full, h * DH, off, jseg + q0);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1, use = j >> 1;
-        mbar_wait(bar_kv_empty + 8 * st, (use & 1) ^ 1);
-        mbar_expect_tx(bar_kv_full + 8 * st, 2 * TILE_BYTES);
-        tma_load_3d(sbase + FwdSmem::K + st * TILE_BYTES, map, bar_kv_full + 8 * st, E + h * DH, off, jseg + j * BT);
-        tma_load_3d(sbase + FwdSmem::V + st * TILE_BYTES, map, bar_kv_full + 8 * st, 2 * E + h * DH, off, jseg + j * BT);
+        mbar_wait(bar_k_empty + 8 * st, (use & 1) ^ 1);
+        mbar_expect_tx(bar_k_full + 8 * st, TILE_BYTES);
+        tma_load_3d(sbase + FwdSmem::K + st * TILE_BYTES, map, bar_k_full + 8 * st, E + h * DH, off, jseg + j * BT);
+        mbar_wait(bar_v_empty + 8 * st, (use & 1) ^ 1);
+        mbar_expect_tx(bar_v_full + 8 * st, TILE_BYTES);
+        tma_load_3d(sbase + FwdSmem::V + st * TILE_BYTES, map, bar_v_full + 8 * st, 2 * E + h * DH, off, jseg + j * BT);
       }
     }
   } else if (warp == W_MMA) {
@@ -419,26 +451,28 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
           umma_ss(tmem_s, umma_desc_adv(q_desc, k * 32), umma_desc_adv(kd, k * 32), IDESC_QK, k > 0);
+        umma_commit(bar_k_empty + 8 * (j & 1));
         umma_commit(bar_s_full);
       }
       __syncwarp();
     };
     MT_TRACE_DECL
     mbar_wait(bar_q_full, 0);
-    mbar_wait(bar_kv_full, 0);
+    mbar_wait(bar_k_full, 0);
     tc_fence_after();
     MT_TRACE(0);
     issue_qk(0);
     for (int j = 0; j < n_kv; ++j) {
       if (j + 1 < n_kv) {
-        mbar_wait(bar_kv_full + 8 * ((j + 1) & 1), ((j + 1) >> 1) & 1);
+        mbar_wait(bar_k_full + 8 * ((j + 1) & 1), ((j + 1) >> 1) & 1);
         MT_TRACE(100 + j);
         mbar_wait(bar_s_free, j & 1);  // the softmax threads have read S_j out of TMEM
         tc_fence_after();
         MT_TRACE(200 + j);
         issue_qk(j + 1);
       }
-      mbar_wait(bar_p_full, j & 1);    // P_j is in TMEM (and the O tile of P_{j-1} V_{j-1} has been folded)
+      mbar_wait(bar_p_full, j & 1);    // P_j is in TMEM
+      mbar_wait(bar_v_full + 8 * (j & 1), (j >> 1) & 1);
       tc_fence_after();
       MT_TRACE(300 + j);
       if (elect_one()) {
@@ -448,7 +482,7 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k)
           umma_ts(tmem_o, tmem_p + k * 8, umma_desc_adv(vd, k * 2048), IDESC_PV, (j > 0) || (k > 0));
-        umma_commit(bar_kv_empty + 8 * (j & 1));
+        umma_commit(bar_v_empty + 8 * (j & 1));
         umma_commit(bar_o_full);
       }
       __syncwarp();
@@ -460,11 +494,26 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
     // log2 domain (P <= 2^8 stays exact enough in bf16, l is fp32): the O accumulator then never needs the per-tile
     // rescale, and in the rare tile where a row does move, its warp rescales its 32 rows of O in TMEM in place.
     const int lane_grp = warp & 3;                    // TMEM lanes this warp may touch: [32*lane_grp, +32)
+    const int half = (TPR == 2) ? (warp >> 2) : 0;    // which half of the score / output columns this thread owns
+    constexpr int NC = BT / TPR;                      // score columns per thread
+    constexpr int OC = DH / TPR;                      // output columns per thread
+    float* xch = reinterpret_cast<float*>(smem + FwdSmem::XCH);   // [3][2 halves][128 rows]: maxima (x2), row sums
     const int row = lane_grp * 32 + lane;
     const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
     float m_used = -INFINITY, l_run = 0.f;
     const float scale_log2 = P.scale_log2;
     MT_TRACE_DECL
+#if MT_FWD_STAGGER > 0
+    // The two CTAs of an SM alternate between an exponential phase (MUFU-bound, ~1 100 cycles per tile when a CTA has
+    // the unit to itself) and a phase without exponentials (score load, maximum, barriers).  CTAs that start together
+    // stay in phase -- both in their exponentials at half rate, then both off the MUFU unit -- and the offset between
+    // two equally long CTAs never changes.  Delaying the second CTA of every SM in the first wave by about half a tile
+    // period puts the pairs in anti-phase; their successors inherit the offset.
+    if (blockIdx.x >= kNumSMs && blockIdx.x < 2 * kNumSMs) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < MT_FWD_STAGGER) {}
+    }
+#endif
     auto tile = [&](int j, auto mask_tag) {
       constexpr bool MASK = decltype(mask_tag)::value;
       const int kvalid = bg.m - j * BT;  // key slots of this tile that belong to the segment (>= 1)
@@ -472,20 +521,46 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
       mbar_wait(bar_s_full, j & 1);
       tc_fence_after();
       MT_TRACE(1100 + j);
-      float sv[128];
-      tmem_ld64(tmem_s + t_lane, sv);
-      tmem_ld64(tmem_s + t_lane + 64, sv + 64);
+      // The row maximum is four independent 3-input chains (a single chain of 64 dependent FMNMX3 cost ~300 cycles in
+      // which this warp kept neither the MUFU nor the FMA pipe busy); with one thread per row the maximum of the first
+      // 64 columns is taken while the load of the second 64 is still in flight.
+      float sv[NC];
+      float m4[4];
+      auto max_block = [&](int c0) {    // 64 columns starting at c0: 4 chains x 16 values
+        if (MASK) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) sv[c0 + i] = (half * NC + c0 + i < kvalid) ? sv[c0 + i] : -INFINITY;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float m = fmax3(sv[c0 + 16 * q], sv[c0 + 16 * q + 1], sv[c0 + 16 * q + 2]);
+#pragma unroll
+          for (int i = 3; i + 1 < 16; i += 2) m = fmax3(m, sv[c0 + 16 * q + i], sv[c0 + 16 * q + i + 1]);
+          m = fmaxf(m, sv[c0 + 16 * q + 15]);
+          m4[q] = (c0 == 0) ? m : fmaxf(m4[q], m);
+        }
+      };
+      tmem_ld64(tmem_s + t_lane + half * NC, sv);
       tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(bar_s_free);          // S_j is in registers: the MMA warp may overwrite it with S_{j+1}
-      if (MASK) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i) sv[i] = (i < kvalid) ? sv[i] : -INFINITY;
+      if (TPR == 1) {
+        tmem_ld64(tmem_s + t_lane + 64, sv + (TPR == 1 ? 64 : 0));
+        max_block(0);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(bar_s_free);        // S_j is in registers: the MMA warp may overwrite it with S_{j+1}
+        max_block(TPR == 1 ? 64 : 0);
+      } else {
+        tc_fence_before();
+        mbar_arrive(bar_s_free);
+        max_block(0);
       }
-      float mx = fmax3(sv[0], sv[1], sv[2]);
-#pragma unroll
-      for (int i = 3; i + 1 < 128; i += 2) mx = fmax3(mx, sv[i], sv[i + 1]);
-      mx = fmaxf(mx, sv[127]);
+      float mx = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
+      if (TPR == 2) {   // the two threads of a row agree on its maximum (double-buffered slot, 64-thread named barrier)
+        float* x = xch + (j & 1) * 256;
+        x[half * 128 + row] = mx;
+        pair_bar_sync(lane_grp);
+        mx = fmaxf(mx, x[(half ^ 1) * 128 + row]);
+      }
       MT_TRACE(1200 + j);
       bool waited = false;
       if (j == 0) {
@@ -497,15 +572,15 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
           tc_fence_after();
           waited = true;
           const float alpha = need ? ex2((m_used - mx) * scale_log2) : 1.f;
-          float t[16];
+          float t[8];
 #pragma unroll
-          for (int c = 0; c < DH / 16; ++c) {
-            tmem_ld16(tmem_o + t_lane + c * 16, t);
+          for (int c = 0; c < OC / 8; ++c) {
+            tmem_ld8(tmem_o + t_lane + half * OC + c * 8, t);
             tmem_ld_wait();
-            uint32_t u[16];
+            uint32_t u[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) u[i] = __float_as_uint(t[i] * alpha);
-            tmem_st16(tmem_o + t_lane + c * 16, u);
+            for (int i = 0; i < 8; ++i) u[i] = __float_as_uint(t[i] * alpha);
+            tmem_st8(tmem_o + t_lane + half * OC + c * 8, u);
           }
           if (need) {
             l_run *= alpha;
@@ -514,23 +589,27 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
         }
       }
       const float mb = m_used * scale_log2;
-      if (j > 0 && !waited) {             // P_j overwrites P_{j-1}: its P V must have read it
-        mbar_wait(bar_o_full, (j - 1) & 1);
-        tc_fence_after();
-      }
       MT_TRACE(1300 + j);
       float rs = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NC / 32; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2(fmaf(sv[c * 32 + i], scale_log2, -mb));       // masked slots: ex2(-inf) = 0
-          const float p1 = ex2(fmaf(sv[c * 32 + i + 1], scale_log2, -mb));
+          // MT_FWD_POLY of every 8 exponentials run as an FMA-pipe polynomial (full tiles only: masked slots need
+          // ex2(-inf) = 0 exactly)
+          const float x0 = fmaf(sv[c * 32 + i], scale_log2, -mb);
+          const float x1 = fmaf(sv[c * 32 + i + 1], scale_log2, -mb);
+          const float p0 = (!MASK && (i & 7) < MT_FWD_POLY) ? ex2_poly(x0) : ex2(x0);
+          const float p1 = (!MASK && ((i + 1) & 7) < MT_FWD_POLY) ? ex2_poly(x1) : ex2(x1);
           rs += p0 + p1;
           pk[i >> 1] = pack_bf16(p0, p1);
         }
-        tmem_st16(tmem_p + t_lane + c * 16, pk);  // 32 keys = 16 packed columns
+        if (c == 0 && j > 0 && !waited) {   // P_j overwrites P_{j-1}: its P V must have read it.  Waiting only here,
+          mbar_wait(bar_o_full, (j - 1) & 1);  // with the first 32 exponentials already computed, hides the wait
+          tc_fence_after();
+        }
+        tmem_st16(tmem_p + t_lane + half * (NC / 2) + c * 16, pk);  // 32 keys = 16 packed columns
       }
       l_run += rs;
       tmem_st_wait();
@@ -549,29 +628,35 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
     const int slot = q0 + row;
     const int pos = s * bg.g + off + slot * bg.r;
     const int seg_end = min(N, (s + 1) * bg.g);
-    float o_acc[DH];
+    float o_acc[OC];
 #pragma unroll
-    for (int c = 0; c < DH / 16; ++c) {
-      float t[16];
-      tmem_ld16(tmem_o + t_lane + c * 16, t);
+    for (int c = 0; c < OC / 8; ++c) {
+      float t[8];
+      tmem_ld8(tmem_o + t_lane + half * OC + c * 8, t);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] = t[i];
+      for (int i = 0; i < 8; ++i) o_acc[c * 8 + i] = t[i];
+    }
+    if (TPR == 2) {   // row sum = sum of the two column halves
+      float* x = xch + 512;
+      x[half * 128 + row] = l_run;
+      pair_bar_sync(lane_grp);
+      l_run += x[(half ^ 1) * 128 + row];
     }
     if (n_zero_tail > 0) {   // the zero keys of the tiles that were skipped
       const float m_fin = fmaxf(m_used, 0.f);
       const float alpha = ex2((m_used - m_fin) * scale_log2);
       l_run = l_run * alpha + (float)n_zero_tail * ex2(-m_fin * scale_log2);
 #pragma unroll
-      for (int i = 0; i < DH; ++i) o_acc[i] *= alpha;
+      for (int i = 0; i < OC; ++i) o_acc[i] *= alpha;
       m_used = m_fin;
     }
     if (slot < bg.m && pos < seg_end) {
       const float inv = 1.f / l_run;
       const int slot_h = h - off * bg.hpb;
-      __nv_bfloat16* dst = o_br + bg.o_off + ((int64_t)pos * bg.hpb + slot_h) * DH;
+      __nv_bfloat16* dst = o_br + bg.o_off + ((int64_t)pos * bg.hpb + slot_h) * DH + half * OC;
 #pragma unroll
-      for (int c = 0; c < DH / 8; ++c) {
+      for (int c = 0; c < OC / 8; ++c) {
         uint4 u;
         u.x = pack_bf16(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
         u.y = pack_bf16(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
@@ -579,7 +664,7 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
         u.w = pack_bf16(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
         *reinterpret_cast<uint4*>(dst + c * 8) = u;
       }
-      lse_br[bg.lse_off + (int64_t)pos * bg.hpb + slot_h] = m_used * P.scale + logf(l_run);
+      if (half == 0) lse_br[bg.lse_off + (int64_t)pos * bg.hpb + slot_h] = m_used * P.scale + logf(l_run);
     }
   }
   // ---- teardown ------------------------------------------------------------------------------------------------------
@@ -711,10 +796,16 @@ int dilated_attn_fwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int
   int* flag = error_flag();
   MT_REQUIRE(flag != nullptr, "dilated_attn_fwd: cannot allocate the error flag");
   if (impl == 2) {
-    MT_CUDA(cudaFuncSetAttribute(dilated_fwd2_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
-    dilated_fwd2_sm100_kernel<<<P.item_prefix[P.geo.nb], FWD_THREADS, FwdSmem::TOTAL, st>>>(
+    MT_CUDA(cudaFuncSetAttribute(dilated_fwd2_sm100_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
+    dilated_fwd2_sm100_kernel<1><<<P.item_prefix[P.geo.nb], FWD_THREADS, FwdSmem::TOTAL, st>>>(
         maps, P, (__nv_bfloat16*)o_br, lse_br, flag);
-    return check_launch("dilated_fwd2_sm100_kernel");
+    return check_launch("dilated_fwd2_sm100_kernel<1>");
+  }
+  if (impl == 3) {
+    MT_CUDA(cudaFuncSetAttribute(dilated_fwd2_sm100_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
+    dilated_fwd2_sm100_kernel<2><<<P.item_prefix[P.geo.nb], 64 + 256, FwdSmem::TOTAL, st>>>(
+        maps, P, (__nv_bfloat16*)o_br, lse_br, flag);
+    return check_launch("dilated_fwd2_sm100_kernel<2>");
   }
   MT_CUDA(cudaFuncSetAttribute(dilated_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
   dilated_fwd_sm100_kernel<<<P.item_prefix[P.geo.nb], FWD_THREADS, FwdSmem::TOTAL, st>>>(

@@ -415,21 +415,26 @@ __global__ void __launch_bounds__(RowCfg<COLS>::THREADS, RowCfg<COLS>::MINB) add
 }
 
 // backward of y = a + gate * (a + b):  da = dy * (1 + gate), db = dy * gate, dgate[c] += sum_r dy * (a + b)
+// The column sums are reduced over the rows of a block in shared memory and flushed with one 16-byte reduce-add pair
+// per column chunk and block: a few hundred blocks adding 8 scalars per thread into the same 24 cache lines spent
+// most of the kernel serialised in the L2 atomic units.
 template <typename TB>
-__global__ void __launch_bounds__(256) gated_residual_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a,
+__global__ void __launch_bounds__(768) gated_residual_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a,
                                                                  const TB* __restrict__ b,
                                                                  const float* __restrict__ gate, float* __restrict__ da,
                                                                  TB* __restrict__ db, float* __restrict__ dgate,
                                                                  int64_t rows, int cols) {
-  // thread t owns column chunk (t % chunks) for rows (blockIdx.x * rpb + t / chunks) + k * gridDim.x * rpb
+  // thread t owns column chunk (t % chunks) for rows (blockIdx.x * rpb + t / chunks) + k * gridDim.x * rpb;
+  // blockDim.x == chunks * rpb
+  extern __shared__ float gr_red[];
   const int chunks = cols / 8;
   const int rpb = blockDim.x / chunks;
   const int ch = threadIdx.x % chunks, rib = threadIdx.x / chunks;
-  if (rib >= rpb) return;
   float gv[8], acc[8];
   load8(gate + ch * 8, gv);
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll 2
   for (int64_t row = (int64_t)blockIdx.x * rpb + rib; row < rows; row += (int64_t)gridDim.x * rpb) {
     const int64_t off = row * cols + ch * 8;
     float d[8], av[8], bv[8], oa[8], ob[8];
@@ -445,8 +450,20 @@ __global__ void __launch_bounds__(256) gated_residual_bwd_kernel(const float* __
     store8(da + off, oa);
     store8(db + off, ob);
   }
+  if (rib > 0) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(dgate + ch * 8 + j, acc[j]);
+    for (int j = 0; j < 8; ++j) gr_red[((rib - 1) * chunks + ch) * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  if (rib == 0) {
+    for (int r = 0; r + 1 < rpb; ++r) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += gr_red[(r * chunks + ch) * 8 + j];
+    }
+    float4* dst = reinterpret_cast<float4*>(dgate + ch * 8);
+    atomicAdd(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    atomicAdd(dst + 1, make_float4(acc[4], acc[5], acc[6], acc[7]));
+  }
 }
 
 // y = x + a + bias[c]: the residual add after fc2 (encoder.py:169-175) with the GEMM's bias folded in
@@ -706,13 +723,17 @@ extern "C" int mt_gated_residual_bwd(const float* dy, const float* a, const void
   cudaStream_t st = (cudaStream_t)stream;
   MT_CUDA(cudaMemsetAsync(dgate, 0, sizeof(float) * (size_t)cols, st));
   if (rows == 0) return 0;
-  const int rpb = 256 / (int)(cols / 8);
+  const int chunks = (int)(cols / 8);
+  const int rpb = 768 / chunks;                  // >= 3 (chunks <= 256)
+  const int threads = chunks * rpb;
   int grid = grid_for(rows, rpb);
-  if (grid > kNumSMs * 4) grid = kNumSMs * 4;  // bound the number of atomic flushes
+  if (grid > kNumSMs) grid = kNumSMs;            // one 768-thread block per SM; bounds the number of reduce-add flushes
+  const size_t smem = sizeof(float) * 8 * (size_t)chunks * (rpb - 1);
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(dgate) & 15) == 0, "gated_residual_bwd: dgate must be 16-byte aligned");
   if (b_dtype == MT_F32)
-    gated_residual_bwd_kernel<float><<<grid, 256, 0, st>>>(dy, a, (const float*)b, gate, da, (float*)db, dgate, rows, (int)cols);
+    gated_residual_bwd_kernel<float><<<grid, threads, smem, st>>>(dy, a, (const float*)b, gate, da, (float*)db, dgate, rows, (int)cols);
   else
-    gated_residual_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dy, a, (const __nv_bfloat16*)b, gate, da, (__nv_bfloat16*)db, dgate, rows, (int)cols);
+    gated_residual_bwd_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(dy, a, (const __nv_bfloat16*)b, gate, da, (__nv_bfloat16*)db, dgate, rows, (int)cols);
   return check_launch("gated_residual_bwd_kernel");
 }
 

@@ -153,6 +153,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
@@ -225,6 +232,18 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], relative error 7.5e-5,
+// below the bf16 rounding of the probabilities it feeds): takes part of the exponentials off the 16 / clk MUFU unit,
+// which bounds the forward kernel at head_dim 48.  x is clamped to >= -125 (result >= 2^-125, never a denormal).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;             // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);       // fraction in [-0.5, 0.5]
+  float p = fmaf(f, 0x1.c3f76p-5f, 0x1.f0de1ap-3f);
+  p = fmaf(p, f, 0x1.62f31ap-1f);
+  p = fmaf(p, f, 0x1.fff692p-1f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));   // p * 2^n through the exponent field
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

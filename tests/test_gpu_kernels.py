@@ -211,7 +211,8 @@ def test_dilated_attention_tcgen05_forward(N, sl):
     g = torch.Generator().manual_seed(N + 1)
     qkv = _qkv(N, geom.n_alloc, g, torch.bfloat16, 1.5).to(DEV)
     o_s, l_s = ops.dilated_attn_fwd(geom, qkv, 0)
-    for impl in (1, 2):   # 1: O folded in registers every tile, 2: O accumulated in TMEM with a lazily raised maximum
+    # 1: O folded in registers every tile, 2: O accumulated in TMEM with a lazily raised maximum, 3: 2 with two threads per row
+    for impl in (1, 2, 3):
         o_t, l_t = ops.dilated_attn_fwd(geom, qkv, impl)
         torch.cuda.synchronize()
         assert rel(l_t, l_s) < 2e-3, (impl, rel(l_t, l_s))       # P is rounded to bf16 before P V; lse itself is fp32
@@ -236,7 +237,7 @@ def test_dilated_attention_tcgen05_forward_rising_maximum(N):
     qkv[:N, 768:1536] *= sign                                         # and alternating, so maxima move both ways
     qkv = qkv.to(torch.bfloat16).to(DEV)
     o_s, l_s = ops.dilated_attn_fwd(geom, qkv, 0)
-    for impl in (1, 2):
+    for impl in (1, 2, 3):
         o_t, l_t = ops.dilated_attn_fwd(geom, qkv, impl)
         torch.cuda.synchronize()
         assert torch.isfinite(o_t.float()).all() and torch.isfinite(l_t).all(), impl

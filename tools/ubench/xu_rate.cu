@@ -1,0 +1,84 @@
+// Microbenchmark (B200): per-SM throughput of the softmax inner-loop instructions of the forward attention kernel and
+// whether they share an execution pipe:
+//   0: ex2.approx.ftz.f32 alone (MUFU.EX2)          1: cvt.rn.bf16x2.f32 alone (F2FP.BF16.F32.PACK_AB)
+//   2: the kernel's mix, 2 ex2 + 1 pack             3: 2 ex2 + integer rounding pack (IADD x2 + PRMT)
+//   4: mix 2 plus the FFMA / FADD of the real loop
+// 8 warps per SM (2 per scheduler, like two co-resident forward CTAs); prints operations per clock and SM.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+__device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t pack(float a, float b) {
+  uint32_t r; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r;
+}
+__device__ __forceinline__ uint32_t pack_int(float a, float b) {
+  const uint32_t ua = __float_as_uint(a) + 0x8000u, ub = __float_as_uint(b) + 0x8000u;
+  return __byte_perm(ua, ub, 0x7632);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k(int iters, float seed, float scale, long long* cyc, uint32_t* sink) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = seed + 0.001f * (threadIdx.x + i);
+  uint32_t acc = 0;
+  float rs = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      if (MODE == 0) {
+        v[i] = ex2(v[i]); v[i + 1] = ex2(v[i + 1]);
+      } else if (MODE == 1) {
+        acc ^= pack(v[i], v[i + 1]); v[i] += 1.f;   // the FADD keeps the pack from being hoisted
+      } else if (MODE == 2) {
+        const float a = ex2(v[i]), b = ex2(v[i + 1]);
+        acc ^= pack(a, b); v[i] = a; v[i + 1] = b;
+      } else if (MODE == 3) {
+        const float a = ex2(v[i]), b = ex2(v[i + 1]);
+        acc ^= pack_int(a, b); v[i] = a; v[i + 1] = b;
+      } else {
+        const float a = ex2(fmaf(v[i], scale, -seed)), b = ex2(fmaf(v[i + 1], scale, -seed));
+        rs += a + b;
+        acc ^= pack(a, b); v[i] = a; v[i + 1] = b;
+      }
+    }
+  }
+  const long long t1 = clock64();
+  __syncthreads();
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+  float s = rs;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+  if (s == 12345.678f) sink[0] = acc;
+  if (acc == 0xdeadbeefu) sink[1] = 1;
+}
+
+int main() {
+  long long* cyc; uint32_t* sink;
+  cudaMalloc(&cyc, 148 * 8); cudaMalloc(&sink, 8);
+  const int iters = 4096;
+  const char* names[] = {"ex2 only", "F2FP pack only (+1 FADD)", "2 ex2 + F2FP", "2 ex2 + int pack", "2 FFMA + 2 ex2 + 2 FADD + F2FP"};
+  for (int mode = 0; mode < 5; ++mode) {
+    for (int rep = 0; rep < 2; ++rep) {
+      switch (mode) {
+        case 0: k<0><<<148, 256>>>(iters, -0.5f, 1.f, cyc, sink); break;
+        case 1: k<1><<<148, 256>>>(iters, -0.5f, 1.f, cyc, sink); break;
+        case 2: k<2><<<148, 256>>>(iters, -0.5f, 1.f, cyc, sink); break;
+        case 3: k<3><<<148, 256>>>(iters, -0.5f, 1.f, cyc, sink); break;
+        default: k<4><<<148, 256>>>(iters, -0.5f, 1.f, cyc, sink); break;
+      }
+      cudaDeviceSynchronize();
+    }
+    long long h[148]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double c = 0; for (int i = 0; i < 148; ++i) c += h[i]; c /= 148;
+    const double elems = (double)iters * 16 * 256;   // elements (= exponentials where present) per SM
+    printf("mode %d %-34s %9.0f cycles  %.2f elements/clk/SM  (%.2f cycles per 128x128 tile)\n", mode, names[mode], c, elems / c,
+           16384.0 * c / elems);
+  }
+  printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
