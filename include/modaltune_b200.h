@@ -110,7 +110,8 @@ int mt_gelu_ln_bwd(const void* dy, int dy_dtype, const void* h, int h_dtype, con
  *        16/r_b heads that own position p (heads (p%r)*16/r ..), each head_dim wide.           (dtype)
  * lse_br: same compaction, [N][H/r_b] float, natural-log LSE including the zero-slot keys.
  * impl: 0 = SIMT fp32 math (any dtype), >= 1 = tcgen05/TMA (bf16 only).  Forward: 1 = O folded in registers per key
- * tile, 2 = O accumulated in TMEM with a lazily raised row maximum (fastest).  Backward: 1 = operands through shared
+ * tile, 2 = O accumulated in TMEM with a lazily raised row maximum (fastest), 3 = 2 with two threads per query row
+ * (eight softmax warps per CTA).  Backward: 1 = operands through shared
  * memory, 2 = transposed formulation with its A operands in TMEM, 3 = 2 with the row statistics folded into the MMAs
  * and TMA reduce-adds for the gradients (fastest). */
 int mt_dilated_attn_fwd(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc, int dtype,

@@ -57,7 +57,7 @@ AUTO_IMPL = {"fwd": 2, "bwd": 3}
 
 def attn_impl(direction: str = "fwd") -> int:
     """The ``impl`` argument of mt_dilated_attn_{fwd,bwd}: 0 = SIMT, 1 = first tcgen05 version; forward 2 = O accumulated
-    in TMEM with a lazily raised row maximum (default); backward 2 = transposed formulation with its A operands in TMEM,
+    in TMEM with a lazily raised row maximum (default), 3 = the same with two threads per query row; backward 2 = transposed formulation with its A operands in TMEM,
     3 = the same with the per-query statistics folded into the MMAs and TMA reduce-adds for dQ / dK / dV (default)."""
     impl = _state["attn_impl"]
     if impl == "simt" or _state["mode"] == "fp32":

@@ -15,6 +15,59 @@ static constexpr int HD = 16;
 static constexpr int XT = 128;  // threads per CTA = rows (queries or keys) per CTA
 static constexpr int XC = 64;   // staged rows per chunk
 
+// Two fp32 FMAs in one instruction (FFMA2, new with sm_100): the kernels below are bound by instruction issue (one
+// shared-memory operand per four FMAs plus the exponentials), so halving the FMA instruction count is a direct win.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t ra = *reinterpret_cast<uint64_t*>(&a), rb = *reinterpret_cast<uint64_t*>(&b);
+  uint64_t rc = *reinterpret_cast<uint64_t*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+// dot product of a register row (8 float2) with a 16-float shared-memory row, two accumulator chains
+__device__ __forceinline__ float dot16(const float2 (&a)[HD / 2], const float* __restrict__ row) {
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+  float2 d0 = make_float2(0.f, 0.f), d1 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < HD / 4; ++c) {
+    const float4 k = r4[c];
+    d0 = ffma2(a[2 * c], make_float2(k.x, k.y), d0);
+    d1 = ffma2(a[2 * c + 1], make_float2(k.z, k.w), d1);
+  }
+  return (d0.x + d1.x) + (d0.y + d1.y);
+}
+// register-register dot product in EXACTLY the order of dot16: delta = dO.o must equal dO.v bit for bit when a query
+// has a single key (p = 1, o = v), so that dS is exactly zero there
+__device__ __forceinline__ float dot16v(const float (&a)[HD], const float (&b)[HD]) {
+  float2 d0 = make_float2(0.f, 0.f), d1 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < HD / 4; ++c) {
+    d0 = ffma2(make_float2(a[4 * c], a[4 * c + 1]), make_float2(b[4 * c], b[4 * c + 1]), d0);
+    d1 = ffma2(make_float2(a[4 * c + 2], a[4 * c + 3]), make_float2(b[4 * c + 2], b[4 * c + 3]), d1);
+  }
+  return (d0.x + d1.x) + (d0.y + d1.y);
+}
+// acc += w * row
+__device__ __forceinline__ void axpy16(float2 (&acc)[HD / 2], float w, const float* __restrict__ row) {
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+  const float2 w2 = make_float2(w, w);
+#pragma unroll
+  for (int c = 0; c < HD / 4; ++c) {
+    const float4 k = r4[c];
+    acc[2 * c] = ffma2(w2, make_float2(k.x, k.y), acc[2 * c]);
+    acc[2 * c + 1] = ffma2(w2, make_float2(k.z, k.w), acc[2 * c + 1]);
+  }
+}
+// acc += w * r (register row)
+__device__ __forceinline__ void axpy16r(float2 (&acc)[HD / 2], float w, const float2 (&r)[HD / 2]) {
+  const float2 w2 = make_float2(w, w);
+#pragma unroll
+  for (int c = 0; c < HD / 2; ++c) acc[c] = ffma2(w2, r[c], acc[c]);
+}
+__device__ __forceinline__ void to_pairs(const float (&v)[HD], float scale, float2 (&o)[HD / 2]) {
+#pragma unroll
+  for (int c = 0; c < HD / 2; ++c) o[c] = make_float2(v[2 * c] * scale, v[2 * c + 1] * scale);
+}
+
 template <typename T>
 __device__ __forceinline__ void load16(const T* p, float (&v)[HD]) {
   float a[8], b[8];
@@ -59,11 +112,11 @@ __global__ void __launch_bounds__(XT) cross_fwd_kernel(const T* __restrict__ q, 
   else
 #pragma unroll
     for (int j = 0; j < HD; ++j) qv[j] = 0.f;
+  float2 q2[HD / 2], acc2[HD / 2];
+  to_pairs(qv, 0.25f, q2);  // 1/sqrt(16)
+  float m = -INFINITY, l = 0.f;
 #pragma unroll
-  for (int j = 0; j < HD; ++j) qv[j] *= 0.25f;  // 1/sqrt(16)
-  float m = -INFINITY, l = 0.f, acc[HD];
-#pragma unroll
-  for (int j = 0; j < HD; ++j) acc[j] = 0.f;
+  for (int j = 0; j < HD / 2; ++j) acc2[j] = make_float2(0.f, 0.f);
   const int64_t kbeg = split * keys_per_split, kend = min(lk, kbeg + keys_per_split);
   for (int64_t k0 = kbeg; k0 < kend; k0 += XC) {
     __syncthreads();
@@ -75,27 +128,30 @@ __global__ void __launch_bounds__(XT) cross_fwd_kernel(const T* __restrict__ q, 
       float s[8], mx = m;
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
-        float d = 0.f;
-#pragma unroll
-        for (int e = 0; e < HD; ++e) d = fmaf(qv[e], Ks[(j0 + jj) * HD + e], d);
+        const float d = dot16(q2, Ks + (j0 + jj) * HD);
         s[jj] = (j0 + jj < cnt) ? d : -INFINITY;
         mx = fmaxf(mx, s[jj]);
       }
       const float alpha = expf(m - mx);
       l *= alpha;
 #pragma unroll
-      for (int e = 0; e < HD; ++e) acc[e] *= alpha;
+      for (int e = 0; e < HD / 2; ++e) acc2[e] = make_float2(acc2[e].x * alpha, acc2[e].y * alpha);
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const float p = expf(s[jj] - mx);
         l += p;
-#pragma unroll
-        for (int e = 0; e < HD; ++e) acc[e] = fmaf(p, Vs[(j0 + jj) * HD + e], acc[e]);
+        axpy16(acc2, p, Vs + (j0 + jj) * HD);
       }
       m = mx;
     }
   }
   if (!live) return;
+  float acc[HD];
+#pragma unroll
+  for (int e = 0; e < HD / 2; ++e) {
+    acc[2 * e] = acc2[e].x;
+    acc[2 * e + 1] = acc2[e].y;
+  }
   if (nsplit == 1) {
     const float inv = 1.f / l;
     float out[HD];
@@ -165,12 +221,14 @@ __global__ void __launch_bounds__(XT) cross_bwd_dq_kernel(const T* __restrict__ 
     load16(q + qi * ld + h * HD, qv);
     load16(d_o + qi * ld + h * HD, gv);
     load16(o + qi * ld + h * HD, ov);
-#pragma unroll
-    for (int j = 0; j < HD; ++j) delta = fmaf(gv[j], ov[j], delta);
+    delta = dot16v(gv, ov);
     L = lse[qi * heads + h];
   }
+  float2 q2[HD / 2], g2[HD / 2], acc2[HD / 2];
+  to_pairs(qv, 0.25f, q2);
+  to_pairs(gv, 1.f, g2);
 #pragma unroll
-  for (int j = 0; j < HD; ++j) qv[j] *= 0.25f;
+  for (int j = 0; j < HD / 2; ++j) acc2[j] = make_float2(0.f, 0.f);
   const int64_t kbeg = split * keys_per_split, kend = min(lk, kbeg + keys_per_split);
   for (int64_t k0 = kbeg; k0 < kend; k0 += XC) {
     __syncthreads();
@@ -178,17 +236,17 @@ __global__ void __launch_bounds__(XT) cross_bwd_dq_kernel(const T* __restrict__ 
     stage16(Vs, v, ld, h, k0, kend);
     __syncthreads();
     const int cnt = (int)min((int64_t)XC, kend - k0);
+#pragma unroll 2
     for (int j = 0; j < cnt; ++j) {
-      float s = 0.f, dp = 0.f;
-#pragma unroll
-      for (int e = 0; e < HD; ++e) {
-        s = fmaf(qv[e], Ks[j * HD + e], s);
-        dp = fmaf(gv[e], Vs[j * HD + e], dp);
-      }
+      const float s = dot16(q2, Ks + j * HD), dp = dot16(g2, Vs + j * HD);
       const float ds = expf(s - L) * (dp - delta) * 0.25f;
-#pragma unroll
-      for (int e = 0; e < HD; ++e) acc[e] = fmaf(ds, Ks[j * HD + e], acc[e]);
+      axpy16(acc2, ds, Ks + j * HD);
     }
+  }
+#pragma unroll
+  for (int e = 0; e < HD / 2; ++e) {
+    acc[2 * e] = acc2[e].x;
+    acc[2 * e + 1] = acc2[e].y;
   }
   if (live) {
     float* dst = dq + qi * ld + h * HD;
@@ -223,6 +281,11 @@ __global__ void __launch_bounds__(XT) cross_bwd_dkv_kernel(const T* __restrict__
     load16(k + ki * ld + h * HD, kv);
     load16(v + ki * ld + h * HD, vv);
   }
+  float2 k2[HD / 2], v2[HD / 2], dk2[HD / 2], dv2[HD / 2];
+  to_pairs(kv, 1.f, k2);
+  to_pairs(vv, 1.f, v2);
+#pragma unroll
+  for (int j = 0; j < HD / 2; ++j) dk2[j] = dv2[j] = make_float2(0.f, 0.f);
   const int64_t qbeg = split * q_per_split, qend = min(lq, qbeg + q_per_split);
   for (int64_t q0 = qbeg; q0 < qend; q0 += XC) {
     __syncthreads();
@@ -233,8 +296,7 @@ __global__ void __launch_bounds__(XT) cross_bwd_dkv_kernel(const T* __restrict__
         load16(q + qi * ld + h * HD, a);
         load16(d_o + qi * ld + h * HD, g);
         load16(o + qi * ld + h * HD, ov);
-#pragma unroll
-        for (int e = 0; e < HD; ++e) de = fmaf(g[e], ov[e], de);
+        de = dot16v(g, ov);
         Ls[threadIdx.x] = lse[qi * heads + h];
       } else {
 #pragma unroll
@@ -250,21 +312,21 @@ __global__ void __launch_bounds__(XT) cross_bwd_dkv_kernel(const T* __restrict__
     }
     __syncthreads();
     const int cnt = (int)min((int64_t)XC, qend - q0);
+#pragma unroll 2
     for (int j = 0; j < cnt; ++j) {
-      float s = 0.f, dp = 0.f;
-#pragma unroll
-      for (int e = 0; e < HD; ++e) {
-        s = fmaf(Qs[j * HD + e], kv[e], s);
-        dp = fmaf(Gs[j * HD + e], vv[e], dp);
-      }
+      const float s = dot16(k2, Qs + j * HD), dp = dot16(v2, Gs + j * HD);
       const float p = expf(s - Ls[j]);
       const float ds = p * (dp - Ds[j]);
-#pragma unroll
-      for (int e = 0; e < HD; ++e) {
-        dva[e] = fmaf(p, Gs[j * HD + e], dva[e]);
-        dka[e] = fmaf(ds, Qs[j * HD + e], dka[e]);  // Qs already carries the 1/4
-      }
+      axpy16(dv2, p, Gs + j * HD);
+      axpy16(dk2, ds, Qs + j * HD);  // Qs already carries the 1/4
     }
+  }
+#pragma unroll
+  for (int e = 0; e < HD / 2; ++e) {
+    dka[2 * e] = dk2[e].x;
+    dka[2 * e + 1] = dk2[e].y;
+    dva[2 * e] = dv2[e].x;
+    dva[2 * e + 1] = dv2[e].y;
   }
   if (live) {
     float* dstk = dk + ki * ld + h * HD;

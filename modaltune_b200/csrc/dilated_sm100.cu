@@ -44,9 +44,6 @@ using namespace sm100;
 #ifndef MT_FWD_POLY
 #define MT_FWD_POLY 0                     // exponentials per 8 computed on the FMA pipes in the forward (ex2_poly)
 #endif
-#ifndef MT_FWD_STAGGER
-#define MT_FWD_STAGGER 0                  // start delay (cycles) of the second forward CTA of each SM in the first wave
-#endif
 static constexpr int DH = 48;            // head dim
 static constexpr int BT = 128;           // slots per tile (queries and keys)
 static constexpr int TILE_BYTES = BT * 128;  // [128 rows][128 B]: 64 bf16 columns per row, SWIZZLE_128B
@@ -73,9 +70,8 @@ struct FwdSmem {
   static constexpr int K = Q + TILE_BYTES;
   static constexpr int V = K + KV_STAGES * TILE_BYTES;
   static constexpr int BAR = V + KV_STAGES * TILE_BYTES;
-  // barriers (8 B each): q_full, kv_full[2], kv_empty[2], s_full, s_free, p_full, o_full[2], (forward v2: v_full[2],
-  // v_empty[2], the first two pairs then serve K alone); then the TMEM pointer
-  static constexpr int NBAR = 14;
+  // barriers (8 B each): q_full, kv_full[2], kv_empty[2], s_full, s_free, p_full, o_full[2]; then the TMEM pointer
+  static constexpr int NBAR = 10;
   static constexpr int TMEM_PTR = BAR + NBAR * 8;
   static constexpr int XCH = TMEM_PTR + 16;          // forward with two threads per row: 3 x [2][128] floats
   static constexpr int TOTAL = XCH + 3 * 2 * 128 * 4;
@@ -380,12 +376,8 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
   const int n_zero_tail = max(0, bg.m - n_kv * BT);
 
   const uint32_t bar_q_full = sbase + FwdSmem::BAR + 0;
-  // K and V have their own 2-stage rings: a K stage is free as soon as its Q K^T has completed, a full tile time before
-  // the P V that frees the V stage, so the load of K_{j+1} (which gates S_{j+1}) starts a tile earlier
-  const uint32_t bar_k_full = sbase + FwdSmem::BAR + 8;     // [2]
-  const uint32_t bar_k_empty = sbase + FwdSmem::BAR + 24;   // [2]
-  const uint32_t bar_v_full = sbase + FwdSmem::BAR + 80;    // [2]
-  const uint32_t bar_v_empty = sbase + FwdSmem::BAR + 96;   // [2]
+  const uint32_t bar_kv_full = sbase + FwdSmem::BAR + 8;    // [2]
+  const uint32_t bar_kv_empty = sbase + FwdSmem::BAR + 24;  // [2]
   const uint32_t bar_s_full = sbase + FwdSmem::BAR + 40;
   const uint32_t bar_s_free = sbase + FwdSmem::BAR + 48;
   const uint32_t bar_p_full = sbase + FwdSmem::BAR + 56;
@@ -395,10 +387,8 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
   if (threadIdx.x == 0) {
     mbar_init(bar_q_full, 1);
     for (int i = 0; i < KV_STAGES; ++i) {
-      mbar_init(bar_k_full + 8 * i, 1);
-      mbar_init(bar_k_empty + 8 * i, 1);
-      mbar_init(bar_v_full + 8 * i, 1);
-      mbar_init(bar_v_empty + 8 * i, 1);
+      mbar_init(bar_kv_full + 8 * i, 1);
+      mbar_init(bar_kv_empty + 8 * i, 1);
       mbar_init(bar_o_full + 8 * i, 1);
     }
     mbar_init(bar_s_full, 1);
@@ -427,12 +417,10 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
       tma_load_3d(sbase + FwdSmem::Q, map, bar_q_full, h * DH, off, jseg + q0);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1, use = j >> 1;
-        mbar_wait(bar_k_empty + 8 * st, (use & 1) ^ 1);
-        mbar_expect_tx(bar_k_full + 8 * st, TILE_BYTES);
-        tma_load_3d(sbase + FwdSmem::K + st * TILE_BYTES, map, bar_k_full + 8 * st, E + h * DH, off, jseg + j * BT);
-        mbar_wait(bar_v_empty + 8 * st, (use & 1) ^ 1);
-        mbar_expect_tx(bar_v_full + 8 * st, TILE_BYTES);
-        tma_load_3d(sbase + FwdSmem::V + st * TILE_BYTES, map, bar_v_full + 8 * st, 2 * E + h * DH, off, jseg + j * BT);
+        mbar_wait(bar_kv_empty + 8 * st, (use & 1) ^ 1);
+        mbar_expect_tx(bar_kv_full + 8 * st, 2 * TILE_BYTES);
+        tma_load_3d(sbase + FwdSmem::K + st * TILE_BYTES, map, bar_kv_full + 8 * st, E + h * DH, off, jseg + j * BT);
+        tma_load_3d(sbase + FwdSmem::V + st * TILE_BYTES, map, bar_kv_full + 8 * st, 2 * E + h * DH, off, jseg + j * BT);
       }
     }
   } else if (warp == W_MMA) {
@@ -451,28 +439,26 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
           umma_ss(tmem_s, umma_desc_adv(q_desc, k * 32), umma_desc_adv(kd, k * 32), IDESC_QK, k > 0);
-        umma_commit(bar_k_empty + 8 * (j & 1));
         umma_commit(bar_s_full);
       }
       __syncwarp();
     };
     MT_TRACE_DECL
     mbar_wait(bar_q_full, 0);
-    mbar_wait(bar_k_full, 0);
+    mbar_wait(bar_kv_full, 0);
     tc_fence_after();
     MT_TRACE(0);
     issue_qk(0);
     for (int j = 0; j < n_kv; ++j) {
       if (j + 1 < n_kv) {
-        mbar_wait(bar_k_full + 8 * ((j + 1) & 1), ((j + 1) >> 1) & 1);
+        mbar_wait(bar_kv_full + 8 * ((j + 1) & 1), ((j + 1) >> 1) & 1);
         MT_TRACE(100 + j);
         mbar_wait(bar_s_free, j & 1);  // the softmax threads have read S_j out of TMEM
         tc_fence_after();
         MT_TRACE(200 + j);
         issue_qk(j + 1);
       }
-      mbar_wait(bar_p_full, j & 1);    // P_j is in TMEM
-      mbar_wait(bar_v_full + 8 * (j & 1), (j >> 1) & 1);
+      mbar_wait(bar_p_full, j & 1);    // P_j is in TMEM (and the O tile of P_{j-1} V_{j-1} has been folded)
       tc_fence_after();
       MT_TRACE(300 + j);
       if (elect_one()) {
@@ -482,7 +468,7 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k)
           umma_ts(tmem_o, tmem_p + k * 8, umma_desc_adv(vd, k * 2048), IDESC_PV, (j > 0) || (k > 0));
-        umma_commit(bar_v_empty + 8 * (j & 1));
+        umma_commit(bar_kv_empty + 8 * (j & 1));
         umma_commit(bar_o_full);
       }
       __syncwarp();
@@ -503,17 +489,6 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
     float m_used = -INFINITY, l_run = 0.f;
     const float scale_log2 = P.scale_log2;
     MT_TRACE_DECL
-#if MT_FWD_STAGGER > 0
-    // The two CTAs of an SM alternate between an exponential phase (MUFU-bound, ~1 100 cycles per tile when a CTA has
-    // the unit to itself) and a phase without exponentials (score load, maximum, barriers).  CTAs that start together
-    // stay in phase -- both in their exponentials at half rate, then both off the MUFU unit -- and the offset between
-    // two equally long CTAs never changes.  Delaying the second CTA of every SM in the first wave by about half a tile
-    // period puts the pairs in anti-phase; their successors inherit the offset.
-    if (blockIdx.x >= kNumSMs && blockIdx.x < 2 * kNumSMs) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < MT_FWD_STAGGER) {}
-    }
-#endif
     auto tile = [&](int j, auto mask_tag) {
       constexpr bool MASK = decltype(mask_tag)::value;
       const int kvalid = bg.m - j * BT;  // key slots of this tile that belong to the segment (>= 1)
@@ -521,40 +496,20 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
       mbar_wait(bar_s_full, j & 1);
       tc_fence_after();
       MT_TRACE(1100 + j);
-      // The row maximum is four independent 3-input chains (a single chain of 64 dependent FMNMX3 cost ~300 cycles in
-      // which this warp kept neither the MUFU nor the FMA pipe busy); with one thread per row the maximum of the first
-      // 64 columns is taken while the load of the second 64 is still in flight.
       float sv[NC];
-      float m4[4];
-      auto max_block = [&](int c0) {    // 64 columns starting at c0: 4 chains x 16 values
-        if (MASK) {
-#pragma unroll
-          for (int i = 0; i < 64; ++i) sv[c0 + i] = (half * NC + c0 + i < kvalid) ? sv[c0 + i] : -INFINITY;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float m = fmax3(sv[c0 + 16 * q], sv[c0 + 16 * q + 1], sv[c0 + 16 * q + 2]);
-#pragma unroll
-          for (int i = 3; i + 1 < 16; i += 2) m = fmax3(m, sv[c0 + 16 * q + i], sv[c0 + 16 * q + i + 1]);
-          m = fmaxf(m, sv[c0 + 16 * q + 15]);
-          m4[q] = (c0 == 0) ? m : fmaxf(m4[q], m);
-        }
-      };
       tmem_ld64(tmem_s + t_lane + half * NC, sv);
+      if (TPR == 1) tmem_ld64(tmem_s + t_lane + 64, sv + (TPR == 1 ? 64 : 0));
       tmem_ld_wait();
-      if (TPR == 1) {
-        tmem_ld64(tmem_s + t_lane + 64, sv + (TPR == 1 ? 64 : 0));
-        max_block(0);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(bar_s_free);        // S_j is in registers: the MMA warp may overwrite it with S_{j+1}
-        max_block(TPR == 1 ? 64 : 0);
-      } else {
-        tc_fence_before();
-        mbar_arrive(bar_s_free);
-        max_block(0);
+      tc_fence_before();
+      mbar_arrive(bar_s_free);          // S_j is in registers: the MMA warp may overwrite it with S_{j+1}
+      if (MASK) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) sv[i] = (half * NC + i < kvalid) ? sv[i] : -INFINITY;
       }
-      float mx = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
+      float mx = fmax3(sv[0], sv[1], sv[2]);
+#pragma unroll
+      for (int i = 3; i + 1 < NC; i += 2) mx = fmax3(mx, sv[i], sv[i + 1]);
+      mx = fmaxf(mx, sv[NC - 1]);
       if (TPR == 2) {   // the two threads of a row agree on its maximum (double-buffered slot, 64-thread named barrier)
         float* x = xch + (j & 1) * 256;
         x[half * 128 + row] = mx;
@@ -589,6 +544,10 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
         }
       }
       const float mb = m_used * scale_log2;
+      if (j > 0 && !waited) {             // P_j overwrites P_{j-1}: its P V must have read it
+        mbar_wait(bar_o_full, (j - 1) & 1);
+        tc_fence_after();
+      }
       MT_TRACE(1300 + j);
       float rs = 0.f;
 #pragma unroll
@@ -604,10 +563,6 @@ dilated_fwd2_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Pa
           const float p1 = (!MASK && ((i + 1) & 7) < MT_FWD_POLY) ? ex2_poly(x1) : ex2(x1);
           rs += p0 + p1;
           pk[i >> 1] = pack_bf16(p0, p1);
-        }
-        if (c == 0 && j > 0 && !waited) {   // P_j overwrites P_{j-1}: its P V must have read it.  Waiting only here,
-          mbar_wait(bar_o_full, (j - 1) & 1);  // with the first 32 exponentials already computed, hides the wait
-          tc_fence_after();
         }
         tmem_st16(tmem_p + t_lane + half * (NC / 2) + c * 16, pk);  // 32 keys = 16 packed columns
       }

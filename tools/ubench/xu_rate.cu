@@ -19,7 +19,7 @@ __device__ __forceinline__ uint32_t pack_int(float a, float b) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) k(int iters, float seed, float scale, long long* cyc, uint32_t* sink) {
+__global__ void __launch_bounds__(512) k(int iters, float seed, float scale, long long* cyc, uint32_t* sink) {
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = seed + 0.001f * (threadIdx.x + i);
@@ -78,6 +78,15 @@ int main() {
     const double elems = (double)iters * 16 * 256;   // elements (= exponentials where present) per SM
     printf("mode %d %-34s %9.0f cycles  %.2f elements/clk/SM  (%.2f cycles per 128x128 tile)\n", mode, names[mode], c, elems / c,
            16384.0 * c / elems);
+  }
+  // the full mix with 1, 2 and 4 warps per scheduler: can ONE warp keep the MUFU unit of its scheduler busy?
+  for (int threads = 128; threads <= 512; threads *= 2) {
+    for (int rep = 0; rep < 2; ++rep) { k<4><<<148, threads>>>(iters, -0.5f, 1.f, cyc, sink); cudaDeviceSynchronize(); }
+    long long h[148]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double c = 0; for (int i = 0; i < 148; ++i) c += h[i]; c /= 148;
+    const double elems = (double)iters * 16 * threads;
+    printf("mode 4 with %d warp(s) per scheduler: %.2f elements/clk/SM (%.1f cycles per exponential and scheduler)\n", threads / 128,
+           elems / c, c / (iters * 16.0 * (threads / 128)));
   }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
