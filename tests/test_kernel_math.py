@@ -51,3 +51,36 @@ def test_ex2_poly_clamps_instead_of_underflowing():
     x = np.array([-1e4, -126.0, -125.5, -np.inf], dtype=np.float32)
     got = ex2_poly(x)
     assert np.all(np.isfinite(got)) and np.all(got > 0) and np.all(got <= np.float32(2.0 ** -124))
+
+
+def _erf_fast_constants():
+    src = open(os.path.join(ROOT, "modaltune_b200", "csrc", "elementwise.cu")).read()
+    body = src[src.index("float erf_fast(float x)"):]
+    body = body[:body.index("asm(")]
+    hexes = re.findall(r"-?0x1\.[0-9a-f]+p[-+]\d+f", body)
+    assert len(hexes) == 6, hexes
+    return [np.float32(float.fromhex(h[:-1])) for h in hexes]   # c6 .. c1
+
+
+def erf_fast(x):
+    """fp32 restatement of elementwise.cu:erf_fast: 1 - 2^-(t * poly(t)), t = min(|x|, 4)."""
+    cs = _erf_fast_constants()
+    x = x.astype(np.float32)
+    t = np.minimum(np.abs(x), np.float32(4.0))
+    r = np.full_like(t, cs[0])
+    for c in cs[1:]:
+        r = (r * t + c).astype(np.float32)
+    e = np.exp2(-(r * t).astype(np.float32).astype(np.float64)).astype(np.float32)
+    return np.copysign((np.float32(1.0) - e).astype(np.float32), x)
+
+
+def test_erf_fast_absolute_error():
+    from scipy.special import erf
+    x = np.concatenate([np.linspace(-6, 6, 240001), [0.0, 1e-6, -1e-6, 4.0, 100.0, -100.0]]).astype(np.float32)
+    got = erf_fast(x).astype(np.float64)
+    err = np.abs(got - erf(x.astype(np.float64)))
+    assert err.max() < 5e-7, err.max()
+    # what the kernels use it for: GELU(x) = x/2 (1 + erf(x / sqrt 2)) within 1e-6 absolute on the whole range
+    g = 0.5 * x.astype(np.float64) * (1.0 + erf_fast((x * np.float32(0.70710678118654752)).astype(np.float32)))
+    g_ref = 0.5 * x.astype(np.float64) * (1.0 + erf(x.astype(np.float64) / np.sqrt(2.0)))
+    assert np.abs(g - g_ref).max() < 2e-5 and np.abs(g - g_ref)[np.abs(x) < 6].max() < 2e-6
