@@ -288,10 +288,10 @@ def main():
     # for the configuration that capture was taken on
     traffic, traffic_src = None, None
     if args.tiles == 10000 and config.attn_impl("bwd") == 3:
-        traffic = 242.375936e6 + 97.083392e6
-        traffic_src = "profiles/r1_ncu_attention_v3.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+        traffic = 243.394560e6 + 97.534208e6
+        traffic_src = "profiles/r1_ncu_attention_final.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
     bwd_names = {0: "simt", 1: "tcgen05", 2: "tcgen05-tmem", 3: "tcgen05-tmem-aug"}
-    fwd_names = {0: "simt", 1: "tcgen05", 2: "tcgen05-tmem-acc"}
+    fwd_names = {0: "simt", 1: "tcgen05", 2: "tcgen05-tmem-acc", 3: "tcgen05-tmem-acc-2tpr"}
     roofline = {
         "bound": "tensor", "kernel": f"dilated_attn_bwd[{bwd_names[config.attn_impl('bwd')]}]", "achieved": ach_bwd,
         "peak": peak, "peak_source": peak_src, "unit": "TFLOP/s", "frac": ach_bwd / peak, "traffic": traffic,
