@@ -10,7 +10,8 @@ rank processes its own slides (weak scaling, no data-path collective).  Prints O
 
 * ``value``: device-resident slides/s (inputs already in HBM), CUDA events, max over ranks.
 * ``e2e``: the same step driven from pinned HOST buffers through the module API, H2D copy of the slide and D2H read of
-  loss / logits inside the timed region.
+  loss / logits inside the timed region (every step copies its slide; the copy of slide i + 1 is issued on a copy stream
+  while step i runs, ``GraphedStep.prefetch``).
 * ``roofline``: the dilated-attention backward kernel (the dominant kernel), timed live with CUDA events on its stream
   inside the timed region; algorithmic FLOPs = 2.5 * 4*d*sum c^2 per launch against the measured bf16
   tensor peak of MEASURED_PEAKS.json.
@@ -247,6 +248,7 @@ def main():
             loss, logits = eager_step({k: v.to(dev, non_blocking=True) for k, v in h.items()})
         else:
             loss, logits = graphed(h)
+            graphed.prefetch(hosts[(i + 1) % n_slides][0])   # the next slide's H2D copy overlaps this step
         out["loss"], out["logits"] = float(loss), logits.float().cpu()   # D2H reads (synchronising, like loss.item())
 
     e2e_step(0)

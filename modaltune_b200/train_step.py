@@ -158,6 +158,7 @@ class GraphedStep:
         self.model, self.projector, self.flat, self.sizes = model, projector, flat, list(sizes)
         dev = next(model.parameters()).device
         self.static = {k: v.to(dev).clone() for k, v in packed_example.items()}
+        self._copy_stream, self._staging, self._staged_for = None, None, None
         slide = unpack_slide(self.static, self.sizes)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -174,9 +175,34 @@ class GraphedStep:
             self.grads = flat.gather()
 
     def load(self, packed: Dict):
-        """Copy one packed slide (pinned host or device tensors of the captured shapes) into the static inputs."""
+        """Copy one packed slide (pinned host or device tensors of the captured shapes) into the static inputs.  A slide
+        announced with ``prefetch`` is already in the device staging buffers: it costs one device-to-device copy."""
+        if packed is self._staged_for:
+            torch.cuda.current_stream().wait_event(self._staged_evt)
+            for k, v in self.static.items():
+                v.copy_(self._staging[k], non_blocking=True)
+            self._consumed_evt.record()
+            self._staged_for = None
+            return
         for k, v in self.static.items():
             v.copy_(packed[k], non_blocking=True)
+
+    def prefetch(self, packed: Dict):
+        """Double buffering of the input path (the job of the reference's pinned-memory DataLoader workers,
+        utils/base_trainer.py:283-300): start the host-to-device copy of the NEXT slide on a copy stream, into staging
+        buffers, while the current step runs.  The copy waits only for the previous consumer of the staging buffers,
+        not for the step in flight; ``load`` of the same ``packed`` object then takes it from there."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._staging = {k: torch.empty_like(v) for k, v in self.static.items()}
+            self._staged_evt, self._consumed_evt = torch.cuda.Event(), torch.cuda.Event()
+            self._consumed_evt.record()
+        self._copy_stream.wait_event(self._consumed_evt)
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in self._staging.items():
+                v.copy_(packed[k], non_blocking=True)
+            self._staged_evt.record()
+        self._staged_for = packed
 
     def __call__(self, packed: Optional[Dict] = None):
         if packed is not None:

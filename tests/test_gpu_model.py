@@ -211,6 +211,33 @@ def test_graphed_step_equals_eager_step(model):
     assert helpers.relerr(g_graph, g_eager) < 1e-3
 
 
+def test_graphed_step_prefetch_double_buffering(model):
+    """``GraphedStep.prefetch`` (H2D copy of the next slide on a copy stream while a step runs) feeds the same inputs
+    as the direct host copy: slides alternate A, B, A through the staging buffers and reproduce the direct results."""
+    proj = helpers.build_projector(0, DEV)
+    flat = train_step.FlatGradAllReduce([p for p in model.parameters() if p.requires_grad])
+    slides = [synthetic.synthetic_slide(700, seed=s, group_sizes=helpers.SMALL_GROUPS) for s in (41, 42)]
+    packed = [train_step.pack_host_slide(s)[0] for s in slides]
+    sizes = train_step.pack_host_slide(slides[0])[1]
+    with config.using(mode="bf16"):
+        graphed = train_step.GraphedStep(model, proj, packed[0], sizes, flat)
+        direct = []
+        for k in (0, 1):
+            loss, logits = graphed(packed[k])
+            direct.append((float(loss), logits.clone()))
+        graphed.prefetch(packed[0])
+        got = []
+        for i in range(3):
+            loss, logits = graphed(packed[i % 2])           # staged by the previous iteration's prefetch
+            graphed.prefetch(packed[(i + 1) % 2])           # overlaps the step in flight
+            got.append((float(loss), logits.clone()))
+    for i, (loss, logits) in enumerate(got):
+        want = direct[i % 2]
+        assert abs(loss - want[0]) < 1e-5 * abs(want[0]) + 1e-7, (i, loss, want[0])
+        assert helpers.relerr(logits, want[1]) < 1e-5, i
+    assert abs(direct[0][0] - direct[1][0]) > 1e-6          # the two slides really differ
+
+
 def test_variable_length_slides_and_pancancer_task_tokens():
     """C5-style use: one model instance steps slides of different tile counts back to back (geometry, workspaces and
     tensor maps are per call), and a 4-way task one-hot (pan-cancer, train_modaltune_pancancer.py) drives the same path."""
