@@ -77,10 +77,12 @@ int mt_embed_assemble(const void* proj, int proj_dtype, const float* bias, const
 int mt_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, const void* add, int add_dtype,
                      int64_t add_rows, void* y, int y_dtype, float* mean, float* rstd, int64_t rows, int64_t cols,
                      float eps, void* stream);
-/* bwd: dx = LN'(dy) [+ residual];  optional dgamma/dbeta [cols] f32 (accumulated with atomics into zeroed buffers). */
+/* bwd: dx = LN'(dy) [+ residual];  optional dgamma/dbeta [cols] f32 (accumulated with atomics into zeroed buffers);
+ * dx_bf16 (or NULL): a second copy of dx rounded to bf16, written in the same pass for the GEMM that consumes the
+ * gradient next (saves a separate cast pass over [rows, cols]). */
 int mt_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma, const float* mean,
-                     const float* rstd, const void* residual, int res_dtype, void* dx, int dx_dtype, float* dgamma,
-                     float* dbeta, int64_t rows, int64_t cols, void* stream);
+                     const float* rstd, const void* residual, int res_dtype, void* dx, int dx_dtype, void* dx_bf16,
+                     float* dgamma, float* dbeta, int64_t rows, int64_t cols, void* stream);
 
 /* residual add fused with the next pre-LN (torchscale/architecture/encoder.py:152-166):
  * x_out = x + D(a [+ abias]) (f32 residual stream, a in a_dtype, abias [cols] f32 or NULL = bias of the GEMM that

@@ -200,8 +200,8 @@ __global__ void __launch_bounds__(RowCfg<COLS>::THREADS, RowCfg<COLS>::MINB) ln_
                                                      const float* __restrict__ xbias,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const TR* __restrict__ residual,
-                                                     TDX* __restrict__ dx, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, int64_t rows) {
+                                                     TDX* __restrict__ dx, __nv_bfloat16* __restrict__ dx_lp,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows) {
   using C = RowCfg<COLS>;
   __shared__ float red[C::RPB * (C::TPR / 32) + 1];
   const int t = threadIdx.x % C::TPR, rib = threadIdx.x / C::TPR;
@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(RowCfg<COLS>::THREADS, RowCfg<COLS>::MINB) ln_
           for (int j = 0; j < 8; ++j) o[j] += r[j];
         }
         store8(dx + row * COLS + c, o);
+        if (dx_lp != nullptr) store8(dx_lp + row * COLS + c, o);   // bf16 twin for the GEMM that consumes dx next
       }
     }
   }
@@ -578,7 +579,7 @@ static int dispatch_ln_fwd(const void* x, int xd, const float* xbias, const floa
 
 template <int COLS, bool GELU, typename TDY, typename TX, typename TDX>
 static int launch_ln_bwd(const void* dy, const void* x, const float* xbias, const float* gamma, const float* mean, const float* rstd,
-                         const void* residual, int rd, void* dx, float* dgamma, float* dbeta, int64_t rows,
+                         const void* residual, int rd, void* dx, void* dx_lp, float* dgamma, float* dbeta, int64_t rows,
                          cudaStream_t st) {
   using C = RowCfg<COLS>;
   int grid = grid_for(rows, C::RPB);
@@ -590,23 +591,23 @@ static int launch_ln_bwd(const void* dy, const void* x, const float* xbias, cons
         return MT_E_UNSUPPORTED;
       }
       ln_bwd_kernel<COLS, TDY, TX, float, TDX, GELU, true><<<grid, C::THREADS, 0, st>>>(
-          (const TDY*)dy, (const TX*)x, xbias, gamma, mean, rstd, (const float*)residual, (TDX*)dx, dgamma, dbeta, rows);
+          (const TDY*)dy, (const TX*)x, xbias, gamma, mean, rstd, (const float*)residual, (TDX*)dx, (__nv_bfloat16*)dx_lp, dgamma, dbeta, rows);
     }
   } else if (residual == nullptr || rd == MT_F32)
     ln_bwd_kernel<COLS, TDY, TX, float, TDX, GELU, false><<<grid, C::THREADS, 0, st>>>(
-        (const TDY*)dy, (const TX*)x, xbias, gamma, mean, rstd, (const float*)residual, (TDX*)dx, dgamma, dbeta, rows);
+        (const TDY*)dy, (const TX*)x, xbias, gamma, mean, rstd, (const float*)residual, (TDX*)dx, (__nv_bfloat16*)dx_lp, dgamma, dbeta, rows);
   else
     ln_bwd_kernel<COLS, TDY, TX, __nv_bfloat16, TDX, GELU, false><<<grid, C::THREADS, 0, st>>>(
-        (const TDY*)dy, (const TX*)x, xbias, gamma, mean, rstd, (const __nv_bfloat16*)residual, (TDX*)dx, dgamma, dbeta, rows);
+        (const TDY*)dy, (const TX*)x, xbias, gamma, mean, rstd, (const __nv_bfloat16*)residual, (TDX*)dx, (__nv_bfloat16*)dx_lp, dgamma, dbeta, rows);
   return check_launch("ln_bwd_kernel");
 }
 
 template <int COLS, bool GELU>
 static int dispatch_ln_bwd(const void* dy, int dyd, const void* x, int xd, const float* xbias, const float* gamma, const float* mean,
-                           const float* rstd, const void* residual, int rd, void* dx, int dxd, float* dgamma,
+                           const float* rstd, const void* residual, int rd, void* dx, int dxd, void* dx_lp, float* dgamma,
                            float* dbeta, int64_t rows, cudaStream_t st) {
 #define MT_LNB(TDY, TX, TDX) \
-  return launch_ln_bwd<COLS, GELU, TDY, TX, TDX>(dy, x, xbias, gamma, mean, rstd, residual, rd, dx, dgamma, dbeta, rows, st)
+  return launch_ln_bwd<COLS, GELU, TDY, TX, TDX>(dy, x, xbias, gamma, mean, rstd, residual, rd, dx, dx_lp, dgamma, dbeta, rows, st)
   using bf = __nv_bfloat16;
   if (dyd == MT_F32 && xd == MT_F32 && dxd == MT_F32) MT_LNB(float, float, float);
   if (dyd == MT_BF16 && xd == MT_F32 && dxd == MT_F32) MT_LNB(bf, float, float);
@@ -655,14 +656,15 @@ extern "C" int mt_layernorm_fwd(const void* x, int x_dtype, const float* gamma, 
 
 extern "C" int mt_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
                                 const float* mean, const float* rstd, const void* residual, int res_dtype, void* dx,
-                                int dx_dtype, float* dgamma, float* dbeta, int64_t rows, int64_t cols, void* stream) {
+                                int dx_dtype, void* dx_bf16, float* dgamma, float* dbeta, int64_t rows, int64_t cols,
+                                void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (rows == 0) return 0;
   MT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm bwd: dgamma and dbeta go together");
   if (cols == 768)
-    return dispatch_ln_bwd<768, false>(dy, dy_dtype, x, x_dtype, nullptr, gamma, mean, rstd, residual, res_dtype, dx, dx_dtype, dgamma, dbeta, rows, st);
+    return dispatch_ln_bwd<768, false>(dy, dy_dtype, x, x_dtype, nullptr, gamma, mean, rstd, residual, res_dtype, dx, dx_dtype, dx_bf16, dgamma, dbeta, rows, st);
   if (cols == 3072)
-    return dispatch_ln_bwd<3072, false>(dy, dy_dtype, x, x_dtype, nullptr, gamma, mean, rstd, residual, res_dtype, dx, dx_dtype, dgamma, dbeta, rows, st);
+    return dispatch_ln_bwd<3072, false>(dy, dy_dtype, x, x_dtype, nullptr, gamma, mean, rstd, residual, res_dtype, dx, dx_dtype, dx_bf16, dgamma, dbeta, rows, st);
   set_error("layernorm bwd: width %lld not supported (768, 3072)", (long long)cols);
   return MT_E_UNSUPPORTED;
 }
@@ -687,9 +689,9 @@ extern "C" int mt_gelu_ln_bwd(const void* dy, int dy_dtype, const void* h, int h
   cudaStream_t st = (cudaStream_t)stream;
   if (rows == 0) return 0;
   if (cols == 3072)
-    return dispatch_ln_bwd<3072, true>(dy, dy_dtype, h, h_dtype, hbias, gamma, mean, rstd, nullptr, 0, dh, dh_dtype, nullptr, nullptr, rows, st);
+    return dispatch_ln_bwd<3072, true>(dy, dy_dtype, h, h_dtype, hbias, gamma, mean, rstd, nullptr, 0, dh, dh_dtype, nullptr, nullptr, nullptr, rows, st);
   if (cols == 768)
-    return dispatch_ln_bwd<768, true>(dy, dy_dtype, h, h_dtype, hbias, gamma, mean, rstd, nullptr, 0, dh, dh_dtype, nullptr, nullptr, rows, st);
+    return dispatch_ln_bwd<768, true>(dy, dy_dtype, h, h_dtype, hbias, gamma, mean, rstd, nullptr, 0, dh, dh_dtype, nullptr, nullptr, nullptr, rows, st);
   set_error("gelu_ln bwd: width %lld not supported (768, 3072)", (long long)cols);
   return MT_E_UNSUPPORTED;
 }

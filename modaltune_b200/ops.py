@@ -144,18 +144,35 @@ def layernorm_fwd(x, gamma, beta, out_dtype, add=None, eps: float = LN_EPS, want
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx_dtype, residual=None, want_wgrad: bool = False, out=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_dtype, residual=None, want_wgrad: bool = False, out=None,
+                  bf16_twin: bool = False):
+    """``bf16_twin``: also write dx rounded to bf16 in the same pass (kept as ``dx._mt_bf16``): the next GEMM of the
+    backward chain takes it instead of running a separate cast over the tensor."""
     rows, cols = x.shape
     dx = out if out is not None else torch.empty((rows, cols), device=x.device, dtype=dx_dtype)
+    twin = torch.empty((rows, cols), device=x.device, dtype=torch.bfloat16) if bf16_twin else None
     dgamma = dbeta = None
     if want_wgrad:
         dgamma = torch.zeros(cols, device=x.device, dtype=torch.float32)
         dbeta = torch.zeros(cols, device=x.device, dtype=torch.float32)
     rc = _lib.load().mt_layernorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(mean), _p(rstd), _p(residual),
-                                      _dt(residual) if residual is not None else 0, _p(dx), _dt(dx), _p(dgamma),
-                                      _p(dbeta), rows, cols, _stream())
+                                      _dt(residual) if residual is not None else 0, _p(dx), _dt(dx), _p(twin),
+                                      _p(dgamma), _p(dbeta), rows, cols, _stream())
     _check(rc, "mt_layernorm_bwd")
+    if twin is not None:
+        dx._mt_bf16 = twin
     return dx, dgamma, dbeta
+
+
+def _as_compute(t: torch.Tensor, cdt: torch.dtype) -> torch.Tensor:
+    """``t`` in the compute dtype: the bf16 twin written by the producing LayerNorm backward when there is one (the
+    attribute travels with the tensor object through autograd), else a cast pass."""
+    if cdt == torch.float32:
+        return t
+    twin = getattr(t, "_mt_bf16", None)
+    if twin is not None and cdt == torch.bfloat16 and twin.shape == t.shape:
+        return twin
+    return cast(t, cdt)
 
 
 class DropSpec:
@@ -582,18 +599,19 @@ def encoder_layer_backward(dy: torch.Tensor, saved, W: FrozenLayerWeights, geom:
     if rng:
         d_f2 = dropout_bwd_cast(dy, cdt, rng[1])
     else:
-        d_f2 = dy if cdt == torch.float32 else cast(dy, cdt)
+        d_f2 = _as_compute(dy, cdt)
     dg = _matmul_f32out(d_f2, W.w_2)                                 # fp32 [N, 3072]
     d_f1 = gelu_ln_bwd(dg, f1, W.ln_ffn[0], mean_f, rstd_f, cdt, hbias=W.b_1)
     del dg
     dh2 = _matmul_f32out(d_f1, W.w_1)                                # fp32 [N, 768]
     del d_f1
-    dx1, _, _ = layernorm_bwd(dh2, x1, W.ln2[0], mean2, rstd2, torch.float32, residual=dy)
+    twin = cdt == torch.bfloat16 and not rng
+    dx1, _, _ = layernorm_bwd(dh2, x1, W.ln2[0], mean2, rstd2, torch.float32, residual=dy, bf16_twin=twin)
     del dh2
     if rng:
         d_out = dropout_bwd_cast(dx1, cdt, rng[0])
     else:
-        d_out = dx1 if cdt == torch.float32 else cast(dx1, cdt)
+        d_out = _as_compute(dx1, cdt)
     d_aln = _matmul_f32out(d_out, W.w_o)                             # fp32 [N, 768]
     dattn, delta_br = dilated_merge_ln_bwd(geom, d_aln, o_br, lse_br, W.ln_in[0], mean_a, rstd_a)
     del d_aln

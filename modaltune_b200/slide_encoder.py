@@ -115,8 +115,10 @@ class LongNetEncoderLayer(nn.Module):
         if self.training and (self.dropout > 0.0 or self.drop_path_prob > 0.0):
             assert B == 1, "train-mode DropPath is drawn per sample; the ModalTune path runs one slide per step"
             rng = ops.train_rng(x.device, self.dropout, self.drop_path_prob, 2 * self.layer_index)
+        if B == 1:   # pure views: the backward of x[0] would zero-fill and copy a [1, N, 768] gradient per layer
+            return ops.frozen_encoder_layer(x.reshape(N, E).float(), W, geom, cdt, impl, rng).unsqueeze(0), None
         outs = [ops.frozen_encoder_layer(x[b].float(), W, geom, cdt, impl, rng) for b in range(B)]
-        y = outs[0].unsqueeze(0) if B == 1 else torch.stack(outs, 0)
+        y = torch.stack(outs, 0)
         return y, None
 
 

@@ -36,7 +36,7 @@ def _ln_bwd(dy, u, gamma, mean, rstd):
     return rstd[:, None] * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True)), xh
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx_dtype, residual=None, want_wgrad=False, out=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_dtype, residual=None, want_wgrad=False, out=None, bf16_twin=False):
     dx, xh = _ln_bwd(dy, x.float(), gamma, mean, rstd)
     if residual is not None:
         dx = dx + residual.float()
@@ -46,6 +46,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx_dtype, residual=None, want_wgrad=
     if out is not None:
         out.copy_(dx)
         dx = out
+    if bf16_twin:
+        dx._mt_bf16 = dx.to(torch.bfloat16)
     return dx, dg, db
 
 

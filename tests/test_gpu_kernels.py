@@ -49,6 +49,10 @@ def test_layernorm_fwd_bwd(rows, cols, xdt, ydt):
     assert rel(dx, dx_c) < 2e-5
     if want_w:
         assert rel(dg, dg_c) < 1e-4 and rel(db, db_c) < 1e-4
+    # the bf16 twin written in the same pass is exactly the rounded fp32 result
+    dx2, _, _ = ops.layernorm_bwd(dy.to(DEV), x.to(DEV), gamma.to(DEV), m, r, torch.float32, residual=res.to(DEV),
+                                  bf16_twin=True)
+    assert torch.equal(dx2, dx) and torch.equal(dx2._mt_bf16, dx.to(torch.bfloat16))
 
 
 def test_layernorm_fused_add_and_add_layernorm():
