@@ -74,7 +74,7 @@ def _mha_core(mha: nn.MultiheadAttention, query, key, value):
 
 def _rows(t: torch.Tensor) -> torch.Tensor:
     assert t.dim() == 3 and t.shape[0] == 1, "the ModalTune path runs one slide per step (batch 1, train_modaltune.py:78)"
-    return t[0]
+    return t.squeeze(0)   # a view both ways: the backward of t[0] zero-fills and copies a [1, L, 768] gradient
 
 
 def _pos_rows(pos: Optional[torch.Tensor], rows: int) -> Optional[torch.Tensor]:

@@ -28,3 +28,11 @@ tot = sum(r[0] for r in rows)
 print(f"GPU kernel time total {tot/1e3:.2f} ms over {sum(r[1] for r in rows)} kernels")
 for t, c, k in rows[:45]:
     print(f"{t/1e3:9.3f} ms {c:6d}x {100*t/tot:5.1f}%  {k[:110]}")
+if "--ops" in sys.argv:   # ATen operators by device time, grouped by input shape: where the autograd glue comes from
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof2:
+        step(); torch.cuda.synchronize()
+    ops_ = [e for e in prof2.key_averages(group_by_input_shape=True) if e.device_type.name == "CPU" and e.self_device_time_total > 0]
+    ops_.sort(key=lambda e: -e.self_device_time_total)
+    print("\nATen operators by SELF device time (grouped by input shapes)")
+    for e in ops_[:40]:
+        print(f"{e.self_device_time_total/1e3:9.3f} ms {e.count:5d}x  {e.key[:40]:40s} {str(e.input_shapes)[:110]}")
