@@ -95,6 +95,72 @@ def _cases():
     return out
 
 
+def _write_synthetic_dataset(root, n_cases=N_CASES, n_tiles=L_TILES):
+    """The on-disk inputs of the reference's FeaturesGeneTextDataset (data_utils/datasets.py:144-285), synthetic:
+    feature bags ``{"features": [n, 1536], "coords": [n, 2]}``, the text-embedding dict ``{case_id: [4, 512]}``, the
+    clinical dict ``{case_id: [5]}``, a genomics csv with the 4 987 pathway genes, and the datalist of the json splits."""
+    import pandas as pd
+
+    genes = pd.read_csv(os.path.join(ref_shims.REFERENCE_ROOT, "dataset", "gene_pathway_processed_v2.csv"))["gene"].tolist()
+    g = torch.Generator().manual_seed(77)
+    datalist, text, clin, rows = [], {}, {}, []
+    for i in range(n_cases):
+        cid = f"TCGA-XX-{i:04d}"
+        s = synthetic.synthetic_slide(n_tiles, seed=700 + i, group_sizes=[1])
+        path = os.path.join(root, f"{cid}.pt")
+        torch.save({"features": s["x"][0].clone(), "coords": s["coords"][0].clone()}, path)
+        datalist.append({"case_id": cid, "case_submitter_id": cid, "features_path": path, "primary_class": i % 2})
+        text[cid] = torch.randn(4, 512, generator=g)
+        clin[cid] = torch.randn(5, generator=g)
+        rows.append([cid] + torch.randn(len(genes), generator=g).tolist())
+    csv = os.path.join(root, "genomics.csv")
+    pd.DataFrame(rows, columns=["case_id"] + genes).to_csv(csv, index=False)
+    torch.save(text, os.path.join(root, "text.pt"))
+    torch.save(clin, os.path.join(root, "clinical.pt"))
+    return datalist, csv
+
+
+def test_reference_dataset_and_loader_feed_the_b200_modules(tmp_path):
+    """Files -> the reference's FeaturesGeneTextDataset -> the reference's ``Trainer.get_train_iterator`` DataLoader ->
+    the reference's ``train_one_epoch`` -> B200 module classes (331 pathway groups of the real pathway table)."""
+    from functools import partial
+
+    tm = _import_reference_script("train_modaltune")
+    from data_utils.datasets import FeaturesGeneTextDataset
+    from models.aggregators import Aggregator as RefAggregator
+    from models.genomic_utils.define_gene_groups import pathway_gene_groups
+    from modaltune_b200.longvit_adapter import Aggregator as B200Aggregator
+    import pandas as pd
+
+    datalist, csv = _write_synthetic_dataset(str(tmp_path))
+    groups = pathway_gene_groups(gene_df=pd.read_csv(csv), group_definations=True)    # train_modaltune.py:93-95
+    assert len(groups) == 331
+    saved = dict(RefAggregator.subclasses)
+    try:
+        RefAggregator.subclasses.update(B200Aggregator.subclasses)
+        tr = _make_trainer(tm, "train_modaltune", groups)
+        tr.args.__dict__.update(labelset="primary_class", text_location=os.path.join(str(tmp_path), "text.pt"),
+                                genomics_csv_path=csv, clinical_location=os.path.join(str(tmp_path), "clinical.pt"),
+                                batch_size=1, drop_last=False, workers=0)
+        tr.train_transforms = None
+        tr.Dataset_Class = partial(FeaturesGeneTextDataset, case_wise=True, return_case=True,          # :98-103
+                                   gene_group_defination=groups, threshold=25000)
+        torch.manual_seed(0)
+        with cpu_kernels.installed():
+            tr.init_model_and_optimizer()
+            loader = tm.Trainer.get_train_iterator(tr, datalist)                                   # base_trainer.py:278-300
+            tr.model.eval()
+            tr.model.train = lambda mode=True: tr.model
+            w0 = tr.model.interactions[0].injector.gamma.detach().clone()
+            with config.using(mode="fp32"):
+                loss = tr.train_one_epoch(loader)[3]
+    finally:
+        RefAggregator.subclasses.clear()
+        RefAggregator.subclasses.update(saved)
+    assert len(loader) == N_CASES and loss == loss and 0.0 < loss < 100.0
+    assert not torch.equal(w0, tr.model.interactions[0].injector.gamma.detach())    # the optimizer stepped our parameters
+
+
 def _run_epoch(tm, script, swap: bool):
     from models.aggregators import Aggregator as RefAggregator
     from modaltune_b200.longvit_adapter import Aggregator as B200Aggregator
