@@ -18,6 +18,67 @@ __device__ __forceinline__ uint32_t pack_int(float a, float b) {
   return __byte_perm(ua, ub, 0x7632);
 }
 
+// mode 5: the softmax loop of the forward kernel as it is written there -- 128 live scores per thread, 4 chunks of 32,
+// non-volatile ex2, one dependent row-sum chain, 16 packed words per chunk consumed at once (stand-in for tcgen05.st)
+__device__ __forceinline__ float ex2nv(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t packnv(float a, float b) {
+  uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r;
+}
+template <int V>
+__global__ void __launch_bounds__(256) k5(int iters, const float* __restrict__ in, float scale, long long* cyc, uint32_t* sink) {
+  float sv[128];
+#pragma unroll
+  for (int i = 0; i < 128; ++i) sv[i] = in[(threadIdx.x * 128 + i) & 4095];
+  uint32_t acc = 0;
+  float l = 0.f, mb = 0.25f;
+  __syncthreads();
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+    float rs = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t pk[16];
+      if (V == 0 || V == 3) {        // the kernel's loop: exponential, sum and pack per pair
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2nv(fmaf(sv[c * 32 + i], scale, -mb));
+          const float p1 = ex2nv(fmaf(sv[c * 32 + i + 1], scale, -mb));
+          rs += p0 + p1;
+          pk[i >> 1] = packnv(p0, p1);
+          if (V == 3 && (i & 15) == 14) asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
+        }
+      } else {                       // two phases per chunk: 32 exponentials first, then sums and packs
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) p[i] = ex2nv(fmaf(sv[c * 32 + i], scale, -mb));
+        if (V == 2) asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
+        float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          r0 += p[i] + p[i + 1];
+          r1 += p[i + 2] + p[i + 3];
+          pk[i >> 1] = packnv(p[i], p[i + 1]);
+          pk[(i >> 1) + 1] = packnv(p[i + 2], p[i + 3]);
+        }
+        rs += r0 + r1;
+        if (V == 2) asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
+      }
+      uint32_t x = 0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) x ^= pk[q];
+      acc += x;
+    }
+    l += rs;
+    mb += 1e-3f;
+  }
+  const long long t1 = clock64();
+  __syncthreads();
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+  if (l == 12345.678f) sink[0] = acc;
+  if (acc == 0xdeadbeefu) sink[1] = 1;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(512) k(int iters, float seed, float scale, long long* cyc, uint32_t* sink) {
   float v[16];
@@ -87,6 +148,26 @@ int main() {
     const double elems = (double)iters * 16 * threads;
     printf("mode 4 with %d warp(s) per scheduler: %.2f elements/clk/SM (%.1f cycles per exponential and scheduler)\n", threads / 128,
            elems / c, c / (iters * 16.0 * (threads / 128)));
+  }
+  {
+    float* in; cudaMalloc(&in, 4096 * 4);
+    float h[4096]; for (int i = 0; i < 4096; ++i) h[i] = -3.f + 6.f * (float)((i * 2654435761u) >> 8 & 0xffff) / 65536.f;
+    cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
+    const char* vn[] = {"kernel-shaped (per pair)", "two-phase per 32-chunk", "two-phase + warp-sync fences", "per pair + fence every 16"};
+    for (int v = 0; v < 4; ++v)
+      for (int threads = 128; threads <= 256; threads *= 2) {
+        for (int rep = 0; rep < 2; ++rep) {
+          if (v == 0) k5<0><<<148, threads>>>(iters / 8, in, 0.2f, cyc, sink);
+          if (v == 1) k5<1><<<148, threads>>>(iters / 8, in, 0.2f, cyc, sink);
+          if (v == 2) k5<2><<<148, threads>>>(iters / 8, in, 0.2f, cyc, sink);
+          if (v == 3) k5<3><<<148, threads>>>(iters / 8, in, 0.2f, cyc, sink);
+          cudaDeviceSynchronize();
+        }
+        long long hc[148]; cudaMemcpy(hc, cyc, sizeof(hc), cudaMemcpyDeviceToHost);
+        double c = 0; for (int i = 0; i < 148; ++i) c += hc[i]; c /= 148;
+        printf("mode 5 %-30s %d warp(s)/scheduler: %5.1f cycles per exponential and scheduler, %5.0f cycles per 128-exponential row\n",
+               vn[v], threads / 128, c / ((iters / 8) * 128.0 * (threads / 128)), c / (iters / 8));
+      }
   }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
