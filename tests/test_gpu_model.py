@@ -46,8 +46,13 @@ def _self_attention_bwd(dy, saved, geom, cdt, impl):
     return ops._matmul_f32out(dqkv.to(cdt), W.w_qkv)
 
 
-@pytest.mark.parametrize("mode,t_out,t_grad", [("fp32", 1e-4, 1e-4), ("bf16", 3e-2, 5e-2)])
-def test_dilated_self_attention_golden(model, mode, t_out, t_grad):
+@pytest.mark.parametrize("mode,attn,t_out,t_grad", [("fp32", "simt", 1e-4, 1e-4), ("bf16", "simt", 3e-2, 5e-2),
+                                                    ("bf16", "auto", 3e-2, 5e-2)])
+def test_dilated_self_attention_golden(model, mode, attn, t_out, t_grad):
+    """bf16 / auto = the tcgen05 kernels bench.py runs (config.AUTO_IMPL) against the REFERENCE's fixture."""
+    with config.using(mode=mode, attn_impl=attn):
+        impl_f, impl_b = config.attn_impl("fwd"), config.attn_impl("bwd")
+    assert (impl_f, impl_b) == ((0, 0) if attn == "simt" or mode == "fp32" else (config.AUTO_IMPL["fwd"], config.AUTO_IMPL["bwd"]))
     gold = torch.load(os.path.join(helpers.GOLDEN, "dilated_attention.pt"))
     layer = model.encoder.layers[0]
     cdt = torch.float32 if mode == "fp32" else torch.bfloat16
@@ -57,28 +62,34 @@ def test_dilated_self_attention_golden(model, mode, t_out, t_grad):
         x = torch.randn(1, N, 768, generator=g, dtype=torch.float64)
         dy = torch.randn(1, N, 768, generator=g, dtype=torch.float64)
         geom = ops.Geometry.get(N, case["segment_lengths"], DILATED_RATIO)
-        y, saved = _self_attention(layer, x[0].float().to(DEV), geom, cdt, 0)
-        gx = _self_attention_bwd(dy[0].float().to(DEV), saved, geom, cdt, 0)
+        y, saved = _self_attention(layer, x[0].float().to(DEV), geom, cdt, impl_f)
+        gx = _self_attention_bwd(dy[0].float().to(DEV), saved, geom, cdt, impl_b)
         rows = case["rows"]
         assert helpers.relerr(y.float().cpu()[rows], case["y_rows"]) < t_out, name
         assert helpers.relerr(gx.float().cpu()[rows], case["gx_rows"]) < t_grad, name
         assert abs(float(y.float().norm()) - case["y_norm"]) < t_out * case["y_norm"], name
 
 
-@pytest.mark.parametrize("mode,t_out,t_grad", [("fp32", 1e-4, 1e-4), ("bf16", 2e-2, 5e-2)])
-def test_encoder_layer_golden(model, mode, t_out, t_grad):
-    gold = torch.load(os.path.join(helpers.GOLDEN, "encoder_layer.pt"))
+@pytest.mark.parametrize("fixture", ["encoder_layer.pt", "encoder_layer_10k.pt", "encoder_layer_32k.pt"])
+@pytest.mark.parametrize("mode,attn,t_out,t_grad", [("fp32", "simt", 1e-4, 1e-4), ("bf16", "simt", 2e-2, 5e-2),
+                                                    ("bf16", "auto", 2e-2, 5e-2)])
+def test_encoder_layer_golden(model, fixture, mode, attn, t_out, t_grad):
+    """One frozen encoder layer forward + dX against the REFERENCE's fixtures at N = 1 200 and at the bench geometries
+    N = 10 001 (config 2) and 32 769 (config 3); bf16 / auto is the tcgen05 path bench.py times."""
+    gold = torch.load(os.path.join(helpers.GOLDEN, fixture))
     N = gold["N"]
     g = torch.Generator().manual_seed(gold["seed"])
     x = torch.randn(1, N, 768, generator=g, dtype=torch.float64).float().to(DEV).requires_grad_(True)
     dy = torch.randn(1, N, 768, generator=g, dtype=torch.float64).float().to(DEV)
-    with config.using(mode=mode, attn_impl="simt"):
+    with config.using(mode=mode, attn_impl=attn):
         y, _ = model.encoder.layers[gold["layer"]](x, encoder_padding_mask=torch.zeros(1, N, dtype=torch.bool, device=DEV))
         (gx,) = torch.autograd.grad(y, x, dy)
     rows = gold["rows"]
     assert helpers.relerr(y[0].cpu()[rows], gold["y_rows"]) < t_out
     assert helpers.relerr(gx[0].cpu()[rows], gold["gx_rows"]) < t_grad
-    assert abs(float(gx.norm()) - gold["gx_norm"]) < t_grad * gold["gx_norm"]
+    assert abs(float(y.double().norm()) - gold["y_norm"]) < t_out * gold["y_norm"]
+    assert abs(float(gx.double().norm()) - gold["gx_norm"]) < t_grad * gold["gx_norm"]
+    assert _cos(gx[0].cpu()[rows], gold["gx_rows"]) > (0.999999 if mode == "fp32" else 0.9995)
 
 
 @pytest.mark.parametrize("mode,t", [("fp32", 1e-4), ("bf16", 5e-3)])
@@ -107,13 +118,13 @@ def test_injector_extractor_golden(model, mode, t):
         assert helpers.relerr(y[0].cpu(), gold["prompt_sa_y"]) < (1e-4 if mode == "fp32" else 2e-3)
 
 
-def _step(model, tag, mode):
+def _step(model, tag, mode, attn="simt"):
     gold = torch.load(os.path.join(helpers.GOLDEN, "training_step.pt"))[tag]
     slide = train_step.slide_to_device(
         synthetic.synthetic_slide(gold["L"], seed=gold["seed"], group_sizes=gold["group_sizes"]), DEV)
     proj = helpers.build_projector(0, DEV)
     model.zero_grad()
-    with config.using(mode=mode, attn_impl="simt"):
+    with config.using(mode=mode, attn_impl=attn):
         loss, logits = train_step.forward_backward(model, proj, slide)
     grads = {k: p.grad for k, p in model.named_parameters() if p.requires_grad}
     return gold, float(loss), logits.float().cpu(), grads
@@ -140,9 +151,10 @@ def test_training_step_fp32_matches_reference(model, tag):
         assert float((got["vals"].double() - want["vals"].double()).abs().max()) <= 2e-2 * float(want["vals"].abs().max()) + 2e-5 * gmax, k
 
 
+@pytest.mark.parametrize("attn", ["simt", "auto"])
 @pytest.mark.parametrize("tag", ["L300_float32", "L1100_float32"])
-def test_training_step_bf16_within_tolerance(model, tag):
-    gold, loss, logits, grads = _step(model, tag, "bf16")
+def test_training_step_bf16_within_tolerance(model, tag, attn):
+    gold, loss, logits, grads = _step(model, tag, "bf16", attn)
     assert helpers.relerr(logits, gold["logits"]) < 2e-2
     gmax = max(v["norm"] for v in gold["grads"].values())
     for k, want in gold["grads"].items():
@@ -155,36 +167,82 @@ def test_training_step_bf16_within_tolerance(model, tag):
         assert abs(got["norm"] - want["norm"]) < 0.05 * want["norm"], k
 
 
-def test_full_gradient_cosine_vs_oracle_bf16_and_fp32(model):
-    """Per-parameter cosine >= 0.999 over FULL gradient tensors: the oracle (CPU, fp32) on the same weights/slide."""
+def _load_exceptions():
+    """Named exceptions to the per-parameter cosine >= 0.999 bar in bf16 mode, with the value measured on the B200
+    (``tools/diag_grad_cosine.py`` writes the candidates).  Everything not listed must reach 0.999."""
+    import json
+    with open(os.path.join(helpers.GOLDEN, "bf16_grad_cosine_exceptions.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("pathways", ["toy10", "full331"])
+def test_full_gradient_cosine_vs_oracle_bf16_and_fp32(model, pathways):
+    """Per-parameter cosine >= 0.999 over FULL gradient tensors of every non-dead trainable parameter: the oracle (CPU,
+    fp32) on the same weights / slide against fp32 mode and bf16 mode, the latter on BOTH attention paths (SIMT and the
+    default tcgen05 kernels).  ``full331`` = the 331-pathway model bench.py runs."""
     L = 520
-    slide = synthetic.synthetic_slide(L, seed=77, group_sizes=helpers.SMALL_GROUPS)
-    sd = {k: v.detach().cpu().clone().requires_grad_(v.requires_grad) for k, v in model.named_parameters()}
+    groups = helpers.SMALL_GROUPS if pathways == "toy10" else None
+    m = model if pathways == "toy10" else helpers.build_model(None, device=DEV)
+    slide = synthetic.synthetic_slide(L, seed=77, group_sizes=groups)
+    sd = {k: v.detach().cpu().clone().requires_grad_(v.requires_grad) for k, v in m.named_parameters()}
     proj_sd = synthetic.seeded_projector_state(0)
-    genes = [slide["genes"][i] for i in range(len(helpers.SMALL_GROUPS))]
+    genes = [slide["genes"][i] for i in range(len(slide["genes"]))]
     loss_o, logits_o = O.training_step(sd, proj_sd, slide["x"][0], slide["coords"][0], genes, slide["clinical"],
                                        slide["text"])
     loss_o.backward()
     gmax = max(float(v.grad.norm()) for v in sd.values() if v.grad is not None)
     proj = helpers.build_projector(0, DEV)
     dslide = train_step.slide_to_device(slide, DEV)
-    keys = [k for k, p in model.named_parameters() if p.requires_grad and float(sd[k].grad.norm()) >= 1e-4 * gmax]
-    for mode, t_logit in (("fp32", 1e-4), ("bf16", 2e-2)):
-        model.zero_grad()
-        with config.using(mode=mode, attn_impl="simt"):
-            loss, logits = train_step.forward_backward(model, proj, dslide)
-        assert helpers.relerr(logits.float().cpu(), logits_o.detach()) < t_logit, mode
-        grads = dict(model.named_parameters())
+    # dead = structurally zero gradients (a bias that the next LayerNorm removes): rounding noise on both sides
+    keys = [k for k, p in m.named_parameters() if p.requires_grad and float(sd[k].grad.norm()) >= 1e-4 * gmax]
+    allowed = _load_exceptions().get(pathways, {})
+    for mode, attn, t_logit in (("fp32", "simt", 1e-4), ("bf16", "simt", 2e-2), ("bf16", "auto", 2e-2)):
+        m.zero_grad()
+        with config.using(mode=mode, attn_impl=attn):
+            loss, logits = train_step.forward_backward(m, proj, dslide)
+        assert helpers.relerr(logits.float().cpu(), logits_o.detach()) < t_logit, (mode, attn)
+        assert abs(float(loss) - float(loss_o)) < (1e-3 if mode == "fp32" else 5e-2) * abs(float(loss_o)), (mode, attn)
+        grads = dict(m.named_parameters())
         cs = {k: _cos(grads[k].grad, sd[k].grad) for k in keys}
         glob = _cos(torch.cat([grads[k].grad.flatten().cpu() for k in keys]), torch.cat([sd[k].grad.flatten() for k in keys]))
         if mode == "fp32":
             assert min(cs.values()) > 0.9999, min(cs.items(), key=lambda kv: kv[1])
-        else:
-            # bf16 operands: >= 0.999 on (nearly) every tensor; the stragglers are ReLU-FFN / LayerNorm weights of the
-            # modal-token branches whose gradients flip with single pre-activation signs (DESIGN.md "numerics")
-            assert glob > 0.9999, glob
-            assert min(cs.values()) > 0.995, min(cs.items(), key=lambda kv: kv[1])
-            assert sum(c > 0.999 for c in cs.values()) >= 0.98 * len(cs), sorted(cs.values())[:8]
+            continue
+        assert glob > 0.9999, (attn, glob)
+        low = {k: c for k, c in cs.items() if c < 0.999}
+        unlisted = {k: round(c, 5) for k, c in low.items() if k not in allowed}
+        assert not unlisted, (attn, "below 0.999 and not a named exception", unlisted)
+        for k, c in low.items():
+            assert c > allowed[k] - 2e-3, (attn, k, c, allowed[k])     # a named exception may not get worse either
+        assert len(low) <= 0.02 * len(cs) + 1, (attn, len(low), len(cs))
+
+
+@pytest.mark.parametrize("mode,attn,t_logit", [("fp32", "simt", 1e-4), ("bf16", "auto", 2e-2)])
+def test_training_step_331_pathways_matches_reference(mode, attn, t_logit):
+    """The 331-pathway model of the bench (not the 10 toy pathways of the small fixtures) against the REFERENCE's
+    own training step (tests/golden/make_golden_r2.py): logits, loss, and every live gradient tensor."""
+    gold = torch.load(os.path.join(helpers.GOLDEN, "training_step_331.pt"))
+    m = helpers.build_model(None, device=DEV)
+    proj = helpers.build_projector(0, DEV)
+    slide = train_step.slide_to_device(synthetic.synthetic_slide(gold["L"], seed=gold["seed"]), DEV)
+    m.zero_grad()
+    with config.using(mode=mode, attn_impl=attn):
+        loss, logits = train_step.forward_backward(m, proj, slide)
+    assert helpers.relerr(logits.float().cpu(), gold["logits"]) < t_logit
+    assert abs(float(loss) - gold["loss"]) < (1e-3 if mode == "fp32" else 5e-2) * abs(gold["loss"])
+    grads = {k: p.grad for k, p in m.named_parameters() if p.requires_grad}
+    assert set(grads) == set(gold["grads"])
+    gmax = max(v["norm"] for v in gold["grads"].values())
+    allowed = _load_exceptions().get("full331", {})
+    for k, want in gold["grads"].items():
+        if want["norm"] < 1e-3 * gmax:
+            continue
+        got = helpers.grad_summary(k, grads[k])
+        tn = 2e-3 if mode == "fp32" else 5e-2
+        assert abs(got["norm"] - want["norm"]) <= tn * want["norm"] + 2e-5 * gmax, k
+        # the fixture stores 64 sampled entries + 4 random projections per tensor, not the tensor: a coarse cosine
+        c = _cos(torch.cat([got["vals"], got["proj"]]), torch.cat([want["vals"], want["proj"]]))
+        assert c > (0.998 if mode == "fp32" else (0.99 if k not in allowed else 0.97)), (k, c)
 
 
 def test_graphed_step_equals_eager_step(model):

@@ -100,3 +100,42 @@ def test_training_step_fixture(sd):
         got = helpers.grad_summary(k, sdg[k].grad)
         assert abs(got["norm"] - want["norm"]) < 1e-3 * want["norm"], k
         assert helpers.relerr(got["proj"], want["proj"]) < 5e-3, k
+
+
+def test_encoder_layer_fixture_bench_size():
+    """Round-2 fixture from the reference at N = 10 001 tokens (BASELINE config 2, fp32): oracle forward + dX."""
+    gold = torch.load(os.path.join(helpers.GOLDEN, "encoder_layer_10k.pt"))
+    l, N = gold["layer"], gold["N"]
+    sd = {k: v.detach() for k, v in helpers.build_model(helpers.SMALL_GROUPS).state_dict().items()
+          if k.startswith(f"encoder.layers.{l}.")}
+    g = torch.Generator().manual_seed(gold["seed"])
+    x = torch.randn(1, N, 768, generator=g, dtype=torch.float32)[0].requires_grad_(True)
+    dy = torch.randn(1, N, 768, generator=g, dtype=torch.float32)[0]
+    y = O.encoder_layer(sd, l, x, O.optimal_segment_lengths(), O.DILATED_RATIO)
+    (gx,) = torch.autograd.grad(y, x, dy)
+    assert gold["gx_source"] == "reference autograd"
+    assert helpers.relerr(y[gold["rows"]], gold["y_rows"]) < 1e-5
+    assert helpers.relerr(gx[gold["rows"]], gold["gx_rows"]) < 1e-5
+    assert abs(float(gx.double().norm()) - gold["gx_norm"]) < 1e-5 * gold["gx_norm"]
+
+
+def test_training_step_331_pathways_fixture():
+    """Round-2 fixture: the reference's full training step with the real 331-pathway gene encoder."""
+    gold = torch.load(os.path.join(helpers.GOLDEN, "training_step_331.pt"))
+    slide = synthetic.synthetic_slide(gold["L"], seed=gold["seed"])
+    model = helpers.build_model(None)
+    sdg = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in model.named_parameters()}
+    genes = [slide["genes"][i] for i in range(len(slide["genes"]))]
+    loss, logits = O.training_step(sdg, synthetic.seeded_projector_state(0), slide["x"][0], slide["coords"][0], genes,
+                                   slide["clinical"], slide["text"])
+    loss.backward()
+    assert len(gold["grads"]) == 1550
+    assert helpers.relerr(logits.detach(), gold["logits"]) < 1e-5
+    assert abs(float(loss) - gold["loss"]) < 1e-3 * abs(gold["loss"])
+    gmax = max(v["norm"] for v in gold["grads"].values())
+    for k, want in gold["grads"].items():
+        if want["norm"] < 1e-4 * gmax:
+            continue
+        got = helpers.grad_summary(k, sdg[k].grad)
+        assert abs(got["norm"] - want["norm"]) < 1e-3 * want["norm"], k
+        assert helpers.relerr(got["proj"], want["proj"]) < 5e-3, k
