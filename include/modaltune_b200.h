@@ -65,7 +65,10 @@ int mt_device_is_sm100(void);
  * replaces: PatchEmbed.forward bias add (slide_encoder.py:52-56), `x + pos_embed[:, pos]`, cls concat
  * (longvit_adapter.py:232-246) and coords_to_pos (slide_encoder.py:198-211).
  * proj [L, E] = feats @ W^T (GEMM result, dtype `proj_dtype`), bias [E] f32, coords [L,2] f32 (pixels),
- * table [ngrids, E/2] f32 = 1-D sincos factor, cls [E] f32  ->  x [L+1, E] f32 (row 0 = cls). */
+ * table [ngrids, E/2] f32 = 1-D sincos factor, cls [E] f32  ->  x [L+1, E] f32 (row 0 = cls).
+ * Index semantics are the reference's: pos = floor(c0 / tile_size) * ngrids + floor(c1 / tile_size) + 1 into the flat
+ * table (a column index >= ngrids wraps into the next grid row, pos == 0 is the all-zero cls row); an index outside
+ * [0, ngrids^2] -- an IndexError / device assert in the reference -- makes the kernel trap (CUDA error on the stream). */
 int mt_embed_assemble(const void* proj, int proj_dtype, const float* bias, const float* coords, const float* table,
                       const float* cls, float* x, int64_t n_tiles, int64_t embed, int64_t ngrids, float tile_size,
                       void* stream);
@@ -111,11 +114,9 @@ int mt_gelu_ln_bwd(const void* dy, int dy_dtype, const void* h, int h_dtype, con
  * o_br : compact per-branch outputs, branch b at element offset sum_{b'<b} N*E/r_b', layout [N][E/r_b]: row p holds the
  *        16/r_b heads that own position p (heads (p%r)*16/r ..), each head_dim wide.           (dtype)
  * lse_br: same compaction, [N][H/r_b] float, natural-log LSE including the zero-slot keys.
- * impl: 0 = SIMT fp32 math (any dtype), >= 1 = tcgen05/TMA (bf16 only).  Forward: 1 = O folded in registers per key
- * tile, 2 = O accumulated in TMEM with a lazily raised row maximum (fastest), 3 = 2 with two threads per query row
- * (eight softmax warps per CTA).  Backward: 1 = operands through shared
- * memory, 2 = transposed formulation with its A operands in TMEM, 3 = 2 with the row statistics folded into the MMAs
- * and TMA reduce-adds for the gradients (fastest). */
+ * impl: 0 = SIMT fp32 math (any dtype; also the on-device cross-check of the tensor-core kernels), >= 1 = tcgen05 / TMA /
+ * TMEM kernels (bf16 only).  A shared-memory window that is not 1024-byte aligned (never expected) makes the tcgen05
+ * kernels trap: the failure surfaces as a CUDA error on the stream, never as silently unwritten outputs. */
 int mt_dilated_attn_fwd(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc, int dtype,
                         void* o_br, float* lse_br, int impl, void* stream);
 

@@ -51,14 +51,15 @@ def compute_dtype() -> torch.dtype:
     return torch.bfloat16 if _state["mode"] == "bf16" else torch.float32
 
 
-# what "auto" resolves to in bf16 mode, per direction (flipped to 1 as the tcgen05 kernels are validated on B200)
-AUTO_IMPL = {"fwd": 2, "bwd": 3}
+# what "auto" resolves to in bf16 mode, per direction: the ``impl`` selector of mt_dilated_attn_{fwd,bwd}
+# (0 = SIMT fp32-math kernels, 1 = the tcgen05 / TMA / TMEM kernels)
+AUTO_IMPL = {"fwd": 1, "bwd": 1}
 
 
 def attn_impl(direction: str = "fwd") -> int:
-    """The ``impl`` argument of mt_dilated_attn_{fwd,bwd}: 0 = SIMT, 1 = first tcgen05 version; forward 2 = O accumulated
-    in TMEM with a lazily raised row maximum (default), 3 = the same with two threads per query row; backward 2 = transposed formulation with its A operands in TMEM,
-    3 = the same with the per-query statistics folded into the MMAs and TMA reduce-adds for dQ / dK / dV (default)."""
+    """The ``impl`` argument of mt_dilated_attn_{fwd,bwd}: 0 = SIMT, 1 = tcgen05 (forward: O accumulated in TMEM with a
+    lazily raised row maximum; backward: transposed formulation, per-query statistics folded into the MMAs, TMA
+    reduce-adds for dQ / dK / dV)."""
     impl = _state["attn_impl"]
     if impl == "simt" or _state["mode"] == "fp32":
         if impl == "sm100":

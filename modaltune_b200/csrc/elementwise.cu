@@ -323,12 +323,21 @@ __global__ void __launch_bounds__(256) embed_assemble_kernel(const TP* __restric
       float p[8], b[8], e[8];
       load8(proj + i * embed + c, p);
       load8(bias + c, b);
-      // pos = floor(c0/256) * G + floor(c1/256) + 1 ;  pos_embed[pos] = [T[j] | T[i]]
-      int gi = (int)floorf(coords[2 * i] * inv_tile), gj = (int)floorf(coords[2 * i + 1] * inv_tile);
-      gi = min(max(gi, 0), ngrids - 1);
-      gj = min(max(gj, 0), ngrids - 1);
-      if (c < half) load8(table + (int64_t)gj * half + c, e);
-      else load8(table + (int64_t)gi * half + (c - half), e);
+      // pos = floor(c0/256) * G + floor(c1/256) + 1 (slide_encoder.py:198-211), then pos_embed[pos] = [T[j'] | T[i']]
+      // with (i', j') = divmod(pos - 1, G): a column index >= G wraps into the next grid row exactly as the reference's
+      // flat table does, pos == 0 is the all-zero cls row.  An index outside the table is an error in the reference
+      // (device-side index assert); here the kernel traps instead of clamping to a plausible but different embedding.
+      const long long pos = (long long)floorf(coords[2 * i] * inv_tile) * ngrids +
+                            (long long)floorf(coords[2 * i + 1] * inv_tile) + 1;
+      if (pos < 0 || pos > (long long)ngrids * ngrids) __trap();
+      if (pos == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = 0.f;
+      } else {
+        const int gi = (int)((pos - 1) / ngrids), gj = (int)((pos - 1) % ngrids);
+        if (c < half) load8(table + (int64_t)gj * half + c, e);
+        else load8(table + (int64_t)gi * half + (c - half), e);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = p[j] + b[j] + e[j];
     }

@@ -232,8 +232,9 @@ class LongNetViT(nn.Module):
                 else:
                     with ops._tf32():
                         proj = torch.matmul(x[b].float(), wq.t())
-                outs.append(ops.embed_assemble(proj, bias, coords[b].float().contiguous(), self.pos_table, cls,
-                                               float(self.tile_size)))
+                # the reference divides by a literal 256.0 whatever ``tile_size`` says (slide_encoder.py:198-211);
+                # ``coords_to_pos`` above and the kernel use the same divisor
+                outs.append(ops.embed_assemble(proj, bias, coords[b].float().contiguous(), self.pos_table, cls, 256.0))
         return outs[0].unsqueeze(0) if B == 1 else torch.stack(outs, 0)
 
     def forward(self, x, coords, all_layer_embed=False):

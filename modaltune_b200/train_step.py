@@ -159,6 +159,16 @@ class GraphedStep:
         dev = next(model.parameters()).device
         self.static = {k: v.to(dev).clone() for k, v in packed_example.items()}
         self._copy_stream, self._staging, self._staged_for = None, None, None
+        self._warmup = warmup
+        self._capture()
+
+    def _frozen_signature(self):
+        """Identity + version of every frozen parameter the captured kernels read through derived copies
+        (``ops.FrozenLayerWeights``): a ``load_state_dict`` / in-place edit after capture changes it."""
+        return tuple((p.data_ptr(), p._version) for p in self.model.parameters() if not p.requires_grad)
+
+    def _capture(self):
+        model, projector, flat, warmup = self.model, self.projector, self.flat, self._warmup
         slide = unpack_slide(self.static, self.sizes)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -173,6 +183,9 @@ class GraphedStep:
         with torch.cuda.graph(self.graph):
             self.loss, self.logits = forward_backward(model, projector, slide)
             self.grads = flat.gather()
+        # views of the captured flat buffer, handed back to ``p.grad`` after every replay
+        self._grad_views = [p.grad for p in flat.params]
+        self._signature = self._frozen_signature()
 
     def load(self, packed: Dict):
         """Copy one packed slide (pinned host or device tensors of the captured shapes) into the static inputs.  A slide
@@ -205,6 +218,9 @@ class GraphedStep:
         self._staged_for = packed
 
     def __call__(self, packed: Optional[Dict] = None):
+        if self._frozen_signature() != self._signature:
+            # the graph holds pointers to bf16 copies derived from the old frozen weights: capture again
+            self._capture()
         if packed is not None:
             self.load(packed)
         self.graph.replay()
@@ -213,4 +229,8 @@ class GraphedStep:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
             self.grads.div_(dist.get_world_size())
+        # ``optimizer.zero_grad()`` (set_to_none, the reference's loop) or ``flat.zero()`` drop ``p.grad``; the replay
+        # has rewritten the flat buffer, so every parameter gets its view back and ``optimizer.step()`` sees it
+        for p, g in zip(self.flat.params, self._grad_views):
+            p.grad = g
         return self.loss, self.logits

@@ -119,6 +119,27 @@ def test_embed_assemble_and_cast_and_gated_residual():
         assert rel(da, da_c) < 1e-6 and rel(db, db_c) < tol(dt) and rel(dg, dg_c) < 1e-4
 
 
+def test_embed_assemble_follows_the_reference_flat_index():
+    """pos = floor(c0/256)*G + floor(c1/256) + 1 into the flat [1 + G*G, E] table (slide_encoder.py:198-211): a column
+    index >= G wraps into the next grid row exactly as the reference's gather does, and pos == 0 is the zero cls row."""
+    from modaltune_b200.slide_encoder import sincos_factor
+    G = 1000
+    table = sincos_factor(G, 768)
+    g = torch.Generator().manual_seed(9)
+    cells = torch.tensor([[3, 1005], [0, 0], [998, 999], [7, 2500], [0, -1]], dtype=torch.float32)
+    coords = cells * 256.0 + 17.0
+    L = coords.shape[0]
+    proj, bias, cls = torch.randn(L, 768, generator=g), torch.randn(768, generator=g), torch.randn(768, generator=g)
+    pos = (torch.floor(coords[:, 0] / 256.0) * G + torch.floor(coords[:, 1] / 256.0)).long() + 1
+    flat_rows = torch.zeros(L, 768)
+    for n, p_ in enumerate(pos.tolist()):
+        if p_ > 0:   # pos_embed[1 + i*G + j] = [T[j] | T[i]]
+            flat_rows[n] = torch.cat([table[(p_ - 1) % G], table[(p_ - 1) // G]])
+    want = torch.cat([cls[None], proj + bias + flat_rows], 0)
+    got = ops.embed_assemble(proj.to(DEV), bias.to(DEV), coords.to(DEV), table.to(DEV), cls.to(DEV))
+    assert rel(got, want) < 1e-6
+
+
 @pytest.mark.parametrize("lq,lk", [(700, 66), (66, 700), (66, 10000), (5000, 13), (1, 1), (129, 65)])
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_cross_attention_core(lq, lk, dt):
@@ -202,6 +223,7 @@ def test_dilated_attention_linearity_in_v_at_full_size():
 # sizes at which the tcgen05 kernels are held against the ORACLE itself (not only against the SIMT kernels): every small
 # geometry plus the bench geometries of BASELINE configs 2 and 3 (the oracle core needs 2 - 25 s of host time there)
 ORACLE_SIZES = {n for n, _ in GEOMS} | {5793, 10001, 32769}
+FWD_IMPLS = (1,)        # tcgen05 variants of mt_dilated_attn_fwd (0 = SIMT is the on-device cross-check)
 SM100_GEOMS = GEOMS + [(5793, None), (10001, None), (300, [128, 256, 512, 1024, 2048]),
                        # whole-tile padding skip: last segments with 1 / 128 / 129 real slots, real counts that are
                        # exact multiples of the 128-slot tile, tails of several all-padding tiles in every branch
@@ -219,8 +241,7 @@ def test_dilated_attention_tcgen05_forward(N, sl):
     qkv = _qkv(N, geom.n_alloc, g, torch.bfloat16, 1.5).to(DEV)
     o_s, l_s = ops.dilated_attn_fwd(geom, qkv, 0)
     oc = None
-    # 1: O folded in registers every tile, 2: O accumulated in TMEM with a lazily raised maximum, 3: 2 with two threads per row
-    for impl in (1, 2, 3):
+    for impl in FWD_IMPLS:
         o_t, l_t = ops.dilated_attn_fwd(geom, qkv, impl)
         torch.cuda.synchronize()
         assert rel(l_t, l_s) < 2e-3, (impl, rel(l_t, l_s))       # P is rounded to bf16 before P V; lse itself is fp32
@@ -246,7 +267,7 @@ def test_dilated_attention_tcgen05_forward_rising_maximum(N):
     qkv[:N, 768:1536] *= sign                                         # and alternating, so maxima move both ways
     qkv = qkv.to(torch.bfloat16).to(DEV)
     o_s, l_s = ops.dilated_attn_fwd(geom, qkv, 0)
-    for impl in (1, 2, 3):
+    for impl in FWD_IMPLS:
         o_t, l_t = ops.dilated_attn_fwd(geom, qkv, impl)
         torch.cuda.synchronize()
         assert torch.isfinite(o_t.float()).all() and torch.isfinite(l_t).all(), impl
@@ -254,7 +275,7 @@ def test_dilated_attention_tcgen05_forward_rising_maximum(N):
         assert rel(o_t, o_s) < 3e-2, (impl, rel(o_t, o_s))
 
 
-BWD_IMPLS = (1, 2, 3)   # 1: operands through smem, 2: transposed with operands in TMEM, 3: statistics on the MMAs
+BWD_IMPLS = (1,)
 
 
 @pytest.mark.parametrize("N,sl", SM100_GEOMS)

@@ -269,6 +269,55 @@ def test_graphed_step_equals_eager_step(model):
     assert helpers.relerr(g_graph, g_eager) < 1e-3
 
 
+def test_graphed_step_drives_an_optimizer_across_replays():
+    """``optimizer.zero_grad()`` (set_to_none, the reference's loop: train_modaltune.py:236-238) between replays must not
+    detach the parameters from the captured flat gradient buffer: two graph steps + AdamW equal two eager steps + AdamW,
+    and a ``load_state_dict`` of the frozen encoder after capture re-captures instead of reading freed weight copies."""
+    import copy
+    proj = helpers.build_projector(0, DEV)
+    slides = [synthetic.synthetic_slide(600, seed=s, group_sizes=helpers.SMALL_GROUPS) for s in (51, 52)]
+    packed = [train_step.pack_host_slide(s)[0] for s in slides]
+    sizes = train_step.pack_host_slide(slides[0])[1]
+    m_g = helpers.build_model(helpers.SMALL_GROUPS, device=DEV)
+    m_e = copy.deepcopy(m_g)
+    with config.using(mode="bf16"):
+        flat = train_step.FlatGradAllReduce([p for p in m_g.parameters() if p.requires_grad])
+        opt_g = torch.optim.AdamW([p for p in m_g.parameters() if p.requires_grad], lr=1e-3)
+        graphed = train_step.GraphedStep(m_g, proj, packed[0], sizes, flat)
+        opt_e = torch.optim.AdamW([p for p in m_e.parameters() if p.requires_grad], lr=1e-3)
+        for k in (0, 1):
+            opt_g.zero_grad()                       # set_to_none=True: p.grad is None until the replay hands it back
+            assert all(p.grad is None for p in flat.params)
+            graphed(packed[k])
+            assert all(p.grad is not None for p in flat.params)
+            opt_g.step()
+            opt_e.zero_grad()
+            dev_slide = train_step.unpack_slide({n: v.to(DEV) for n, v in packed[k].items()}, sizes)
+            train_step.forward_backward(m_e, proj, dev_slide)
+            opt_e.step()
+        moved = 0.0
+        ref = dict(helpers.build_model(helpers.SMALL_GROUPS, device=DEV).named_parameters())
+        for (n, a), (_, b) in zip(m_g.named_parameters(), m_e.named_parameters()):
+            if not a.requires_grad:
+                continue
+            moved = max(moved, float((a - ref[n]).abs().max()))
+            # Adam normalises the step: a gradient entry at the noise floor may move by up to 2 * lr either way
+            assert float((a - b).abs().max()) <= 2.5e-3, n
+            assert _cos(a - ref[n], b - ref[n]) > 0.98 or float((a - ref[n]).norm()) < 1e-6, n
+        assert moved > 5e-4                          # the optimizer really stepped on the graph's gradients
+        # frozen weights replaced after capture: the next call must re-capture (new derived bf16 copies), not crash / go stale
+        sd = {k: v.clone() for k, v in m_g.state_dict().items()}
+        sd["encoder.layers.0.ffn.fc1.weight"] = sd["encoder.layers.0.ffn.fc1.weight"] * 1.5
+        m_g.load_state_dict(sd)
+        g_before = graphed.graph
+        loss2, logits2 = graphed(packed[0])
+        assert graphed.graph is not g_before
+        m_g.zero_grad()
+        dev_slide = train_step.unpack_slide({n: v.to(DEV) for n, v in packed[0].items()}, sizes)
+        loss_e, logits_e = train_step.forward_backward(m_g, proj, dev_slide)
+        assert helpers.relerr(logits2, logits_e) < 1e-5
+
+
 def test_graphed_step_prefetch_double_buffering(model):
     """``GraphedStep.prefetch`` (H2D copy of the next slide on a copy stream while a step runs) feeds the same inputs
     as the direct host copy: slides alternate A, B, A through the staging buffers and reproduce the direct results."""
