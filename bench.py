@@ -44,19 +44,30 @@ def parse():
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--attn", default="auto", choices=["auto", "simt", "sm100"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=200.0, help="seconds of oracle steps the reference arm may time")
+    ap.add_argument("--no-extras", action="store_true", help="skip the comparator / 32k / train-mode sub-records")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
-METRIC = "slides/s fwd+bwd, GigaPath+ModalTune 10k tiles"
 UNIT = "slides/s"
+
+
+def metric_name(tiles: int) -> str:
+    return f"slides/s fwd+bwd, GigaPath+ModalTune {tiles // 1000}k tiles" if tiles % 1000 == 0 else \
+        f"slides/s fwd+bwd, GigaPath+ModalTune {tiles} tiles"
+
+
+def baseline_config_name(tiles: int) -> str:
+    return {1024: "BASELINE.json configs[0]", 10000: "BASELINE.json configs[1]",
+            32768: "BASELINE.json configs[2] slide size"}.get(tiles, "custom tile count (not a BASELINE.json config)")
 
 
 def workload_config(args, world):
     return {
         "workload": f"ModalTune-GigaPath (LongNet 12L/768d/16h dilated attention + Modal Adapter), synthetic "
                     f"{args.tiles}-tile slides + 331 pathway tokens + clinical + text-task embeddings, 3 task passes "
-                    f"fwd + KL-distillation loss + bwd per slide (BASELINE.json configs[1])",
+                    f"fwd + KL-distillation loss + bwd per slide ({baseline_config_name(args.tiles)})",
         "tiles": args.tiles, "tokens": args.tiles + 1, "modal_tokens": 66, "task_passes": 3,
         "slides_per_step_per_gpu": 1, "parallelism": f"slide-sharded dp{world}",
         "l2": "working set per step (several GB of saved activations) exceeds the 126 MB L2; no explicit flush",
@@ -64,67 +75,123 @@ def workload_config(args, world):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port, one encoder layer fwd+bwd at the bench token count, scaled to a slide step
+# CPU arm: COMPLETE training steps of the oracle port (3 task passes forward + KL loss + backward, 331 pathways)
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_layer_sample(n_tokens: int, reps: int = 1):
-    """Seconds for one frozen-encoder-layer forward+backward (dX) of the oracle at ``n_tokens`` tokens, fp32."""
-    from modaltune_b200 import synthetic
-    from oracle import modaltune_oracle as O
+class CpuStep:
+    """One slide step of the reference's CPU arithmetic: ``oracle.training_step`` + backward on all host threads, fp32,
+    same seeded weights / synthetic slide generator as the GPU arm.  The reference itself is pure Python and does not
+    travel to the GPU box (and has no CPU attention of its own, flash_attention.py:143-146), so the arm is the oracle
+    port (``kind: "port"``), pinned to the reference by tests/golden."""
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    shapes = {"self_attn.q_proj": (768, 768), "self_attn.k_proj": (768, 768), "self_attn.v_proj": (768, 768),
-              "self_attn.out_proj": (768, 768), "ffn.fc1": (3072, 768), "ffn.fc2": (768, 3072)}
-    sd = {}
-    for k, shp in shapes.items():
-        sd[f"encoder.layers.0.{k}.weight"] = torch.empty(shp)
-        sd[f"encoder.layers.0.{k}.bias"] = torch.empty(shp[0])
-    for k, n in (("self_attn.inner_attn_ln", 768), ("self_attn_layer_norm", 768), ("final_layer_norm", 768),
-                 ("ffn.ffn_layernorm", 3072)):
-        sd[f"encoder.layers.0.{k}.weight"] = torch.empty(n)
-        sd[f"encoder.layers.0.{k}.bias"] = torch.empty(n)
-    synthetic.seeded_init_(sd.items(), seed=0)
-    g = torch.Generator().manual_seed(0)
-    seg = O.optimal_segment_lengths()
-    times = []
-    for _ in range(reps):
-        x = torch.randn(n_tokens, 768, generator=g).requires_grad_(True)
-        dy = torch.randn(n_tokens, 768, generator=g)
+    def __init__(self, tiles: int):
+        from modaltune_b200 import factory, synthetic
+        from oracle import modaltune_oracle as O
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.O, self.tiles = O, tiles
+        # above ~2k tiles the dense attention probabilities of 36 layer passes (5 GB per layer at 10k tiles) cannot
+        # stay alive for the backward on any host: every encoder layer is recomputed in the backward, the reference's
+        # own ``checkpoint_activations`` option (TS/architecture/encoder.py:317-319).  Same arithmetic, ~1.3x the time.
+        self.checkpoint = tiles > 2048
+        model = factory.build_model(None)
+        self.sd = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in model.named_parameters()}
+        self.proj_sd = synthetic.seeded_projector_state(0)
+        self.table = O.sincos_table()
+        self.slides = [synthetic.synthetic_slide(tiles, seed=1000 + i) for i in range(2)]
+        # untimed one-off costs (thread pool, allocator, autograd / MKL first touches: ~15 s on the first call) are paid
+        # on a tiny 256-tile step, so that even a single timed step is a warm measurement
+        tiny = synthetic.synthetic_slide(256, seed=999)
+        self._run(tiny)
+
+    def _run(self, s):
+        genes = [s["genes"][j] for j in range(len(s["genes"]))]
+        for v in self.sd.values():
+            v.grad = None
+        loss, _ = self.O.training_step(self.sd, self.proj_sd, s["x"][0], s["coords"][0], genes, s["clinical"], s["text"],
+                                       table=self.table, checkpoint_layers=self.checkpoint)
+        loss.backward()
+
+    def __call__(self, i: int = 0) -> float:
         t0 = time.perf_counter()
-        y = O.encoder_layer(sd, 0, x, seg, O.DILATED_RATIO)
-        torch.autograd.grad(y, x, dy)
-        times.append(time.perf_counter() - t0)
-    return sorted(times)[len(times) // 2]
+        self._run(self.slides[i % len(self.slides)])
+        return time.perf_counter() - t0
 
 
-def cpu_baseline(n_tokens: int):
-    t = cpu_layer_sample(n_tokens, reps=1)
-    return {"value": 1.0 / (36.0 * t), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": f"oracle (CPU restatement of the reference, fp32, torch {torch.get_num_threads()} threads): one "
-                      f"LongNet encoder layer forward+backward at {n_tokens} tokens = {t:.2f} s, scaled by the 36 layer "
-                      f"passes of a slide step (adapter cross-attention and embedding, ~3% of the FLOPs, excluded)"}
+CPU_ARM_CACHE = os.path.join(os.environ.get("TMPDIR", "/tmp"), "modaltune_b200_cpu_reference_arm.json")
+
+
+def cpu_baseline(tiles: int):
+    """``cpu_baseline`` of the GPU arm.  A complete oracle step at 10k tiles takes minutes of host time, too long for the
+    default run, so: (1) SURVEY.md 8(d)'s C1 protocol is always measured here (full oracle step at 1 024 tiles,
+    1 warm-up + 3 timed, median); (2) when ``bench.py --impl reference`` has run on THIS box (the driver runs it first),
+    its measured full-step figure at the bench tile count is reported as ``value``; otherwise ``value`` is the C1 figure
+    and ``sample`` says that it is the 1 024-tile workload.  Nothing is extrapolated."""
+    c1 = CpuStep(1024)
+    c1(0)
+    ts = sorted(c1(i) for i in range(3))
+    c1_rec = {"value": 1.0 / ts[1], "unit": UNIT, "tiles": 1024, "seconds_per_step": ts[1], "reps": 3, "warmup": 1,
+              "protocol": "SURVEY.md 8(d): full oracle step at 1 024 tiles (BASELINE.json configs[0]), median of 3"}
+    cached = None
+    try:
+        with open(CPU_ARM_CACHE) as f:
+            cached = json.load(f)
+        if cached.get("tiles") != tiles or time.time() - cached.get("when", 0) > 6 * 3600:
+            cached = None
+    except Exception:
+        cached = None
+    if cached is not None:
+        return {"value": cached["value"], "unit": UNIT, "cores": cached["cores"], "kind": "port",
+                "sample": "measured by `bench.py --impl reference` on this box "
+                          f"{time.time() - cached['when']:.0f} s earlier: " + cached["sample"], "c1": c1_rec}
+    return {"value": c1_rec["value"], "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"oracle (CPU restatement of the reference, fp32, torch {torch.get_num_threads()} threads): complete "
+                      f"training steps (3 task passes fwd + KL loss + bwd, 331 pathways) at 1 024 tiles (configs[0]), "
+                      f"1 warm-up + 3 timed, median {ts[1]:.1f} s.  NOT the {tiles}-tile workload of this line: the "
+                      f"full-size CPU figure comes from `bench.py --impl reference` ({tiles} tiles, minutes per step)",
+            "c1": c1_rec}
 
 
 def run_reference(args):
+    """``--impl reference``: complete oracle training steps at the bench tile count on the host cores.  A step takes
+    about a minute at 10k tiles, so the run does as many of the requested steps as fit ``--cpu-budget`` seconds (at
+    least one) and reports the TRUE ``steps`` / ``warmup`` it ran and the measured mean, never a scaled figure."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_tokens = args.tiles + 1
-    for _ in range(min(args.warmup, 1)):
-        cpu_layer_sample(n_tokens)
-    ts = [cpu_layer_sample(n_tokens) for _ in range(args.steps)]
+    step = CpuStep(args.tiles)
+    t_first = step(0)
+    warm = 1 if (args.warmup > 0 and 3.0 * t_first < args.cpu_budget) else 0
+    ts = [] if warm else [t_first]
+    spent = t_first
+    i = 1
+    while len(ts) < args.steps and (not ts or spent + ts[-1] < args.cpu_budget):
+        ts.append(step(i))
+        spent += ts[-1]
+        i += 1
     t = sum(ts) / len(ts)
-    value = 1.0 / (36.0 * t)
+    value = 1.0 / t
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 36.0 * t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": metric_name(args.tiles), "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(ts), "warmup": warm, "requested_steps": args.steps, "requested_warmup": args.warmup,
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"each step = one oracle encoder-layer fwd+bwd at {n_tokens} tokens "
-                                   f"({t:.2f} s mean), scaled x36 layer passes per slide step; the reference is pure "
-                                   f"Python with no CPU attention kernel of its own (flash_attn_func is None on CPU)"},
+                         "sample": f"{len(ts)} complete oracle training steps (3 task passes fwd + KL loss + bwd, 331 "
+                                   f"pathways{', every encoder layer recomputed in the backward (activation checkpointing)' if step.checkpoint else ''}) "
+                                   f"at {args.tiles} tiles, {torch.get_num_threads()} threads, "
+                                   f"{'1 full warm-up step' if warm else 'warm-up = one untimed 256-tile step'}; steps in seconds: "
+                                   f"{[round(x, 1) for x in ts]}; stopped at the {args.cpu_budget:.0f} s budget; the "
+                                   f"reference is pure Python with no CPU attention kernel of its own "
+                                   f"(flash_attn_func is None on CPU), so the arm is the oracle port pinned by tests/golden"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:
+        with open(CPU_ARM_CACHE, "w") as f:
+            json.dump({"tiles": args.tiles, "value": value, "cores": os.cpu_count(), "when": time.time(),
+                       "sample": line["cpu_baseline"]["sample"]}, f)
+    except OSError:
+        pass
     print(json.dumps(line))
 
 
@@ -174,8 +241,7 @@ def main():
 
     import torch.distributed as dist
 
-    from modaltune_b200 import _lib, config, ops, synthetic, train_step
-    from tests import helpers
+    from modaltune_b200 import _lib, config, factory, ops, synthetic, train_step
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -189,8 +255,8 @@ def main():
     config.set_mode(args.mode)
     config.set_attn_impl(args.attn)
 
-    model = helpers.build_model(None, device=dev)          # full 331-pathway ModalTune-GigaPath, seeded random init
-    proj = helpers.build_projector(0, dev)
+    model = factory.build_model(None, device=dev)          # full 331-pathway ModalTune-GigaPath, seeded random init
+    proj = factory.build_projector(0, dev)
     flat = train_step.FlatGradAllReduce([p for p in model.parameters() if p.requires_grad])
     n_slides = 2
     hosts = [train_step.pack_host_slide(synthetic.synthetic_slide(args.tiles, seed=1000 + rank * 100 + i))
@@ -306,7 +372,7 @@ def main():
                 "algorithmic_gflop_per_launch": f_fwd / 1e9, "share_of_step": t_fwd * n_fwd / args.steps / (ms / args.steps)},
     }
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": metric_name(args.tiles), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
         "config": workload_config(args, world),
@@ -318,8 +384,18 @@ def main():
         "attention_tflops": {"fwd": ach_fwd, "bwd": ach_bwd},
         "loss": out.get("loss"),
     }
+    if world == 1 and not args.no_extras:
+        # same-box comparator: the kernel the reference runs (flash_attn_func, FA2 built for sm_100) on its five per-layer
+        # shapes at this token count, next to our kernels (tools/bench_fa2_branches.py); library code, comparator only
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_fa2_branches
+
+            line["fa2_comparator"] = bench_fa2_branches.run(args.tiles + 1, reps=5, dev=dev)
+        except Exception as e:  # flash-attn missing on the box: say so, the bench line stands
+            line["fa2_comparator"] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.tiles + 1)
+        line["cpu_baseline"] = cpu_baseline(args.tiles)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

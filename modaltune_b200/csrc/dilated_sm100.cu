@@ -40,6 +40,23 @@ using namespace sm100;
 #define MT_TRACE_DUMP(who)
 #endif
 
+// experiment-only CTA timeline (compile with -DMT_DEBUG_TIMELINE): every CTA records (SM id, loop length, clock64 at entry
+// and exit) so that tools/attn_timeline.py can separate the time inside CTAs from the gaps between them on each SM
+#ifdef MT_DEBUG_TIMELINE
+__device__ long long mt_timeline[32768 * 4];
+#define MT_TL_BEGIN const long long tl_t0_ = clock64();
+#define MT_TL_END(n)                                                        \
+  if (threadIdx.x == 0 && blockIdx.x < 32768) {                             \
+    unsigned sm_;                                                           \
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));                        \
+    long long* e_ = mt_timeline + 4 * blockIdx.x;                           \
+    e_[0] = sm_; e_[1] = (n); e_[2] = tl_t0_; e_[3] = clock64();            \
+  }
+#else
+#define MT_TL_BEGIN
+#define MT_TL_END(n)
+#endif
+
 #ifndef MT_FWD_POLY
 #define MT_FWD_POLY 0                     // exponentials per 8 computed on the FMA pipes in the forward (ex2_poly)
 #endif
@@ -82,6 +99,7 @@ struct FwdSmem {
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Params P, __nv_bfloat16* __restrict__ o_br,
                          float* __restrict__ lse_br) {
+  MT_TL_BEGIN
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   // roles by warp id: the scheduler favours high warp ids, so the latency-critical single-thread roles sit last
@@ -360,6 +378,7 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
   tc_fence_before();
   __syncthreads();
   if (warp == W_MMA) tmem_dealloc(tmem, TMEM_COLS);
+  MT_TL_END(n_kv)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -547,6 +566,7 @@ __global__ void __launch_bounds__(BWD3_THREADS, 1)
 dilated_bwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ TensorMaps do_maps,
                           const __grid_constant__ TensorMaps dq32_maps, const __grid_constant__ TensorMaps dq16_maps,
                           const Sm100Params P, const float* __restrict__ lse, const float* __restrict__ delta_br) {
+  MT_TL_BEGIN
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   // roles by warp id: compute 0-15, dQ drain 16-19, TMA 20, statistics columns 21, MMA 22 (last: the scheduler
@@ -930,6 +950,7 @@ dilated_bwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
   tc_fence_before();
   __syncthreads();
   if (warp == W_MMA) tmem_dealloc(tmem, 512);
+  MT_TL_END(n_q)
 }
 
 int dilated_attn_bwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,
@@ -963,3 +984,16 @@ int dilated_attn_bwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int
 }
 
 }  // namespace mt
+
+#ifdef MT_DEBUG_TIMELINE
+// experiment builds only: copy the CTA timeline to the host ([n][4] long long) and clear it
+extern "C" int mt_debug_timeline(long long* dst, int n) {
+  if (n > 32768) n = 32768;
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(dst, mt::mt_timeline, sizeof(long long) * 4 * (size_t)n) != cudaSuccess) return -1;
+  void* p = nullptr;
+  cudaGetSymbolAddress(&p, mt::mt_timeline);
+  cudaMemset(p, 0, sizeof(long long) * 4 * 32768);
+  return 0;
+}
+#endif

@@ -335,11 +335,16 @@ def gene_encoder(sd, prefix, genes: Sequence[Tensor], depth: int = 3) -> Tensor:
 # ---------------------------------------------------------------------------------------------------------------------
 def adapter_forward(sd: Dict[str, Tensor], feats: Tensor, coords: Tensor, genes: Sequence[Tensor],
                     clinical: Optional[Tensor], task_token: Tensor, segment_lengths=None,
-                    ratios=DILATED_RATIO, table: Optional[Tensor] = None) -> Tensor:
+                    ratios=DILATED_RATIO, table: Optional[Tensor] = None, checkpoint_layers: bool = False) -> Tensor:
     """feats [L,1536], coords [L,2], genes list of [1,n_i], clinical [1,5] or None, task_token [k] -> [1, 256].
 
     prompt_agg='avg', token_agg='sum', use_prompt_sa, use_extra_extractor, multi_task>1 (the shipped JSON config).
     Note the adapter never applies ``self.norm`` / ``encoder.layer_norm`` (longvit_adapter.py:309-312).
+
+    ``checkpoint_layers``: recompute each encoder layer in the backward (torch.utils.checkpoint, the reference's own
+    ``checkpoint_activations`` switch, TS/architecture/encoder.py:317-319) instead of keeping the dense attention
+    probabilities of all 36 layer passes alive -- ~5 GB per layer at 10k tiles, which no host holds for a whole step.
+    Same arithmetic, same results; used by bench.py's CPU arm at the bench size.
     """
     if segment_lengths is None:
         segment_lengths = optimal_segment_lengths()
@@ -362,7 +367,11 @@ def adapter_forward(sd: Dict[str, Tensor], feats: Tensor, coords: Tensor, genes:
         x = injector(sd, f"interactions.{i}.injector", x, c, pe)
         x = torch.cat([cls, x], 0)
         for l in range(lo, hi + 1):
-            x = encoder_layer(sd, l, x, segment_lengths, ratios)
+            if checkpoint_layers and torch.is_grad_enabled():
+                from torch.utils.checkpoint import checkpoint
+                x = checkpoint(encoder_layer, sd, l, x, segment_lengths, ratios, use_reentrant=False)
+            else:
+                x = encoder_layer(sd, l, x, segment_lengths, ratios)
         cls, x = x[:1], x[1:]
         c = extractor(sd, f"interactions.{i}.extractor", c, x, pe)
         if i == len(INTERACTION_INDEXES) - 1:
@@ -397,9 +406,9 @@ def distill_loss(logits: Tensor, text_proj: Tensor) -> Tensor:
 
 
 def training_step(sd, proj_sd, feats, coords, genes, clinical, text, num_tasks: int = 3, segment_lengths=None,
-                  table=None):
+                  table=None, checkpoint_layers: bool = False):
     """Three task passes + loss (multitask_forward, train_modaltune.py:156-179).  Returns (loss, logits [3,256])."""
     eye = torch.eye(num_tasks, dtype=feats.dtype)
-    logits = torch.cat([adapter_forward(sd, feats, coords, genes, clinical, eye[t], segment_lengths, table=table)
-                        for t in range(3)], 0)
+    logits = torch.cat([adapter_forward(sd, feats, coords, genes, clinical, eye[t], segment_lengths, table=table,
+                                        checkpoint_layers=checkpoint_layers) for t in range(3)], 0)
     return distill_loss(logits, text_targets(proj_sd, text)), logits

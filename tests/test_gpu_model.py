@@ -79,8 +79,9 @@ def test_encoder_layer_golden(model, fixture, mode, attn, t_out, t_grad):
     gold = torch.load(os.path.join(helpers.GOLDEN, fixture))
     N = gold["N"]
     g = torch.Generator().manual_seed(gold["seed"])
-    x = torch.randn(1, N, 768, generator=g, dtype=torch.float64).float().to(DEV).requires_grad_(True)
-    dy = torch.randn(1, N, 768, generator=g, dtype=torch.float64).float().to(DEV)
+    gdt = torch.float32 if "gx_source" in gold else torch.float64   # the round-2 fixtures draw their inputs in fp32
+    x = torch.randn(1, N, 768, generator=g, dtype=gdt).float().to(DEV).requires_grad_(True)
+    dy = torch.randn(1, N, 768, generator=g, dtype=gdt).float().to(DEV)
     with config.using(mode=mode, attn_impl=attn):
         y, _ = model.encoder.layers[gold["layer"]](x, encoder_padding_mask=torch.zeros(1, N, dtype=torch.bool, device=DEV))
         (gx,) = torch.autograd.grad(y, x, dy)
@@ -297,8 +298,9 @@ def test_graphed_step_drives_an_optimizer_across_replays():
             opt_e.step()
         moved = 0.0
         ref = dict(helpers.build_model(helpers.SMALL_GROUPS, device=DEV).named_parameters())
+        dead = ("fn.3.bias", "pathway_compression.bias")   # structurally zero gradients: Adam amplifies pure rounding noise
         for (n, a), (_, b) in zip(m_g.named_parameters(), m_e.named_parameters()):
-            if not a.requires_grad:
+            if not a.requires_grad or (n.startswith("gene_encoder.") and n.endswith(dead)):
                 continue
             moved = max(moved, float((a - ref[n]).abs().max()))
             # Adam normalises the step: a gradient entry at the noise floor may move by up to 2 * lr either way
