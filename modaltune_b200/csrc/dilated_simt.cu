@@ -547,7 +547,8 @@ int dilated_attn_bwd_simt(const mt_dilated_geometry* geom, const void* qkv, int6
 int dilated_attn_fwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,
                            void* o_br, float* lse_br, int impl, cudaStream_t st);
 int dilated_attn_bwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,
-                           const void* dattn, const float* lse, const float* delta_br, float* dqkv, cudaStream_t st);
+                           const void* dattn, const float* lse, const float* delta_br, float* dqkv, int impl,
+                           cudaStream_t st);
 
 }  // namespace mt
 
@@ -572,7 +573,7 @@ extern "C" int mt_dilated_attn_bwd(const mt_dilated_geometry* geom, const void* 
   MT_CUDA(cudaMemsetAsync(dqkv_f32, 0, sizeof(float) * (size_t)n_alloc * 3 * geom->n_heads * geom->head_dim, st));
   if (impl == 0) return dilated_attn_bwd_simt(geom, qkv, qkv_ld, dattn, lse, delta_br, dtype, dqkv_f32, st);
   MT_REQUIRE(dtype == MT_BF16, "dilated_attn_bwd: the tcgen05 path computes in bf16");
-  return dilated_attn_bwd_sm100(geom, qkv, qkv_ld, n_alloc, dattn, lse, delta_br, dqkv_f32, st);
+  return dilated_attn_bwd_sm100(geom, qkv, qkv_ld, n_alloc, dattn, lse, delta_br, dqkv_f32, impl, st);
 }
 
 extern "C" int mt_dilated_merge_ln_fwd(const mt_dilated_geometry* geom, const void* o_br, const float* lse_br,

@@ -34,10 +34,16 @@ using namespace sm100;
 #define MT_TRACE_DECL long long tr_[96]; int trn_ = 0; const bool tron_ = (blockIdx.x == MT_TRACE_BLOCK);
 #define MT_TRACE(tag) do { if (tron_ && trn_ < 94) { tr_[trn_++] = (long long)(tag); tr_[trn_++] = clock64(); } } while (0)
 #define MT_TRACE_DUMP(who) do { if (tron_) for (int q_ = 0; q_ + 1 < trn_; q_ += 2) printf("%s %lld %lld\n", who, tr_[q_], tr_[q_ + 1] & 0xffffffffll); } while (0)
+#ifndef MT_TRACE_ITEM
+#define MT_TRACE_ITEM 5
+#endif
+// persistent kernels: stamps only while the CTA works on items MT_TRACE_ITEM .. MT_TRACE_ITEM + 1 (one hand-over)
+#define MT_TRACEW(n, tag) do { if (tron_ && (n) >= MT_TRACE_ITEM && (n) <= MT_TRACE_ITEM + 1 && trn_ < 94) { tr_[trn_++] = (long long)(tag); tr_[trn_++] = clock64(); } } while (0)
 #else
 #define MT_TRACE_DECL
 #define MT_TRACE(tag)
 #define MT_TRACE_DUMP(who)
+#define MT_TRACEW(n, tag)
 #endif
 
 // experiment-only CTA timeline (compile with -DMT_DEBUG_TIMELINE): every CTA records (SM id, loop length, clock64 at entry
@@ -52,6 +58,17 @@ __device__ long long mt_timeline[32768 * 4];
     long long* e_ = mt_timeline + 4 * blockIdx.x;                           \
     e_[0] = sm_; e_[1] = (n); e_[2] = tl_t0_; e_[3] = clock64();            \
   }
+// persistent kernels: one record per ITEM (loop length, clock at the first score tile, clock after the last one)
+__device__ long long mt_item_timeline[65536 * 4];
+__device__ int mt_item_count;
+#define MT_TL_ITEM(n, t_first, t_last)                                      \
+  do {                                                                      \
+    const int k_ = atomicAdd(&mt_item_count, 1);                            \
+    if (k_ < 65536) {                                                       \
+      long long* e_ = mt_item_timeline + 4 * k_;                            \
+      e_[0] = blockIdx.x; e_[1] = (n); e_[2] = (t_first); e_[3] = (t_last); \
+    }                                                                       \
+  } while (0)
 #else
 #define MT_TL_BEGIN
 #define MT_TL_END(n)
@@ -382,6 +399,385 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// forward, persistent (impl 2): the same per-tile pipeline, but the CTAs (2 per SM) stay resident and pull
+// (branch, segment, head, query tile) items from a device counter, longest key loops first.  Measured on B200
+// (tools/attn_timeline.py): a one-shot CTA lives 2 650 cycles per key tile + 4 400 cycles of prologue / epilogue, i.e. a
+// third of an 8-tile CTA's life is spent outside the loop.  Here the barriers, the TMEM allocation and the tensor-map
+// prefetch are paid once per SM, and the producer / MMA warps run ONE ITEM AHEAD: Q of the next item lands in the second
+// Q buffer and its first K / V tiles continue in the same ring while the softmax warps finish the current item, and the
+// first Q K^T of the next item is issued as soon as the last score tile of the current one has left TMEM.  The only
+// serial hand-over is the O accumulator: the first P V of an item waits until the previous item's O has been read out.
+// ---------------------------------------------------------------------------------------------------------------------
+struct FwdPSmem {
+  static constexpr int Q = 0;                                // [2]
+  static constexpr int K = Q + 2 * TILE_BYTES;
+  static constexpr int V = K + KV_STAGES * TILE_BYTES;
+  static constexpr int BAR = V + KV_STAGES * TILE_BYTES;
+  // sched_full[2], sched_empty[2], q_full[2], q_empty[2], kv_full[2], kv_empty[2], s_full, s_free, p_full, o_full, o_free
+  static constexpr int NBAR = 17;
+  static constexpr int QUEUE = BAR + NBAR * 8;               // int[2]: published item ids (-1 = no more work)
+  static constexpr int TMEM_PTR = QUEUE + 8;
+  static constexpr int TOTAL = TMEM_PTR + 16;
+};
+
+struct FwdItem {
+  int b, s, h, off, jseg, q0, n_kv, n_zero_tail;
+};
+
+// item id -> tile coordinates; false for a query tile that holds no real position (whole tiles of zero padding)
+__device__ __forceinline__ bool fwd_decode(const Sm100Params& P, int idx, FwdItem& it) {
+  int oi = 0;
+  while (oi + 1 < P.geo.nb && idx >= P.item_prefix[oi + 1]) ++oi;
+  it.b = P.order[oi];
+  const BranchGeom& bg = P.geo.b[it.b];
+  int local = idx - P.item_prefix[oi];
+  const int qt = local % P.tiles[it.b];
+  local /= P.tiles[it.b];
+  it.h = local % P.geo.H;
+  it.s = local / P.geo.H;
+  it.off = (it.h * bg.r) / P.geo.H;
+  it.jseg = (it.s * bg.g) / bg.r;
+  it.q0 = qt * BT;
+  const int seg_lo = it.s * bg.g + it.off;
+  const int seg_hi = min(P.geo.N, (it.s + 1) * bg.g);
+  const int c_real = seg_hi > seg_lo ? (seg_hi - seg_lo + bg.r - 1) / bg.r : 0;
+  it.n_kv = min(P.tiles[it.b], (c_real + BT - 1) / BT);
+  it.n_zero_tail = max(0, bg.m - it.n_kv * BT);
+  return it.q0 < c_real;
+}
+
+__global__ void __launch_bounds__(FWD_THREADS, 2)
+dilated_fwd_sm100_persistent_kernel(const __grid_constant__ TensorMaps maps, const Sm100Params P,
+                                    __nv_bfloat16* __restrict__ o_br, float* __restrict__ lse_br,
+                                    int* __restrict__ work_counter) {
+  MT_TL_BEGIN
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int W_TMA = 4, W_MMA = 5;
+  if ((sbase & 1023u) != 0) __trap();
+  const int H = P.geo.H, N = P.geo.N, E = H * DH;
+  const int total = P.item_prefix[P.geo.nb];
+
+  const uint32_t bar_sched_full = sbase + FwdPSmem::BAR + 0;     // [2]
+  const uint32_t bar_sched_empty = sbase + FwdPSmem::BAR + 16;   // [2]
+  const uint32_t bar_q_full = sbase + FwdPSmem::BAR + 32;        // [2]
+  const uint32_t bar_q_empty = sbase + FwdPSmem::BAR + 48;       // [2]
+  const uint32_t bar_kv_full = sbase + FwdPSmem::BAR + 64;       // [2]
+  const uint32_t bar_kv_empty = sbase + FwdPSmem::BAR + 80;      // [2]
+  const uint32_t bar_s_full = sbase + FwdPSmem::BAR + 96;
+  const uint32_t bar_s_free = sbase + FwdPSmem::BAR + 104;
+  const uint32_t bar_p_full = sbase + FwdPSmem::BAR + 112;
+  const uint32_t bar_o_full = sbase + FwdPSmem::BAR + 120;
+  const uint32_t bar_o_free = sbase + FwdPSmem::BAR + 128;
+  volatile int* queue = reinterpret_cast<volatile int*>(smem + FwdPSmem::QUEUE);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + FwdPSmem::TMEM_PTR);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_sched_full + 8 * i, 1);
+      mbar_init(bar_sched_empty + 8 * i, 129);   // 128 softmax threads + the MMA warp
+      mbar_init(bar_q_full + 8 * i, 1);
+      mbar_init(bar_q_empty + 8 * i, 1);
+      mbar_init(bar_kv_full + 8 * i, 1);
+      mbar_init(bar_kv_empty + 8 * i, 1);
+    }
+    mbar_init(bar_s_full, 1);
+    mbar_init(bar_s_free, 128);
+    mbar_init(bar_p_full, 128);
+    mbar_init(bar_o_full, 1);
+    mbar_init(bar_o_free, 128);
+    fence_barrier_init();
+    for (int b = 0; b < P.geo.nb; ++b) tma_prefetch_desc(&maps.m[b]);
+  }
+  if (warp == W_MMA) {
+    tmem_alloc(smem_u32((const void*)tmem_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_s = tmem;
+  const uint32_t tmem_p = tmem + 128;
+  const uint32_t tmem_o = tmem + 192;
+  int n_tiles_done = 0;   // timeline only
+
+  if (warp == W_TMA) {
+    // ===== scheduler + TMA producer (one thread) ======================================================================
+    if (lane == 0) {
+      int t = 0;                                   // key tiles loaded so far (ring position)
+      int next_idx = atomicAdd(work_counter, 1);   // always one fetch in flight: its latency hides behind the loads
+      for (int n = 0;; ++n) {
+        FwdItem it;
+        int idx = next_idx;
+        while (idx < total && !fwd_decode(P, idx, it)) idx = atomicAdd(work_counter, 1);
+        next_idx = atomicAdd(work_counter, 1);
+        const int slot = n & 1, use = n >> 1;
+        mbar_wait(bar_sched_empty + 8 * slot, (use & 1) ^ 1);
+        queue[slot] = idx < total ? idx : -1;
+        mbar_arrive(bar_sched_full + 8 * slot);
+        if (idx >= total) break;
+        const void* map = &maps.m[it.b];
+        mbar_wait(bar_q_empty + 8 * slot, (use & 1) ^ 1);
+        mbar_expect_tx(bar_q_full + 8 * slot, TILE_BYTES);
+        tma_load_3d(sbase + FwdPSmem::Q + slot * TILE_BYTES, map, bar_q_full + 8 * slot, it.h * DH, it.off,
+                    it.jseg + it.q0);
+        for (int j = 0; j < it.n_kv; ++j, ++t) {
+          const int st = t & 1;
+          mbar_wait(bar_kv_empty + 8 * st, ((t >> 1) & 1) ^ 1);
+          mbar_expect_tx(bar_kv_full + 8 * st, 2 * TILE_BYTES);
+          tma_load_3d(sbase + FwdPSmem::K + st * TILE_BYTES, map, bar_kv_full + 8 * st, E + it.h * DH, it.off,
+                      it.jseg + j * BT);
+          tma_load_3d(sbase + FwdPSmem::V + st * TILE_BYTES, map, bar_kv_full + 8 * st, 2 * E + it.h * DH, it.off,
+                      it.jseg + j * BT);
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ===== MMA issuer =================================================================================================
+    constexpr uint32_t IDESC_QK = umma_idesc_bf16(BT, BT, 0, 0);
+    constexpr uint32_t IDESC_PV = umma_idesc_bf16(BT, DH, 0, 1);
+    const uint64_t q_desc0 = umma_smem_desc(sbase + FwdPSmem::Q, 16, 1024);
+    const uint64_t k_desc0 = umma_smem_desc(sbase + FwdPSmem::K, 16, 1024);
+    const uint64_t v_desc0 = umma_smem_desc(sbase + FwdPSmem::V, TILE_BYTES, 1024);
+    // S = Q[qslot] K[t & 1]^T; `last` = last Q K^T of its item: the Q buffer is free once it has completed
+    auto issue_qk = [&](int qslot, int t, bool last) {
+      if (elect_one()) {
+        const uint64_t qd = umma_desc_adv(q_desc0, (uint32_t)qslot * TILE_BYTES);
+        const uint64_t kd = umma_desc_adv(k_desc0, (uint32_t)(t & 1) * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_ss(tmem_s, umma_desc_adv(qd, k * 32), umma_desc_adv(kd, k * 32), IDESC_QK, k > 0);
+        umma_commit(bar_s_full);
+        if (last) umma_commit(bar_q_empty + 8 * qslot);
+      }
+      __syncwarp();
+    };
+    // item n of this CTA -> n_kv (0 = no more work); every lane reads the queue, one lane releases the slot
+    auto get_item = [&](int n) -> int {
+      const int slot = n & 1;
+      mbar_wait(bar_sched_full + 8 * slot, (n >> 1) & 1);
+      const int idx = queue[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sched_empty + 8 * slot);
+      if (idx < 0) return 0;
+      FwdItem it;
+      fwd_decode(P, idx, it);
+      return it.n_kv;
+    };
+    int t = 0, n = 0;
+    int n_kv = get_item(0);
+    if (n_kv > 0) {
+      mbar_wait(bar_q_full, 0);
+      mbar_wait(bar_kv_full, 0);
+      tc_fence_after();
+      issue_qk(0, 0, n_kv == 1);
+    }
+    while (n_kv > 0) {
+      int n_kv_next = 0;
+      for (int j = 0; j < n_kv; ++j, ++t) {
+        // look one tile ahead: the next key tile of this item, or the first one of the next item
+        bool ahead = true, ahead_last = false;
+        int ahead_slot = n & 1;
+        if (j + 1 < n_kv) {
+          ahead_last = (j + 2 == n_kv);
+        } else {
+          n_kv_next = get_item(n + 1);
+          ahead = n_kv_next > 0;
+          ahead_slot = (n + 1) & 1;
+          ahead_last = (n_kv_next == 1);
+          if (ahead) mbar_wait(bar_q_full + 8 * ahead_slot, ((n + 1) >> 1) & 1);
+        }
+        if (ahead) {
+          mbar_wait(bar_kv_full + 8 * ((t + 1) & 1), ((t + 1) >> 1) & 1);
+          mbar_wait(bar_s_free, t & 1);        // the softmax threads have read S_t out of TMEM
+          tc_fence_after();
+          issue_qk(ahead_slot, t + 1, ahead_last);
+        }
+        mbar_wait(bar_p_full, t & 1);          // P_t is in TMEM
+        if (j == 0 && n > 0) mbar_wait(bar_o_free, (n - 1) & 1);   // the previous item's O has been read out
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t vd = umma_desc_adv(v_desc0, (uint32_t)(t & 1) * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BT / 16; ++k)
+            umma_ts(tmem_o, tmem_p + k * 8, umma_desc_adv(vd, k * 2048), IDESC_PV, (j > 0) || (k > 0));
+          umma_commit(bar_kv_empty + 8 * (t & 1));
+          umma_commit(bar_o_full);
+        }
+        __syncwarp();
+      }
+      n_kv = n_kv_next;
+      ++n;
+    }
+    n_tiles_done = t;
+  } else {
+    // ===== softmax: one query row per thread; O accumulates in TMEM over the key loop of an item ======================
+    const int lane_grp = warp & 3;
+    const int row = lane_grp * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
+    const float scale_log2 = P.scale_log2;
+    int t = 0;
+    for (int n = 0;; ++n) {
+      const int slot = n & 1;
+      mbar_wait(bar_sched_full + 8 * slot, (n >> 1) & 1);
+      const int idx = queue[slot];
+      mbar_arrive(bar_sched_empty + 8 * slot);
+      if (idx < 0) break;
+      // only the loop length and the segment's slot count stay live across the key loop (its 128 scores per thread
+      // leave no registers to spare); the epilogue decodes the item again
+      int n_kv, seg_m;
+      {
+        FwdItem it0;
+        fwd_decode(P, idx, it0);
+        n_kv = it0.n_kv;
+        seg_m = P.geo.b[it0.b].m;
+      }
+      float m_used = -INFINITY, l_run = 0.f;
+      auto tile = [&](int j, auto mask_tag) {
+        constexpr bool MASK = decltype(mask_tag)::value;
+        const int kvalid = seg_m - j * BT;
+        mbar_wait(bar_s_full, t & 1);
+        tc_fence_after();
+        float sv[BT];
+        tmem_ld64(tmem_s + t_lane, sv);
+        tmem_ld64(tmem_s + t_lane + 64, sv + 64);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(bar_s_free);
+        if (MASK) {
+#pragma unroll
+          for (int i = 0; i < BT; ++i) sv[i] = (i < kvalid) ? sv[i] : -INFINITY;
+        }
+        float mx = fmax3(sv[0], sv[1], sv[2]);
+#pragma unroll
+        for (int i = 3; i + 1 < BT; i += 2) mx = fmax3(mx, sv[i], sv[i + 1]);
+        mx = fmaxf(mx, sv[BT - 1]);
+        bool waited = false;
+        if (j == 0) {
+          m_used = mx;
+        } else {
+          const bool need = (mx - m_used) * scale_log2 > 8.f;
+          if (__any_sync(0xffffffffu, need)) {
+            mbar_wait(bar_o_full, (t - 1) & 1);
+            tc_fence_after();
+            waited = true;
+            const float alpha = need ? ex2((m_used - mx) * scale_log2) : 1.f;
+            float o8[8];
+#pragma unroll
+            for (int c = 0; c < DH / 8; ++c) {
+              tmem_ld8(tmem_o + t_lane + c * 8, o8);
+              tmem_ld_wait();
+              uint32_t u[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) u[i] = __float_as_uint(o8[i] * alpha);
+              tmem_st8(tmem_o + t_lane + c * 8, u);
+            }
+            if (need) {
+              l_run *= alpha;
+              m_used = mx;
+            }
+          }
+        }
+        const float mb = m_used * scale_log2;
+        // P_t overwrites P_{t-1}: its P V must have read it.  For the first tile of an item that P V belongs to the
+        // previous item, whose epilogue has already waited for it.
+        if (j > 0 && !waited) {
+          mbar_wait(bar_o_full, (t - 1) & 1);
+          tc_fence_after();
+        }
+        float rs = 0.f;
+#pragma unroll
+        for (int c = 0; c < BT / 32; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2(fmaf(sv[c * 32 + i], scale_log2, -mb));
+            const float p1 = ex2(fmaf(sv[c * 32 + i + 1], scale_log2, -mb));
+            rs += p0 + p1;
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
+          tmem_st16(tmem_p + t_lane + c * 16, pk);
+        }
+        l_run += rs;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_p_full);
+      };
+      for (int j = 0; j < n_kv; ++j, ++t) {
+        if (seg_m - j * BT >= BT) tile(j, std::false_type{});
+        else tile(j, std::true_type{});
+      }
+      // ---- epilogue of the item: O out of TMEM, then the accumulator is free for the next item ----------------------
+      mbar_wait(bar_o_full, (t - 1) & 1);
+      tc_fence_after();
+      float o_acc[DH];
+#pragma unroll
+      for (int c = 0; c < DH / 16; ++c) {
+        float t16[16];
+        tmem_ld16(tmem_o + t_lane + c * 16, t16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] = t16[i];
+      }
+      tc_fence_before();
+      mbar_arrive(bar_o_free);
+      int idx2 = idx;
+      asm volatile("" : "+r"(idx2));   // decode again instead of keeping the item's fields live across the loop
+      FwdItem it;
+      fwd_decode(P, idx2, it);
+      const BranchGeom& bg = P.geo.b[it.b];
+      if (it.n_zero_tail > 0) {   // the zero keys of the tiles that were skipped
+        const float m_fin = fmaxf(m_used, 0.f);
+        const float alpha = ex2((m_used - m_fin) * scale_log2);
+        l_run = l_run * alpha + (float)it.n_zero_tail * ex2(-m_fin * scale_log2);
+#pragma unroll
+        for (int i = 0; i < DH; ++i) o_acc[i] *= alpha;
+        m_used = m_fin;
+      }
+      const int slot_q = it.q0 + row;
+      const int pos = it.s * bg.g + it.off + slot_q * bg.r;
+      const int seg_end = min(N, (it.s + 1) * bg.g);
+      if (slot_q < bg.m && pos < seg_end) {
+        const float inv = 1.f / l_run;
+        const int slot_h = it.h - it.off * bg.hpb;
+        __nv_bfloat16* dst = o_br + bg.o_off + ((int64_t)pos * bg.hpb + slot_h) * DH;
+#pragma unroll
+        for (int c = 0; c < DH / 8; ++c) {
+          uint4 u;
+          u.x = pack_bf16(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
+          u.y = pack_bf16(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
+          u.z = pack_bf16(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv);
+          u.w = pack_bf16(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
+          *reinterpret_cast<uint4*>(dst + c * 8) = u;
+        }
+        lse_br[bg.lse_off + (int64_t)pos * bg.hpb + slot_h] = m_used * P.scale + logf(l_run);
+      }
+    }
+  }
+  // ---- teardown: the last CTA to finish re-arms the work counter for the next launch that uses it --------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc(tmem, TMEM_COLS);
+  if (threadIdx.x == 0) {
+    if (atomicAdd(work_counter + 1, 1) == (int)gridDim.x - 1) {
+      work_counter[1] = 0;
+      __threadfence();
+      work_counter[0] = 0;
+    }
+  }
+#ifdef MT_DEBUG_TIMELINE
+  if (threadIdx.x == W_MMA * 32) {
+    unsigned sm_;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));
+    long long* e_ = mt_timeline + 4 * blockIdx.x;
+    e_[0] = sm_; e_[1] = n_tiles_done; e_[2] = tl_t0_; e_[3] = clock64();
+  }
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -479,6 +875,21 @@ static int make_sm100_params(const mt_dilated_geometry* geom, Sm100Params* P) {
   return 0;
 }
 
+// Work counters of the persistent kernels: a ring of {next item, finished CTAs} pairs in device memory, zero at rest (the
+// last CTA of a launch re-arms its pair).  Consecutive launches take consecutive pairs, so launches that overlap on
+// different streams (the three task passes of a step) never share one; a pair comes round again 256 launches later.
+static int* next_work_counter() {
+  static int* ring[64] = {nullptr};          // per device
+  static unsigned seq = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (ring[dev] == nullptr) {
+    if (cudaMalloc(&ring[dev], 256 * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+    if (cudaMemset(ring[dev], 0, 256 * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+  }
+  return ring[dev] + 2 * (seq++ % 256);
+}
+
 int dilated_attn_fwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,
                            void* o_br, float* lse_br, int impl, cudaStream_t st) {
   Sm100Params P;
@@ -492,7 +903,17 @@ int dilated_attn_fwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int
     rc = encode_branch_map(&maps.m[b], qkv, qkv_ld, n_alloc, P.geo.b[b].r);
     if (rc) return rc;
   }
-  (void)impl;   // one tcgen05 forward (impl >= 1)
+  if (impl == 2) {   // persistent CTAs with a device work counter
+    int* counter = next_work_counter();
+    MT_REQUIRE(counter != nullptr, "dilated_attn_fwd: cannot allocate the work counters");
+    const int items = P.item_prefix[P.geo.nb];
+    const int grid = items < 2 * kNumSMs ? items : 2 * kNumSMs;
+    MT_CUDA(cudaFuncSetAttribute(dilated_fwd_sm100_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 FwdPSmem::TOTAL));
+    dilated_fwd_sm100_persistent_kernel<<<grid, FWD_THREADS, FwdPSmem::TOTAL, st>>>(maps, P, (__nv_bfloat16*)o_br, lse_br,
+                                                                                   counter);
+    return check_launch("dilated_fwd_sm100_persistent_kernel");
+  }
   MT_CUDA(cudaFuncSetAttribute(dilated_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
   dilated_fwd_sm100_kernel<<<P.item_prefix[P.geo.nb], FWD_THREADS, FwdSmem::TOTAL, st>>>(
       maps, P, (__nv_bfloat16*)o_br, lse_br);
@@ -953,8 +1374,659 @@ dilated_bwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
   MT_TL_END(n_q)
 }
 
+// =====================================================================================================================
+// backward, persistent (impl 2): one CTA per SM stays resident and pulls key tiles from a device counter
+// =====================================================================================================================
+// Measured on B200 (tools/attn_timeline.py): a one-shot backward CTA lives 2 394 cycles per query tile + 9 300 cycles
+// of prologue / epilogue, and the SM idles another 1 400 cycles until the next CTA starts -- with ONE CTA per SM (512
+// TMEM columns, 221 KB of shared memory) nothing hides that: 25 % of the launch at 10k tokens, where a CTA streams only
+// 8-23 query tiles.  Here the per-item pipeline is the one above, but consecutive items overlap:
+//   * K / V of the NEXT item travel through the Q / dO ring as one more entry (K in the Q half, V in the dO half), so
+//     they are in shared memory two tiles before the current item ends; the dedicated V buffer is gone (V is only ever
+//     read once, for the TMEM copy), K is copied ring -> its fixed buffer once the current item's last dQ MMA is done.
+//   * K' / V' of the next item go to TMEM as soon as the compute warps have finished the last half tile of the current
+//     item (its S^T / dP^T MMAs have completed by then), while the MMA warp still issues the last dV / dK / dQ MMAs.
+//   * dK leaves through the dS^T buffer the last tile used, dV through the dQ staging tile of the drain warps; the next
+//     item's first dV / dK MMA only waits until both accumulators have been read into registers.
+struct BwdPSmem {
+  static constexpr int NQ = 3;
+  static constexpr int K = 0;
+  static constexpr int RING = K + TILE_BYTES;              // [NQ] x {Q tile, dO tile}
+  static constexpr int DS = RING + NQ * 2 * TILE_BYTES;    // [2] dS^T tiles: [128 key rows][2 blocks of 64 queries]
+  static constexpr int STG = DS + 4 * TILE_BYTES;          // fp32 staging tile of the dQ / dV reduce-adds (24 KB)
+  static constexpr int BAR = STG + BT * DH * 4;
+  // sched_full[2], sched_empty[2], ring_full[NQ], ring_empty[NQ], aug_full[NQ], kvt_full, st_full[2], pt_full[2],
+  // dq_full, dq_free, done, acc_free
+  static constexpr int NBAR = 4 + 3 * NQ + 9;
+  static constexpr int QUEUE = (BAR + NBAR * 8 + 15) / 16 * 16;   // 2 x 16 ints: decoded items published by the scheduler
+  static constexpr int TMEM_PTR = QUEUE + 128;
+  static constexpr int TOTAL = TMEM_PTR + 16;
+  static constexpr int STG16 = BT * 128;
+};
+static_assert(BwdPSmem::TOTAL <= 232448, "shared memory of the persistent backward kernel");
+
+struct BwdItem {   // 12 ints: three 16-byte shared-memory accesses
+  int n_q;         // query tiles of the item; <= 0: no more work
+  int b, s, h, off, jseg, k0, seg_end, slot_h, pad0, pad1, pad2;
+};
+
+__device__ __forceinline__ bool bwd_decode(const Sm100Params& P, int idx, BwdItem& it) {
+  int oi = 0;
+  while (oi + 1 < P.geo.nb && idx >= P.item_prefix[oi + 1]) ++oi;
+  it.b = P.order[oi];
+  const BranchGeom& bg = P.geo.b[it.b];
+  int local = idx - P.item_prefix[oi];
+  const int kt = local % P.tiles[it.b];
+  local /= P.tiles[it.b];
+  it.h = local % P.geo.H;
+  it.s = local / P.geo.H;
+  it.off = (it.h * bg.r) / P.geo.H;
+  it.jseg = (it.s * bg.g) / bg.r;
+  it.k0 = kt * BT;
+  it.seg_end = min(P.geo.N, (it.s + 1) * bg.g);
+  it.slot_h = it.h - it.off * bg.hpb;
+  const int seg_lo = it.s * bg.g + it.off;
+  const int c_real = it.seg_end > seg_lo ? (it.seg_end - seg_lo + bg.r - 1) / bg.r : 0;
+  it.n_q = min(P.tiles[it.b], (c_real + BT - 1) / BT);
+  return it.k0 < c_real;
+}
+
+__global__ void __launch_bounds__(BWD3_THREADS, 1)
+dilated_bwd_sm100_persistent_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ TensorMaps do_maps,
+                                    const __grid_constant__ TensorMaps dq32_maps, const __grid_constant__ TensorMaps dq16_maps,
+                                    const Sm100Params P, const float* __restrict__ lse, const float* __restrict__ delta_br,
+                                    int* __restrict__ work_counter) {
+  MT_TL_BEGIN
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int W_DRAIN = 16, W_TMA = 20, W_AUG = 21, W_MMA = 22;
+  if ((sbase & 1023u) != 0) __trap();
+  const int H = P.geo.H, E = H * DH;
+  const int total = P.item_prefix[P.geo.nb];
+  constexpr int NQ = BwdPSmem::NQ;
+  constexpr int NCOMP = 512;
+
+  const uint32_t bar_sched_full = sbase + BwdPSmem::BAR + 0;      // [2]
+  const uint32_t bar_sched_empty = sbase + BwdPSmem::BAR + 16;    // [2]
+  const uint32_t bar_ring_full = sbase + BwdPSmem::BAR + 32;      // [NQ] TMA landed
+  const uint32_t bar_ring_empty = bar_ring_full + 8 * NQ;         // [NQ]
+  const uint32_t bar_aug_full = bar_ring_empty + 8 * NQ;          // [NQ] statistics columns written into the entry
+  const uint32_t bar_kvt_full = bar_aug_full + 8 * NQ;            // K' / V' of an item are in TMEM
+  const uint32_t bar_st_full = bar_kvt_full + 8;                  // [2]
+  const uint32_t bar_pt_full = bar_st_full + 16;                  // [2]
+  const uint32_t bar_dq_full = bar_pt_full + 16;
+  const uint32_t bar_dq_free = bar_dq_full + 8;
+  const uint32_t bar_done = bar_dq_free + 8;                      // every MMA of an item has completed
+  const uint32_t bar_acc_free = bar_done + 8;                     // dK / dV of an item have been read out of TMEM
+  uint8_t* queue = smem + BwdPSmem::QUEUE;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + BwdPSmem::TMEM_PTR);
+
+  if (warp == W_TMA && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_sched_full + 8 * i, 1);
+      mbar_init(bar_sched_empty + 8 * i, 22);   // one arrival per consumer warp: 16 compute, 4 drain, statistics, MMA
+      mbar_init(bar_st_full + 8 * i, 1);
+      mbar_init(bar_pt_full + 8 * i, NCOMP);
+    }
+    for (int i = 0; i < NQ; ++i) {
+      mbar_init(bar_ring_full + 8 * i, 1);
+      mbar_init(bar_ring_empty + 8 * i, 1);
+      mbar_init(bar_aug_full + 8 * i, 32);
+    }
+    mbar_init(bar_kvt_full, 256);
+    mbar_init(bar_dq_full, 1);
+    mbar_init(bar_dq_free, 128);
+    mbar_init(bar_done, 1);
+    mbar_init(bar_acc_free, NCOMP + 128);
+    fence_barrier_init();
+    for (int b = 0; b < P.geo.nb; ++b) {
+      tma_prefetch_desc(&maps.m[b]);
+      tma_prefetch_desc(&do_maps.m[b]);
+      tma_prefetch_desc(&dq32_maps.m[b]);
+      tma_prefetch_desc(&dq16_maps.m[b]);
+    }
+  }
+  if (warp == W_MMA) {
+    tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tm_dv = tmem + 256, tm_dk = tmem + 320, tm_dq = tmem + 384, tm_k = tmem + 448, tm_v = tmem + 480;
+  int tl_tiles = 0;   // timeline only
+
+  // item n of this CTA, decoded once by the scheduler thread (the integer divisions of the decode are hundreds of
+  // cycles of cold code; the consumers sit on the hand-over critical path): every consumer warp copies the record out
+  // of shared memory and releases the queue slot with one arrival.  false = no more work.
+  auto read_item = [&](int n, BwdItem& it) -> bool {
+    const int slot = n & 1;
+    mbar_wait(bar_sched_full + 8 * slot, (n >> 1) & 1);
+    const uint4* q = reinterpret_cast<const uint4*>(queue + slot * 64);
+    const uint4 a = q[0], b2 = q[1], c = q[2];
+    it.n_q = (int)a.x; it.b = (int)a.y; it.s = (int)a.z; it.h = (int)a.w;
+    it.off = (int)b2.x; it.jseg = (int)b2.y; it.k0 = (int)b2.z; it.seg_end = (int)b2.w;
+    it.slot_h = (int)c.x;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_sched_empty + 8 * slot);
+    return it.n_q > 0;
+  };
+
+  if (warp == W_TMA) {
+    // ===== scheduler + TMA producer ====================================================================================
+    if (lane == 0) {
+      int e = 0;                                   // ring entries issued so far
+      int next_idx = atomicAdd(work_counter, 1);
+      MT_TRACE_DECL
+      for (int n = 0;; ++n) {
+        BwdItem it;
+        int idx = next_idx;
+        while (idx < total && !bwd_decode(P, idx, it)) idx = atomicAdd(work_counter, 1);
+        const int qs = n & 1;
+        mbar_wait(bar_sched_empty + 8 * qs, ((n >> 1) & 1) ^ 1);
+        {
+          uint4* q = reinterpret_cast<uint4*>(queue + qs * 64);
+          q[0] = make_uint4((uint32_t)(idx < total ? it.n_q : 0), (uint32_t)it.b, (uint32_t)it.s, (uint32_t)it.h);
+          q[1] = make_uint4((uint32_t)it.off, (uint32_t)it.jseg, (uint32_t)it.k0, (uint32_t)it.seg_end);
+          q[2] = make_uint4((uint32_t)it.slot_h, 0u, 0u, 0u);
+        }
+        mbar_arrive(bar_sched_full + 8 * qs);
+        MT_TRACEW(n, 5000);
+        if (idx >= total) break;
+        const void* map = &maps.m[it.b];
+        const void* dmap = &do_maps.m[it.b];
+        {  // K / V entry
+          const int st = e % NQ;
+          mbar_wait(bar_ring_empty + 8 * st, ((e / NQ) & 1) ^ 1);
+          mbar_expect_tx(bar_ring_full + 8 * st, 2 * TILE_BYTES);
+          const uint32_t dst = sbase + BwdPSmem::RING + st * 2 * TILE_BYTES;
+          tma_load_3d(dst, map, bar_ring_full + 8 * st, E + it.h * DH, it.off, it.jseg + it.k0);
+          tma_load_3d(dst + TILE_BYTES, map, bar_ring_full + 8 * st, 2 * E + it.h * DH, it.off, it.jseg + it.k0);
+          MT_TRACEW(n, 5100);
+          ++e;
+        }
+        for (int i = 0; i < it.n_q; ++i, ++e) {
+          // the next item is claimed late -- three tiles before this one ends, enough to hide the atomic's latency --
+          // so that near the end of the launch no CTA sits on a claimed item while others have run out of work
+          if (i == max(0, it.n_q - 3)) next_idx = atomicAdd(work_counter, 1);
+          const int st = e % NQ;
+          mbar_wait(bar_ring_empty + 8 * st, ((e / NQ) & 1) ^ 1);
+          mbar_expect_tx(bar_ring_full + 8 * st, 2 * TILE_BYTES);
+          const uint32_t dst = sbase + BwdPSmem::RING + st * 2 * TILE_BYTES;
+          tma_load_3d(dst, map, bar_ring_full + 8 * st, it.h * DH, it.off, it.jseg + i * BT);
+          tma_load_3d(dst + TILE_BYTES, dmap, bar_ring_full + 8 * st, it.h * DH, it.off, it.jseg + i * BT);
+          if (i < 3 || i >= it.n_q - 2) MT_TRACEW(n, 5200 + i);
+        }
+      }
+      MT_TRACE_DUMP("tma");
+    }
+  } else if (warp == W_AUG) {
+    // ===== statistics columns: lane owns rows lane + 32 j of every Q / dO tile ==========================================
+    // The raw per-query statistics (strided 4-byte gathers of lse / delta: thousands of cycles when they miss L2) are
+    // always loaded ONE RING ENTRY AHEAD, across item boundaries too: at the last tile of an item the warp already
+    // fetches the first tile of the next item, whose record the scheduler has published by then.
+    const float inv_sc = 1.f / P.scale;
+    int e = 0;
+    MT_TRACE_DECL
+    auto load_raw = [&](const BwdItem& t, int i, float (&l)[4], float (&d)[4]) {
+      const BranchGeom& tb = P.geo.b[t.b];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int slot = i * BT + lane + 32 * j;
+        const int pos = t.s * tb.g + t.off + slot * tb.r;
+        const bool qok = slot < tb.m && pos < t.seg_end;
+        const int pc = qok ? pos : 0;
+        l[j] = lse[(int64_t)pc * H + t.h];
+        d[j] = delta_br[tb.lse_off + (int64_t)pc * tb.hpb + t.slot_h];
+      }
+    };
+    BwdItem it;
+    bool have = read_item(0, it);
+    float lr[4], dr[4], ln[4], dn[4];
+    if (have) load_raw(it, 0, lr, dr);
+    for (int n = 0; have; ++n) {
+      const BranchGeom& bg = P.geo.b[it.b];
+      MT_TRACEW(n, 4000);
+      // the K / V entry carries no statistics, but every use of a ring slot must advance the slot's aug_full phase
+      mbar_arrive(bar_aug_full + 8 * (e % NQ));
+      ++e;
+      BwdItem nxt;
+      bool have_next = false;
+      for (int i = 0; i < it.n_q; ++i, ++e) {
+        if (i + 1 < it.n_q) {
+          load_raw(it, i + 1, ln, dn);
+        } else {
+          have_next = read_item(n + 1, nxt);
+          if (have_next) load_raw(nxt, 0, ln, dn);
+        }
+        const int st = e % NQ;
+        mbar_wait(bar_ring_full + 8 * st, (e / NQ) & 1);
+        uint8_t* qt = smem + BwdPSmem::RING + st * 2 * TILE_BYTES;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int row = lane + 32 * j;
+          const int slot = i * BT + row;
+          const int pos = it.s * bg.g + it.off + slot * bg.r;
+          const bool qok = slot < bg.m && pos < it.seg_end;
+          uint32_t w0, w1;
+          split3_bf16(qok ? -lr[j] * inv_sc : -32768.f, w0, w1, -32768.f);
+          *reinterpret_cast<uint4*>(qt + row * 128 + ((6 ^ (row & 7)) << 4)) = make_uint4(w0, w1, 0u, 0u);
+          split3_bf16(qok ? -dr[j] : 0.f, w0, w1, 0.f);
+          *reinterpret_cast<uint4*>(qt + TILE_BYTES + row * 128 + ((6 ^ (row & 7)) << 4)) = make_uint4(w0, w1, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_aug_full + 8 * st);
+        if (i < 3 || i >= it.n_q - 2) MT_TRACEW(n, 4100 + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { lr[j] = ln[j]; dr[j] = dn[j]; }
+      }
+      it = nxt;
+      have = have_next;
+    }
+    if (lane == 0) { MT_TRACE_DUMP("aug"); }
+  } else if (warp == W_MMA) {
+    // ===== MMA issuer =================================================================================================
+    constexpr uint32_t IDESC_ST = umma_idesc_bf16(BT, 64, 0, 0);    // A = K' / V' (TMEM), B = Q' / dO' half tile (K-major)
+    constexpr uint32_t IDESC_TS = umma_idesc_bf16(BT, DH, 0, 1);    // A = P^T / dS^T (TMEM), B = dO / Q (MN-major)
+    constexpr uint32_t IDESC_DQ = umma_idesc_bf16(BT, DH, 1, 1);    // A = dS^T tile (smem, MN-major), B = K (MN-major)
+    const uint64_t ring_k_desc = umma_smem_desc(sbase + BwdPSmem::RING, 16, 1024);          // K-major view of entry 0
+    const uint64_t ring_m_desc = umma_smem_desc(sbase + BwdPSmem::RING, TILE_BYTES, 1024);  // MN-major view of entry 0
+    const uint64_t k_mn_desc = umma_smem_desc(sbase + BwdPSmem::K, TILE_BYTES, 1024);
+    const uint64_t ds_desc0 = umma_smem_desc(sbase + BwdPSmem::DS, TILE_BYTES, 1024);
+    // S'^T and dP'^T of one half tile (ring slot ST, half HH: compile-time, every descriptor is a base plus a constant --
+    // the single issuing thread shares its scheduler with five busy warps and its instructions are critical-path
+    // latency) into TMEM buffer HH
+    auto issue_st = [&](auto ST, auto HH) {
+      constexpr int st = decltype(ST)::value, hh = decltype(HH)::value;
+      if (elect_one()) {
+        constexpr uint32_t so = (uint32_t)(st * 2 * TILE_BYTES + hh * 64 * 128);
+        const uint32_t ts = tmem + hh * 128, td = ts + 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ts(ts, tm_k + k * 8, umma_desc_adv(ring_k_desc, so + k * 32), IDESC_ST, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ts(td, tm_v + k * 8, umma_desc_adv(ring_k_desc, so + TILE_BYTES + k * 32), IDESC_ST, k > 0);
+        umma_commit(bar_st_full + 8 * hh);
+      }
+      __syncwarp();
+    };
+    // dQ of global query tile tg = dS[tg & 1] K: nothing here depends on the ring slot
+    auto issue_dq = [&](int tg) {
+      if (tg > 0) mbar_wait(bar_dq_free, (tg - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t ds = umma_desc_adv(ds_desc0, (uint32_t)(tg & 1) * 2 * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BT / 16; ++k)
+          umma_ss(tm_dq, umma_desc_adv(ds, k * 2048), umma_desc_adv(k_mn_desc, k * 2048), IDESC_DQ, k > 0);
+        umma_commit(bar_dq_full);
+      }
+      __syncwarp();
+    };
+    int e = 0, ti = 0;   // ring entries / query tiles consumed so far (all items)
+    int n = 0, n_half = 0;
+    BwdItem it, nxt;
+    bool have_next = false;
+    MT_TRACE_DECL
+    // S'^T / dP'^T of BOTH halves of the first query tile of item n_item, whose first Q / dO entry is ring entry `ent`:
+    // issued by the previous item's tail (ahead of its last dQ MMA), so that the compute warps find the first score
+    // tile of the next item ready right after the last one of this item
+    auto issue_first = [&](int n_item, int ent) {
+      const int st = ent % NQ;
+      const uint32_t par = (uint32_t)(ent / NQ) & 1u;
+      mbar_wait(bar_kvt_full, n_item & 1);       // K' and V' of that item are in TMEM
+      mbar_wait(bar_ring_full + 8 * st, par);
+      mbar_wait(bar_aug_full + 8 * st, par);
+      tc_fence_after();
+      if (st == 0) {
+        issue_st(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
+        issue_st(std::integral_constant<int, 0>{}, std::integral_constant<int, 1>{});
+      } else if (st == 1) {
+        issue_st(std::integral_constant<int, 1>{}, std::integral_constant<int, 0>{});
+        issue_st(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
+      } else {
+        issue_st(std::integral_constant<int, 2>{}, std::integral_constant<int, 0>{});
+        issue_st(std::integral_constant<int, 2>{}, std::integral_constant<int, 1>{});
+      }
+    };
+    // One item whose first Q / dO entry sits in ring slot S0 (compile time: the three instantiations differ only in
+    // constants).  e = entry index of that first Q / dO entry.
+    auto run_item = [&](auto S0) {
+      constexpr int s0 = decltype(S0)::value;
+      const int ediv = e / NQ;              // ring use count of entry e (e % NQ == s0)
+      MT_TRACEW(n, 2000);
+      // half tile g = 6 * trip + U of the item: tile i = 3 * trip + U / 2 in ring slot (s0 + U / 2) % NQ
+      auto half = [&](int g, int trip, auto U) {
+        constexpr int u = decltype(U)::value;
+        constexpr int u2 = u >> 1, hh = u & 1;
+        constexpr int st = (s0 + u2) % NQ;
+        const int tg = ti + (g >> 1);                              // global tile index
+        mbar_wait(bar_pt_full + 8 * hh, tg & 1);                   // P^T, dS^T of this half are in TMEM (+ dS^T in smem)
+        if (g < 4 || g >= n_half - 4) MT_TRACEW(n, 2100 + g);
+        if (g == 0 && n > 0) mbar_wait(bar_acc_free, (n - 1) & 1);   // the previous item's dK / dV have been read out
+        if (g == 0) MT_TRACEW(n, 2003);
+        tc_fence_after();
+        if (elect_one()) {
+          constexpr uint32_t so = (uint32_t)(st * 2 * TILE_BYTES + hh * 64 * 128);
+          const uint32_t ts = tmem + hh * 128, td = ts + 64;
+          umma_ts(tm_dv, ts, umma_desc_adv(ring_m_desc, so + TILE_BYTES), IDESC_TS, g > 0);
+#pragma unroll
+          for (int k = 1; k < 4; ++k)
+            umma_ts(tm_dv, ts + k * 16, umma_desc_adv(ring_m_desc, so + TILE_BYTES + k * 2048), IDESC_TS, 1);
+          umma_ts(tm_dk, td, umma_desc_adv(ring_m_desc, so), IDESC_TS, g > 0);
+#pragma unroll
+          for (int k = 1; k < 4; ++k) umma_ts(tm_dk, td + k * 16, umma_desc_adv(ring_m_desc, so + k * 2048), IDESC_TS, 1);
+          if (hh == 1) umma_commit(bar_ring_empty + 8 * st);      // last readers of this Q / dO entry
+        }
+        __syncwarp();
+        if (g + 2 < n_half) {          // the S^T / dP^T buffer is free once the MMAs above have consumed it (in order)
+          constexpr int st2 = (st + 1) % NQ;
+          if (hh == 0) {
+            // ring use count of entry e + 3 trip + u2 + 1
+            constexpr int carry = (s0 + u2 + 1) / NQ;
+            const uint32_t par = (uint32_t)(ediv + trip + carry) & 1u;
+            mbar_wait(bar_ring_full + 8 * st2, par);
+            mbar_wait(bar_aug_full + 8 * st2, par);
+            if (g < 4 || g >= n_half - 4) MT_TRACEW(n, 2200 + g);
+          }
+          tc_fence_after();
+          issue_st(std::integral_constant<int, st2>{}, std::integral_constant<int, hh>{});
+        }
+        // both halves of this query tile are done: dQ = dS K (the last tile's dQ is issued by the caller, behind the
+        // score MMAs of the next item's first tile)
+        if (hh == 1 && g != n_half - 1) issue_dq(tg);
+      };
+      auto trip6 = [&](int g0, int trip, auto... Us) {
+        ((g0 + decltype(Us)::value < n_half ? (half(g0 + decltype(Us)::value, trip, Us), 0) : 0), ...);
+      };
+      for (int g0 = 0, trip = 0; g0 < n_half; g0 += 2 * NQ, ++trip)
+        trip6(g0, trip, std::integral_constant<int, 0>{}, std::integral_constant<int, 1>{},
+              std::integral_constant<int, 2>{}, std::integral_constant<int, 3>{}, std::integral_constant<int, 4>{},
+              std::integral_constant<int, 5>{});
+    };
+    static_assert(NQ == 3, "the issue loop is unrolled for three ring slots");
+    bool have = read_item(0, it);
+    if (have) issue_first(0, 1);             // entry 0 = K / V of the first item, entry 1 = its first Q / dO tile
+    for (n = 0; have; ++n) {
+      n_half = 2 * it.n_q;
+      have_next = false;
+      ++e;                                  // the K / V entry (consumed by the compute warps)
+      switch (e % NQ) {
+        case 0: run_item(std::integral_constant<int, 0>{}); break;
+        case 1: run_item(std::integral_constant<int, 1>{}); break;
+        default: run_item(std::integral_constant<int, 2>{}); break;
+      }
+      // tail of the item: its last dQ, then the score MMAs of the next item's first tile.  (Measured the other way round
+      // -- next item's score MMAs ahead of the last dQ, dK epilogue deferred into the next item's first tile: the
+      // hand-over bubble drops from 2 700 to 1 150 cycles, but the first tile of every item grows by 2 800 and the
+      // launch gets 3 % slower: whatever runs once per item is slow wherever it sits.)
+      issue_dq(ti + it.n_q - 1);
+      if (elect_one()) umma_commit(bar_done);
+      __syncwarp();
+      MT_TRACEW(n, 2900);
+      have_next = read_item(n + 1, nxt);
+      if (have_next) issue_first(n + 1, e + it.n_q + 1);
+      MT_TRACEW(n, 2002);
+      e += it.n_q;
+      ti += it.n_q;
+      it = nxt;
+      have = have_next;
+    }
+    tl_tiles = ti;
+    if (lane == 0) { MT_TRACE_DUMP("mma"); }
+  } else if (warp < W_DRAIN) {
+    // ===== compute: 16 warps, thread = (key row, 16 queries of the current 64-query half tile) =======================
+    const int lane_grp = warp & 3;
+    const int qq = warp >> 2;
+    const int row = lane_grp * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
+    const int sw = row & 7;
+    const float scale_log2 = P.scale_log2, sc = P.scale;
+    const int ctid = threadIdx.x;   // 0..511
+    MT_TRACE_DECL
+    int trn_item = 0;                // trace builds only: the item the hand-over helpers belong to
+
+    // K' / V' of an item -> TMEM from its ring entry (quarter 0 copies K, quarter 1 copies V); columns 48..50 = 1 (the
+    // statistics columns), column 51 of K' = 1 for key rows past the segment's m, the rest 0
+    auto kv_to_tmem = [&](int ent, bool key_ok) {
+      mbar_wait(bar_ring_full + 8 * (ent % NQ), (ent / NQ) & 1);
+      if (qq < 2) {
+        const uint8_t* src = smem + BwdPSmem::RING + (ent % NQ) * 2 * TILE_BYTES + (qq == 0 ? 0 : TILE_BYTES) + row * 128;
+        uint32_t w[32];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const uint4 u = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));
+          w[4 * c] = u.x; w[4 * c + 1] = u.y; w[4 * c + 2] = u.z; w[4 * c + 3] = u.w;
+        }
+        w[24] = 0x3f803f80u;
+        w[25] = (qq == 0 && !key_ok) ? 0x3f803f80u : 0x00003f80u;
+#pragma unroll
+        for (int c = 26; c < 32; ++c) w[c] = 0u;
+        const uint32_t dst = (qq == 0 ? tm_k : tm_v) + t_lane;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r8[8];
+#pragma unroll
+          for (int e2 = 0; e2 < 8; ++e2) r8[e2] = w[8 * c + e2];
+          tmem_st8(dst + c * 8, r8);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_kvt_full);
+      }
+    };
+    // K of an item: ring entry -> its fixed buffer (B operand of every dQ MMA of the item), then the entry is released.
+    // Only legal once the previous item's last dQ MMA has completed (bar_done).
+    auto k_to_buffer = [&](int ent) {
+      const uint8_t* src = smem + BwdPSmem::RING + (ent % NQ) * 2 * TILE_BYTES;
+      uint8_t* dst = smem + BwdPSmem::K;
+      const uint4 a = *reinterpret_cast<const uint4*>(src + ctid * 32);
+      const uint4 b2 = *reinterpret_cast<const uint4*>(src + ctid * 32 + 16);
+      *reinterpret_cast<uint4*>(dst + ctid * 32) = a;
+      *reinterpret_cast<uint4*>(dst + ctid * 32 + 16) = b2;
+      MT_TRACEW(trn_item, 1210);
+      fence_proxy_async_smem();
+      MT_TRACEW(trn_item, 1211);
+      named_bar_sync(2, NCOMP);
+      MT_TRACEW(trn_item, 1212);
+      if (ctid == 0) mbar_arrive(bar_ring_empty + 8 * (ent % NQ));
+    };
+
+    int e = 0, ti = 0;
+    int pending_buf = -1;            // dS^T buffer that still feeds an in-flight dK reduce-add
+    // dK of a finished item: wait until all of its MMAs are done, TMEM -> registers (the accumulator is then free for
+    // the next item), fp32 staging in the dS^T buffer its last tile used, one TMA reduce-add per box.
+    struct Pending { int n, b, col, off, j, ti_last; };
+    auto finish_item = [&](const Pending& pd, int kv_entry_next) {
+      MT_TRACEW(pd.n, 1201);
+      mbar_wait(bar_done, pd.n & 1);       // every MMA of that item has completed
+      MT_TRACEW(pd.n, 1202);
+      tc_fence_after();
+      float a[3][4];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tmem_ld4(tm_dk + t_lane + qq * 12 + c * 4, a[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_acc_free);
+      MT_TRACEW(pd.n, 1203);
+      if (kv_entry_next >= 0) k_to_buffer(kv_entry_next);   // the K buffer is free: that item's last dQ MMA is done
+      MT_TRACEW(pd.n, 1204);
+      uint8_t* stg_k = smem + BwdPSmem::DS + (pd.ti_last & 1) * 2 * TILE_BYTES;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        stage_chunk(stg_k, row, qq * 3 + c, make_float4(a[c][0] * sc, a[c][1] * sc, a[c][2] * sc, a[c][3] * sc));
+      fence_proxy_async_smem();
+      if (ctid == 0) bulk_wait_group_read<0>();   // at most one dK reduce-add in flight (the previous one is long done)
+      named_bar_sync(2, NCOMP);
+      if (ctid == 0) {
+        const uint32_t sk = sbase + BwdPSmem::DS + (pd.ti_last & 1) * 2 * TILE_BYTES;
+#ifndef MT_EXP_SKIP_DKV   // experiment builds only (wrong results): the launch without the dK / dV reduce-adds
+        tma_reduce_add_3d(&dq32_maps.m[pd.b], sk, pd.col, pd.off, pd.j);
+        tma_reduce_add_3d(&dq16_maps.m[pd.b], sk + BwdPSmem::STG16, pd.col + 32, pd.off, pd.j);
+#endif
+        bulk_commit_group();
+      }
+      pending_buf = pd.ti_last & 1;
+      MT_TRACEW(pd.n, 1205);
+    };
+
+    BwdItem it;
+    bool have = read_item(0, it);
+    if (have) {
+      kv_to_tmem(e, (it.k0 + row) < P.geo.b[it.b].m);
+      k_to_buffer(e);
+    }
+    Pending pd;
+#ifdef MT_DEBUG_TIMELINE
+    long long tl_first = 0;
+#endif
+    for (int n = 0; have; ++n) {
+      trn_item = n;
+      ++e;   // past the K / V entry of this item
+      const int n_half = 2 * it.n_q;
+      auto half_tile = [&](int g) {
+        const int i = g >> 1, hh = g & 1;
+        const int tg = ti + i;
+        if (hh == 0 && pending_buf == (tg & 1)) {   // this tile's dS^T buffer still feeds the last dK reduce-add
+          if (ctid == 0) bulk_wait_group_read<0>();
+          named_bar_sync(2, NCOMP);
+          pending_buf = -1;
+        }
+        uint8_t* drow = smem + BwdPSmem::DS + (tg & 1) * 2 * TILE_BYTES + hh * TILE_BYTES + row * 128;
+        const uint32_t ts = tmem + hh * 128 + t_lane + qq * 16, td = ts + 64;
+        mbar_wait(bar_st_full + 8 * hh, tg & 1);
+#ifdef MT_DEBUG_TIMELINE
+        if (g == 0) tl_first = clock64();
+#endif
+        if (g < 4 || g >= n_half - 4) MT_TRACEW(n, 1000 + g);
+        tc_fence_after();
+        float sv[16], dp[16];
+        tmem_ld16(ts, sv);
+        tmem_ld16(td, dp);
+        tmem_ld_wait();
+        uint32_t pk[8], dk[8];
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) {
+          const float p0 = ex2(sv[c] * scale_log2);
+          const float p1 = ex2(sv[c + 1] * scale_log2);
+          pk[c >> 1] = pack_bf16(p0, p1);
+          dk[c >> 1] = pack_bf16(p0 * dp[c], p1 * dp[c + 1]);
+        }
+        tmem_st8(ts, pk);
+        tmem_st8(td, dk);
+        *reinterpret_cast<uint4*>(drow + (((2 * qq) ^ sw) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+        *reinterpret_cast<uint4*>(drow + (((2 * qq + 1) ^ sw) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+        tmem_st_wait();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_pt_full + 8 * hh);
+        if (g < 4 || g >= n_half - 4) MT_TRACEW(n, 1100 + g);
+      };
+#pragma unroll 1
+      for (int g = 0; g < n_half; ++g) half_tile(g);
+#ifdef MT_DEBUG_TIMELINE
+      if (ctid == 0) MT_TL_ITEM(it.n_q, tl_first, clock64());
+#endif
+      pd.n = n; pd.b = it.b; pd.col = E + it.h * DH; pd.off = it.off; pd.j = it.jseg + it.k0;
+      pd.ti_last = ti + it.n_q - 1;
+      ti += it.n_q;
+      e += it.n_q;
+      // ---- hand-over: the next item's K' / V' go to TMEM while the MMA warp finishes this item ----------------------
+      have = read_item(n + 1, it);
+      MT_TRACEW(n, 1200);
+      // S^T / dP^T of this item's last half have completed (st_full): K' / V' in TMEM are free for the next item
+      if (have) kv_to_tmem(e, (it.k0 + row) < P.geo.b[it.b].m);
+      finish_item(pd, have ? e : -1);   // this item's dK; the next item's K into the buffer its dQ MMAs read
+    }
+    if (ctid == 0) bulk_wait_group_read<0>();
+    if (ctid == 0) { MT_TRACE_DUMP("cmp"); }
+  } else {
+    // ===== drain (4 warps, one row per thread): dQ of every query tile, dV of every item ===============================
+    const int lane_grp = warp & 3;
+    const int row = lane_grp * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
+    const float sc = P.scale;
+    const bool leader = threadIdx.x == W_DRAIN * 32;
+    MT_TRACE_DECL
+    int trn_item = -1;
+    uint8_t* stg = smem + BwdPSmem::STG;
+    int ti = 0;
+    // one [128][48] fp32 tile: TMEM -> registers -> staging -> one TMA reduce-add per box at column c0 of dqkv
+    auto drain_tile = [&](uint32_t tm_src, float mul, int b, int c0, int off, int j0, uint32_t free_bar) {
+      float v[3][16];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tmem_ld16(tm_src + t_lane + c * 16, v[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(free_bar);
+      MT_TRACEW(trn_item, 3400);
+      if (leader) bulk_wait_group_read<0>();   // the previous reduce-add has read the staging tile
+      MT_TRACEW(trn_item, 3401);
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int c = 0; c < 12; ++c)
+        stage_chunk(stg, row, c, make_float4(v[c >> 2][(c & 3) * 4] * mul, v[c >> 2][(c & 3) * 4 + 1] * mul,
+                                             v[c >> 2][(c & 3) * 4 + 2] * mul, v[c >> 2][(c & 3) * 4 + 3] * mul));
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (leader) {
+#ifdef MT_EXP_SKIP_DKV
+        if (mul != 1.f)
+#endif
+#ifndef MT_EXP_SKIP_DQ    // experiment builds only (wrong results): the launch without any reduce-add of the drain warps
+        {
+          tma_reduce_add_3d(&dq32_maps.m[b], sbase + BwdPSmem::STG, c0, off, j0);
+          tma_reduce_add_3d(&dq16_maps.m[b], sbase + BwdPSmem::STG + BwdPSmem::STG16, c0 + 32, off, j0);
+        }
+#endif
+        bulk_commit_group();
+      }
+    };
+    for (int n = 0;; ++n) {
+      BwdItem it;
+      if (!read_item(n, it)) break;
+      for (int i = 0; i < it.n_q; ++i, ++ti) {
+        trn_item = (i >= it.n_q - 2) ? n : -1;
+        mbar_wait(bar_dq_full, ti & 1);
+        if (i < 2 || i >= it.n_q - 2) MT_TRACEW(n, 3000 + i);
+        tc_fence_after();
+        drain_tile(tm_dq, sc, it.b, it.h * DH, it.off, it.jseg + i * BT, bar_dq_free);
+        if (i < 2 || i >= it.n_q - 2) MT_TRACEW(n, 3100 + i);
+      }
+      mbar_wait(bar_done, n & 1);
+      MT_TRACEW(n, 3200);
+      tc_fence_after();
+      drain_tile(tm_dv, 1.f, it.b, 2 * E + it.h * DH, it.off, it.jseg + it.k0, bar_acc_free);
+      MT_TRACEW(n, 3300);
+    }
+    if (leader) bulk_wait_group_read<0>();
+    if (leader) { MT_TRACE_DUMP("drn"); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc(tmem, 512);
+  if (threadIdx.x == 0) {
+    if (atomicAdd(work_counter + 1, 1) == (int)gridDim.x - 1) {
+      work_counter[1] = 0;
+      __threadfence();
+      work_counter[0] = 0;
+    }
+  }
+#ifdef MT_DEBUG_TIMELINE
+  if (threadIdx.x == W_MMA * 32) {
+    unsigned sm_;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));
+    long long* e_ = mt_timeline + 4 * blockIdx.x;
+    e_[0] = sm_; e_[1] = tl_tiles; e_[2] = tl_t0_; e_[3] = clock64();
+  }
+#endif
+}
+
 int dilated_attn_bwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc,
-                            const void* dattn, const float* lse, const float* delta_br, float* dqkv, cudaStream_t st) {
+                           const void* dattn, const float* lse, const float* delta_br, float* dqkv, int impl,
+                           cudaStream_t st) {
   Sm100Params P;
   int rc = make_sm100_params(geom, &P);
   if (rc) return rc;
@@ -977,6 +2049,17 @@ int dilated_attn_bwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int
     rc = encode_branch_map_f32(&dq16_maps.m[b], dqkv, 3 * E, n_alloc, P.geo.b[b].r, 16);
     if (rc) return rc;
   }
+  if (impl == 2) {   // persistent CTAs (one per SM) with a device work counter
+    int* counter = next_work_counter();
+    MT_REQUIRE(counter != nullptr, "dilated_attn_bwd: cannot allocate the work counters");
+    const int items = P.item_prefix[P.geo.nb];
+    const int grid = items < kNumSMs ? items : kNumSMs;
+    MT_CUDA(cudaFuncSetAttribute(dilated_bwd_sm100_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 BwdPSmem::TOTAL));
+    dilated_bwd_sm100_persistent_kernel<<<grid, BWD3_THREADS, BwdPSmem::TOTAL, st>>>(maps, do_maps, dq32_maps, dq16_maps, P,
+                                                                                    lse, delta_br, counter);
+    return check_launch("dilated_bwd_sm100_persistent_kernel");
+  }
   MT_CUDA(cudaFuncSetAttribute(dilated_bwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd3Smem::TOTAL));
   dilated_bwd_sm100_kernel<<<P.item_prefix[P.geo.nb], BWD3_THREADS, Bwd3Smem::TOTAL, st>>>(
       maps, do_maps, dq32_maps, dq16_maps, P, lse, delta_br);
@@ -987,6 +2070,17 @@ int dilated_attn_bwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int
 
 #ifdef MT_DEBUG_TIMELINE
 // experiment builds only: copy the CTA timeline to the host ([n][4] long long) and clear it
+extern "C" int mt_debug_item_timeline(long long* dst, int n) {
+  if (n > 65536) n = 65536;
+  cudaDeviceSynchronize();
+  int cnt = 0;
+  if (cudaMemcpyFromSymbol(&cnt, mt::mt_item_count, sizeof(int)) != cudaSuccess) return -1;
+  if (cnt > n) cnt = n;
+  if (cudaMemcpyFromSymbol(dst, mt::mt_item_timeline, sizeof(long long) * 4 * (size_t)cnt) != cudaSuccess) return -1;
+  int zero = 0;
+  cudaMemcpyToSymbol(mt::mt_item_count, &zero, sizeof(int));
+  return cnt;
+}
 extern "C" int mt_debug_timeline(long long* dst, int n) {
   if (n > 32768) n = 32768;
   cudaDeviceSynchronize();

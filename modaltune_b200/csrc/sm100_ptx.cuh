@@ -33,19 +33,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must not hang the GPU.  The hot loop is try_wait + branch only (the instruction itself
-// suspends the warp for a hardware time slice); the clock is consulted once per 1024 failed polls and the kernel traps
-// after ~2 s, so a broken protocol surfaces as a launch error instead of a hung box.
+// Bounded wait: a protocol bug must not hang the GPU.  try_wait suspends the warp in hardware for a time slice; the
+// clock is consulted once per 4096 failed polls and the kernel traps after ~2 s, so a broken protocol surfaces as a
+// launch error instead of a hung box.  The wait is inlined dozens of times per kernel and the persistent kernels run
+// their item hand-over code once per item (cold in the instruction cache), so the slow path is kept to a few
+// instructions: no printf, no argument set-up (compile with -DMT_DEBUG_WAIT to get the barrier address printed).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (true) {
+  uint32_t polls = 0;
 #pragma unroll 1
-    for (int i = 0; i < 1024; ++i)
-      if (mbar_try_wait(bar, parity)) return;
-    if (clock64() - t0 > 4000000000ll) {
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++polls & 4095u) == 0 && clock64() - t0 > 4000000000ll) {
+#ifdef MT_DEBUG_WAIT
       printf("modaltune_b200: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
              parity);
+#endif
       __trap();
     }
   }

@@ -15,6 +15,8 @@ from modaltune_b200 import ops  # noqa: E402
 from modaltune_b200.slide_encoder import DILATED_RATIO, optimal_segment_lengths  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 10001
+FWD_IMPL = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+BWD_IMPL = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 dev = "cuda"
 SMS = 148
 
@@ -62,14 +64,14 @@ lse = torch.full((N, 16), 6.0, device=dev)
 cases = [(sl, r) for sl, r in zip(optimal_segment_lengths(), DILATED_RATIO)]
 cases += [(256, 1), (512, 1), (2048, 1), (4096, 1), (16384, 1), (2048, 2), (4096, 4)]
 rows = []
-print(f"N = {N}; cycles at 1.9 GHz; tile pair = 128 queries x 128 keys of one head")
+print(f"N = {N}; fwd impl {FWD_IMPL}, bwd impl {BWD_IMPL}; cycles at 1.9 GHz; tile pair = 128 queries x 128 keys of one head")
 print(f"{'branch':>14} {'CTAs':>6} {'pairs':>7} {'len':>5} | {'fwd ms':>8} {'cyc/pair/SM':>12} | {'bwd ms':>8} {'cyc/pair/SM':>12}")
 for sl, r in cases:
     geom = ops.Geometry(N, [sl], [r])
     ctas, pairs = count(N, sl, r)
     delta = torch.zeros(geom.lse_elems, device=dev)
-    tf = med(lambda: ops.dilated_attn_fwd(geom, qkv, 1))
-    tb = med(lambda: ops.dilated_attn_bwd(geom, qkv, dattn, lse, delta, 1))
+    tf = med(lambda: ops.dilated_attn_fwd(geom, qkv, FWD_IMPL))
+    tb = med(lambda: ops.dilated_attn_bwd(geom, qkv, dattn, lse, delta, BWD_IMPL))
     cf, cb = tf * 1e-3 * 1.9e9 * SMS / pairs, tb * 1e-3 * 1.9e9 * SMS / pairs
     rows.append((ctas, pairs, tf, tb))
     print(f"{sl:>9}/r{r:<3} {ctas:>6} {pairs:>7} {pairs / ctas:>5.1f} | {tf:>8.4f} {cf:>12.0f} | {tb:>8.4f} {cb:>12.0f}")
@@ -84,8 +86,8 @@ for name, col in (("fwd", 2), ("bwd", 3)):
           f"(per SM; the forward runs 2 CTAs per SM)")
 geom = ops.Geometry.get(N, optimal_segment_lengths(), DILATED_RATIO)
 delta = torch.zeros(geom.lse_elems, device=dev)
-tf = med(lambda: ops.dilated_attn_fwd(geom, qkv, 1))
-tb = med(lambda: ops.dilated_attn_bwd(geom, qkv, dattn, lse, delta, 1))
+tf = med(lambda: ops.dilated_attn_fwd(geom, qkv, FWD_IMPL))
+tb = med(lambda: ops.dilated_attn_bwd(geom, qkv, dattn, lse, delta, BWD_IMPL))
 f, b = ops.attention_flops(geom)
 print(f"all five branches in one launch: fwd {tf:.4f} ms = {f / tf / 1e9:.0f} TFLOP/s, bwd {tb:.4f} ms = {b / tb / 1e9:.0f} TFLOP/s; "
       f"sum of the five single-branch launches: fwd {sum(r_[2] for r_ in rows[:5]):.4f} bwd {sum(r_[3] for r_ in rows[:5]):.4f}")

@@ -18,6 +18,8 @@ from modaltune_b200 import _lib, ops  # noqa: E402
 from modaltune_b200.slide_encoder import DILATED_RATIO, optimal_segment_lengths  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 10001
+FWD_IMPL = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+BWD_IMPL = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 dev = "cuda"
 lib = _lib.load()
 lib.mt_debug_timeline.restype = ctypes.c_int
@@ -76,13 +78,40 @@ qkv = qkv.to(torch.bfloat16).to(dev)
 gamma, beta = torch.ones(768, device=dev), torch.zeros(768, device=dev)
 dy = torch.randn(N, 768, generator=g).to(dev)
 for _ in range(2):
-    o, l = ops.dilated_attn_fwd(geom, qkv, 1)
+    o, l = ops.dilated_attn_fwd(geom, qkv, FWD_IMPL)
     y, _, lse, m, r = ops.dilated_merge_ln_fwd(geom, o, l, gamma, beta)
     dattn, delta = ops.dilated_merge_ln_bwd(geom, dy, o, l, gamma, m, r)
-    dq = ops.dilated_attn_bwd(geom, qkv, dattn, lse, delta, 1)
+    dq = ops.dilated_attn_bwd(geom, qkv, dattn, lse, delta, BWD_IMPL)
 torch.cuda.synchronize()
 timeline()
-o, l = ops.dilated_attn_fwd(geom, qkv, 1)
-report(f"forward N={N}", timeline(), 2)
-dq = ops.dilated_attn_bwd(geom, qkv, dattn, lse, delta, 1)
-report(f"backward N={N}", timeline(), 1)
+o, l = ops.dilated_attn_fwd(geom, qkv, FWD_IMPL)
+report(f"forward impl {FWD_IMPL} N={N}", timeline(), 2)
+dq = ops.dilated_attn_bwd(geom, qkv, dattn, lse, delta, BWD_IMPL)
+report(f"backward impl {BWD_IMPL} N={N}", timeline(), 1)
+
+# ---- per-item records of the persistent backward (impl 2): time inside an item vs the bubble between two items ---------
+if BWD_IMPL == 2:
+    lib.mt_debug_item_timeline.restype = ctypes.c_int
+    lib.mt_debug_item_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    buf = np.zeros((65536, 4), dtype=np.int64)
+    cnt = lib.mt_debug_item_timeline(buf.ctypes.data, 65536)   # includes the warm-up launches: keep the last launch
+    dq = ops.dilated_attn_bwd(geom, qkv, dattn, lse, delta, BWD_IMPL)
+    cnt = lib.mt_debug_item_timeline(buf.ctypes.data, 65536)
+    rec = buf[:cnt]
+    inside = rec[:, 3] - rec[:, 2]
+    A = np.stack([rec[:, 1].astype(np.float64), np.ones(cnt)], 1)
+    (a_in, b_in), *_ = np.linalg.lstsq(A, inside.astype(np.float64), rcond=None)
+    bubbles, after_len = [], []
+    for c in np.unique(rec[:, 0]):
+        r = rec[rec[:, 0] == c]
+        r = r[np.argsort(r[:, 2])]
+        bubbles += list(r[1:, 2] - r[:-1, 3])
+        after_len += list(r[:-1, 1])
+    bubbles, after_len = np.array(bubbles), np.array(after_len)
+    print(f"persistent backward, {cnt} items: first score tile -> last P^T of an item = {a_in:.0f} cycles x loop length + {b_in:.0f}")
+    print(f"   bubble between the last half tile of an item and the first score tile of the next: median {np.median(bubbles):.0f}, "
+          f"mean {bubbles.mean():.0f}, p10 {np.percentile(bubbles, 10):.0f}, p90 {np.percentile(bubbles, 90):.0f} cycles")
+    for L in np.unique(rec[:, 1]):
+        m = rec[:, 1] == L
+        print(f"      loop length {L:3d}: {m.sum():5d} items, inside median {np.median(inside[m]):8.0f} -> {np.median(inside[m]) / L:6.0f} per tile; "
+              f"bubble after such an item: median {np.median(bubbles[after_len == L]) if (after_len == L).any() else 0:.0f}")
