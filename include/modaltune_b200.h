@@ -106,6 +106,41 @@ int mt_gelu_ln_bwd(const void* dy, int dy_dtype, const void* h, int h_dtype, con
                    const float* mean,
                    const float* rstd, void* dh, int dh_dtype, int64_t rows, int64_t cols, void* stream);
 
+/* ---- A2 / A6: the frozen linear layers of an encoder layer on the tensor cores, epilogues fused ---------------------
+ * replaces: q/k/v_proj, out_proj (torchscale/component/multihead_attention.py:44-54), fc1 / GELU / ffn_layernorm / fc2
+ * (feedforward_network.py:132-143), the residual adds of EncoderLayer.forward (architecture/encoder.py:152-175) and
+ * the dX GEMMs of their backward (all encoder weights are frozen).
+ * C[M, N] = A[M, K] . W[N, K]^T with bf16 operands (row strides lda / ldw in elements), fp32 accumulation in TMEM;
+ * N must be a multiple of 256 and K of 64.  What happens to the accumulator is the epilogue `mode`:
+ *   MT_EPI_PLAIN        out = acc [+ bias] [+ residual]                       (f32 and / or bf16 output)
+ *   MT_EPI_GELU_STATS   out_f32 = h = acc + bias;  out_bf16 = u = gelu_erf(h);  stats[row][slab] = (sum u, sum u^2) of the
+ *                       ROUNDED u over each 128-column slab (`stats` is [M, N / 128, 2], every entry written once, no
+ *                       atomics: deterministic): fc1 + GELU + the statistics of ffn_layernorm
+ *   MT_EPI_LN_RESIDUAL  out = residual + rstd[row] * (acc - mean[row] * col_c1) + col_c2 with mean / rstd from the
+ *                       ln_cols / 128 slab partials of `stats` (added in a fixed order) over `ln_cols` columns: fc2 applied to LayerNorm(u) WITHOUT materialising it, for
+ *                       W = W2 diag(gamma), col_c1 = W 1, col_c2 = W2 beta + b2, + the residual add. */
+#define MT_EPI_PLAIN 0
+#define MT_EPI_GELU_STATS 3
+#define MT_EPI_LN_RESIDUAL 4
+typedef struct {
+  int32_t mode;
+  int32_t ln_cols;          /* MT_EPI_LN_RESIDUAL: number of columns the statistics were taken over (3072)      */
+  float ln_eps;
+  float reserved;
+  const float* bias;        /* [N] or NULL                                                                        */
+  const float* residual;    /* [M, N] f32 or NULL, row stride ld_residual                                        */
+  const float* col_c1;      /* [N]                                                                                */
+  const float* col_c2;      /* [N]                                                                                */
+  float* stats;             /* [M, cols / 128, 2] slab partials (see the modes)                                   */
+  float* ln_mean_out;       /* MT_EPI_LN_RESIDUAL: [M] or NULL, the row mean / rstd derived from stats, written   */
+  float* ln_rstd_out;       /*   once per row (what the backward of the folded LayerNorm needs)                    */
+  float* out_f32;           /* [M, N] or NULL, row stride ld_out_f32 (0 = N)                                     */
+  void* out_bf16;           /* [M, N] or NULL, row stride ld_out_bf16 (0 = N)                                    */
+  int64_t ld_out_f32, ld_out_bf16, ld_residual;
+} mt_linear_epilogue;
+int mt_linear_sm100(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t M, int64_t N, int64_t K,
+                    const mt_linear_epilogue* epilogue, void* stream);
+
 /* ---- A3/A4: dilated attention, all branches, per-branch outputs ---------------------------------------------------
  * replaces: DilatedAttention.gathering x3 + attention_ops -> flash_attn_func, 5 times per layer
  * (torchscale/component/dilated_attention.py:82-111,216-252; multihead_attention.py:109-119; flash_attention.py:11-28).

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmodaltune_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["abi.cu", "elementwise.cu", "cross_attn.cu", "dilated_simt.cu", "dilated_sm100.cu"]
+SOURCES = ["abi.cu", "elementwise.cu", "cross_attn.cu", "dilated_simt.cu", "dilated_sm100.cu", "gemm_sm100.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

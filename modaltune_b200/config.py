@@ -21,7 +21,20 @@ _state = {
     # the three task passes of a step on separate CUDA streams (parallel branches of the captured graph): ~8 % faster
     # at 10k tiles; MODALTUNE_B200_PASS_STREAMS=0 runs them back to back on one stream
     "pass_streams": os.environ.get("MODALTUNE_B200_PASS_STREAMS", "1") != "0",
+    # frozen linear layers of the encoder in bf16 mode: "sm100" = the hand-written tcgen05 GEMM with fused epilogues
+    # (mt_linear_sm100), "cublas" = library GEMMs + separate element-wise kernels (the round-1 path, kept for comparison)
+    "gemm": os.environ.get("MODALTUNE_B200_GEMM", "sm100"),
 }
+
+
+def gemm_impl() -> str:
+    """Which GEMM runs the frozen encoder linears in bf16 mode (fp32 mode always uses exact fp32 cuBLAS GEMMs)."""
+    return _state["gemm"] if _state["mode"] == "bf16" else "cublas"
+
+
+def set_gemm_impl(impl: str) -> None:
+    assert impl in ("sm100", "cublas")
+    _state["gemm"] = impl
 
 
 def pass_streams() -> bool:
@@ -73,13 +86,15 @@ def attn_impl(direction: str = "fwd") -> int:
 
 
 @contextlib.contextmanager
-def using(mode: str | None = None, attn_impl: str | None = None):
+def using(mode: str | None = None, attn_impl: str | None = None, gemm: str | None = None):
     old = dict(_state)
     try:
         if mode is not None:
             set_mode(mode)
         if attn_impl is not None:
             set_attn_impl(attn_impl)
+        if gemm is not None:
+            set_gemm_impl(gemm)
         yield
     finally:
         _state.update(old)

@@ -1,0 +1,407 @@
+// Frozen-linear GEMMs of the LongNet encoder layer on the 5th-generation tensor cores (sm_100a), with the element-wise
+// work that follows each projection fused into the epilogue.
+//
+//     C[M, N] = A[M, K] . W[N, K]^T        A = activations (bf16, row-major), W = nn.Linear weight (bf16, [out, in])
+//
+// replaces, per encoder layer (torchscale/component/multihead_attention.py:44-54, feedforward_network.py:132-143,
+// architecture/encoder.py:137-175): the q/k/v projection (+ bias), out_proj (+ bias + residual add), fc1 (+ bias + GELU
+// + the row statistics of ffn_layernorm), fc2 (ffn_layernorm folded in algebraically + bias + residual add), and the
+// dX GEMMs of the backward (every encoder weight is frozen: no dW).
+//
+// One persistent CTA per SM walks the 128 x 256 output tiles (n fastest: the ~12 row blocks in flight and the whole
+// weight stay in L2).  Warp roles: warp 0 = TMA producer (A 128 x 64 and W 256 x 64 bf16 boxes, 128-byte swizzle, 4-stage
+// ring), warp 1 = tcgen05.mma issuer (M 128, N 256, K 16; fp32 accumulators in TMEM, two 256-column accumulators so that
+// the epilogue of tile t overlaps the main loop of tile t + 1), warps 2-9 = epilogue (TMEM lane = output row; warps w and
+// w + 4 share 32 rows and take 128 columns each).
+//
+// LayerNorm folding (fc2): fc2(LN(u)) = rstd * (u W2'^T - mean * c1) + c2 with W2' = W2 diag(gamma), c1 = W2' 1,
+// c2 = W2 beta + b2 -- all constants of the frozen layer -- so the normalised [M, 3072] tensor is never written: fc1's
+// epilogue emits gelu(h) in bf16 plus per-row (sum, sum of squares), fc2's epilogue applies mean / rstd per row.
+#include <cuda.h>
+
+#include <cstring>
+
+#include "mt_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace mt {
+using namespace sm100;
+
+namespace gemm {
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;        // 16 KB
+constexpr int B_BYTES = BN * BK * 2;        // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int THREADS = 32 * 10;            // TMA, MMA, 8 epilogue warps
+constexpr int SMEM_STG = STAGES * STAGE_BYTES;          // 8 epilogue warps x [32 rows][32 floats], 128-byte swizzle
+constexpr int STG_BYTES = 32 * 128;
+constexpr int SMEM_BAR = SMEM_STG + 8 * STG_BYTES;
+constexpr int NBAR = 2 * STAGES + 4;        // full[S], empty[S], acc_full[2], acc_empty[2]
+constexpr int SMEM_TMEM_PTR = SMEM_BAR + NBAR * 8;
+constexpr int SMEM_TOTAL = SMEM_TMEM_PTR + 16;
+
+struct Params {
+  int M, N, K;
+  int mode;
+  const float* bias;        // [N] or null
+  const float* residual;    // [M, N] f32 (modes 2, 4)
+  const float* col_c1;      // [N] (mode 4)
+  const float* col_c2;      // [N] (mode 4)
+  float* stats;             // [M, cols / 128, 2]: (sum, sum of squares) per 128-column slab: written in mode 3, read in mode 4
+  float* mean_out;          // mode 4: [M] or null
+  float* rstd_out;
+  float* out_f32;           // [M, N] or null
+  __nv_bfloat16* out_bf16;  // [M, N] or null
+  int64_t ld_f32, ld_bf16, ld_res;
+  float ln_eps;
+  float inv_ln_cols;        // 1 / (number of columns the statistics were summed over)
+  int ln_parts;             // mode 4: partial sums per row = ln_cols / 128
+};
+
+// gelu(x) = x * Phi(x) with erf from Abramowitz-Stegun 7.1.26 (absolute error 1.5e-7: fp32-level; two MUFU ops)
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;   // 1 / (1 + p z): the approximate reciprocal is one MUFU op (1 ulp), __frcp_rn is a software routine
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = ex2(-z * z * 1.4426950408889634f);
+  const float erf_abs = 1.f - p * t * e;                 // erf(|x| / sqrt 2)
+  const float half_x = 0.5f * x;
+  return fmaf(copysignf(erf_abs, x), half_x, half_x);     // 0.5 x (1 + erf(x / sqrt 2))
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+linear_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_c, const Params P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((sbase & 1023u) != 0) __trap();
+  const uint32_t bar_full = sbase + SMEM_BAR;
+  const uint32_t bar_empty = bar_full + 8 * STAGES;
+  const uint32_t bar_acc_full = bar_empty + 8 * STAGES;   // [2]
+  const uint32_t bar_acc_empty = bar_acc_full + 16;        // [2]
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_TMEM_PTR);
+
+  const int m_tiles = (P.M + BM - 1) / BM, n_tiles = P.N / BN, k_blocks = P.K / BK;
+  const int tiles = m_tiles * n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_acc_full + 8 * i, 1);
+      mbar_init(bar_acc_empty + 8 * i, 256);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    if (P.out_f32 != nullptr) tma_prefetch_desc(&map_c);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer ===============================================================================================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int st = it % STAGES;
+          mbar_wait(bar_empty + 8 * st, ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(bar_full + 8 * st, STAGE_BYTES);
+          const uint32_t dst = sbase + st * STAGE_BYTES;
+          tma_load_2d(dst, &map_a, bar_full + 8 * st, kb * BK, m0);
+          tma_load_2d(dst + A_BYTES, &map_b, bar_full + 8 * st, kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =================================================================================================
+    constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 0, 0);
+    const uint64_t a_desc0 = umma_smem_desc(sbase, 16, 1024);
+    const uint64_t b_desc0 = umma_smem_desc(sbase + A_BYTES, 16, 1024);
+    int it = 0, tl = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++tl) {
+      const int buf = tl & 1;
+      mbar_wait(bar_acc_empty + 8 * buf, ((tl >> 1) & 1) ^ 1);   // the epilogue has read this accumulator
+      tc_fence_after();
+      const uint32_t acc = tmem + buf * BN;
+      for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const int st = it % STAGES;
+        mbar_wait(bar_full + 8 * st, (it / STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ad = umma_desc_adv(a_desc0, (uint32_t)st * STAGE_BYTES);
+          const uint64_t bd = umma_desc_adv(b_desc0, (uint32_t)st * STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_ss(acc, umma_desc_adv(ad, k * 32), umma_desc_adv(bd, k * 32), IDESC, (kb > 0) || (k > 0));
+          umma_commit(bar_empty + 8 * st);
+          if (kb == k_blocks - 1) umma_commit(bar_acc_full + 8 * buf);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue: 8 warps, thread = (output row, 128 of the 256 tile columns) ======================================
+    const int ew = warp - 2;
+    const int lane_grp = warp & 3;                 // TMEM lanes this warp may touch: 32 * (warp id % 4)
+    const int half = ew >> 2;                      // which 128 columns
+    const int row_in_tile = lane_grp * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
+    // fp32 outputs leave through a per-warp staging tile and TMA stores: a thread owns a ROW of the accumulator, so
+    // direct stores touch 32 different rows per instruction (measured: the GEMM became epilogue-bound, 480 against
+    // cuBLAS's 620 TFLOP/s); staged, every global write is a full 128-byte line
+    uint8_t* stg = smem + SMEM_STG + ew * STG_BYTES;
+    const uint32_t stg_u32 = sbase + SMEM_STG + ew * STG_BYTES;
+    auto store_f32_chunk = [&](const float (&o)[32], int col, int row0) {
+      if (lane == 0) bulk_wait_group_read<0>();       // the previous store of this warp has read the staging tile
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(stg + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+            make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&map_c, stg_u32, col, row0);
+        bulk_commit_group();
+      }
+    };
+    int tl = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++tl) {
+      const int buf = tl & 1;
+      const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN + half * 128;
+      const int row = m0 + row_in_tile;
+      const bool row_ok = row < P.M;
+      mbar_wait(bar_acc_full + 8 * buf, (tl >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem + buf * BN + half * 128 + t_lane;
+      float mean = 0.f, rstd = 1.f;
+      if (P.mode == 4 && row_ok) {
+        // the partial (sum, sum of squares) of every 128-column slab of the producing GEMM, added in a fixed order:
+        // deterministic, and nobody has to zero the buffer
+        const float2* part = reinterpret_cast<const float2*>(P.stats) + (int64_t)row * P.ln_parts;
+        float2 ss = make_float2(0.f, 0.f);
+        for (int i = 0; i < P.ln_parts; ++i) {
+          const float2 pi = part[i];
+          ss.x += pi.x;
+          ss.y += pi.y;
+        }
+        mean = ss.x * P.inv_ln_cols;
+        const float var = fmaxf(ss.y * P.inv_ln_cols - mean * mean, 0.f);
+        rstd = rsqrtf(var + P.ln_eps);
+        if (P.mean_out != nullptr && n0 == 0) {      // one thread per row publishes the statistics for the backward
+          P.mean_out[row] = mean;
+          P.rstd_out[row] = rstd;
+        }
+      }
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 32) {
+        float v[32];
+        tmem_ld32(acc + c, v);
+        tmem_ld_wait();
+        if (c == 96) {                             // the whole accumulator is in registers: release it to the MMA warp
+          tc_fence_before();
+          mbar_arrive(bar_acc_empty + 8 * buf);
+        }
+        const int col = n0 + c;
+        const int row0 = m0 + lane_grp * 32;      // first row of this warp's 32-row slab (rows >= M are clipped by TMA)
+        if (P.mode == 3) {
+          // h = acc + bias (kept in fp32 for the backward), u = gelu(h) in bf16 for fc2, row statistics of the ROUNDED u
+          float h[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(P.bias + col + i);
+            h[i] = v[i] + b.x; h[i + 1] = v[i + 1] + b.y; h[i + 2] = v[i + 2] + b.z; h[i + 3] = v[i + 3] + b.w;
+          }
+          store_f32_chunk(h, col, row0);
+          if (!row_ok) continue;
+          __nv_bfloat16* ob = P.out_bf16 + (int64_t)row * P.ld_bf16 + col;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 u2 = __floats2bfloat162_rn(gelu_erf(h[i + 2 * j]), gelu_erf(h[i + 2 * j + 1]));
+              const float2 f = __bfloat1622float2(u2);
+              s1 += f.x + f.y;
+              s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, s2));
+              w[j] = *reinterpret_cast<const uint32_t*>(&u2);
+            }
+            *reinterpret_cast<uint4*>(ob + i) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        } else {
+          float o[32];
+          if (P.mode == 4) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 c1 = *reinterpret_cast<const float4*>(P.col_c1 + col + i);
+              const float4 c2 = *reinterpret_cast<const float4*>(P.col_c2 + col + i);
+              o[i] = fmaf(rstd, fmaf(-mean, c1.x, v[i]), c2.x);
+              o[i + 1] = fmaf(rstd, fmaf(-mean, c1.y, v[i + 1]), c2.y);
+              o[i + 2] = fmaf(rstd, fmaf(-mean, c1.z, v[i + 2]), c2.z);
+              o[i + 3] = fmaf(rstd, fmaf(-mean, c1.w, v[i + 3]), c2.w);
+            }
+          } else if (P.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(P.bias + col + i);
+              o[i] = v[i] + b.x; o[i + 1] = v[i + 1] + b.y; o[i + 2] = v[i + 2] + b.z; o[i + 3] = v[i + 3] + b.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = v[i];
+          }
+          if (P.residual != nullptr && row_ok) {
+            const float* rs = P.residual + (int64_t)row * P.ld_res + col;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 r = *reinterpret_cast<const float4*>(rs + i);
+              o[i] += r.x; o[i + 1] += r.y; o[i + 2] += r.z; o[i + 3] += r.w;
+            }
+          }
+          if (P.out_f32 != nullptr) store_f32_chunk(o, col, row0);
+          if (P.out_bf16 != nullptr && row_ok) {
+            __nv_bfloat16* ob = P.out_bf16 + (int64_t)row * P.ld_bf16 + col;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8)
+              *reinterpret_cast<uint4*>(ob + i) = make_uint4(pack_bf16(o[i], o[i + 1]), pack_bf16(o[i + 2], o[i + 3]),
+                                                             pack_bf16(o[i + 4], o[i + 5]), pack_bf16(o[i + 6], o[i + 7]));
+          }
+        }
+      }
+      if (P.mode == 3 && row_ok)   // this thread's 128-column slab of the row: slab index = n0 / 128 of N / 128
+        reinterpret_cast<float2*>(P.stats)[(int64_t)row * (P.N / 128) + n0 / 128] = make_float2(s1, s2);
+    }
+    if (lane == 0) bulk_wait_group_read<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// row-major [rows, ld] fp32 output, box = [32 rows][32 columns] (one 128-byte swizzle atom per row)
+static int encode_out_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return MT_E_UNSUPPORTED;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for a [%lld, %lld] fp32 output", (int)rc, (long long)rows, (long long)cols);
+    return MT_E_BADARG;
+  }
+  return 0;
+}
+
+// row-major [rows, ld] bf16 matrix, box = [box_rows][64 columns], 128-byte swizzle, rows past the end read as zero
+static int encode_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return MT_E_UNSUPPORTED;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for a [%lld, %lld] bf16 matrix", (int)rc, (long long)rows, (long long)cols);
+    return MT_E_BADARG;
+  }
+  return 0;
+}
+}  // namespace gemm
+}  // namespace mt
+
+using namespace mt;
+
+extern "C" int mt_linear_sm100(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t M, int64_t N, int64_t K,
+                               const mt_linear_epilogue* ep, void* stream) {
+  MT_REQUIRE(a != nullptr && w != nullptr && ep != nullptr, "linear_sm100: NULL argument");
+  MT_REQUIRE(M > 0 && N > 0 && K > 0 && N % gemm::BN == 0 && K % gemm::BK == 0,
+             "linear_sm100: N must be a multiple of 256 and K a multiple of 64 (got M=%lld N=%lld K=%lld)", (long long)M,
+             (long long)N, (long long)K);
+  MT_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)w & 15) == 0,
+             "linear_sm100: operands must be 16-byte aligned with row strides that are multiples of 8 elements");
+  MT_REQUIRE(ep->mode == MT_EPI_PLAIN || ep->mode == MT_EPI_GELU_STATS || ep->mode == MT_EPI_LN_RESIDUAL, "linear_sm100: bad epilogue mode %d", ep->mode);
+  MT_REQUIRE(ep->out_f32 != nullptr || ep->out_bf16 != nullptr, "linear_sm100: no output");
+  if (ep->mode == MT_EPI_GELU_STATS)
+    MT_REQUIRE(ep->bias && ep->out_f32 && ep->out_bf16 && ep->stats, "linear_sm100: GELU epilogue needs bias, both outputs, stats");
+  if (ep->mode == MT_EPI_LN_RESIDUAL)
+    MT_REQUIRE(ep->col_c1 && ep->col_c2 && ep->stats && ep->ln_cols > 0, "linear_sm100: LN-fold epilogue needs c1, c2, stats, ln_cols");
+  gemm::Params P;
+  P.M = (int)M; P.N = (int)N; P.K = (int)K;
+  P.mode = ep->mode;
+  P.bias = ep->bias; P.residual = ep->residual; P.col_c1 = ep->col_c1; P.col_c2 = ep->col_c2; P.stats = ep->stats;
+  P.mean_out = ep->ln_mean_out; P.rstd_out = ep->ln_rstd_out;
+  MT_REQUIRE((P.mean_out == nullptr) == (P.rstd_out == nullptr), "linear_sm100: ln_mean_out and ln_rstd_out go together");
+  P.out_f32 = ep->out_f32; P.out_bf16 = (__nv_bfloat16*)ep->out_bf16;
+  P.ld_f32 = ep->ld_out_f32 ? ep->ld_out_f32 : N;
+  P.ld_bf16 = ep->ld_out_bf16 ? ep->ld_out_bf16 : N;
+  P.ld_res = ep->ld_residual ? ep->ld_residual : N;
+  P.ln_eps = ep->ln_eps;
+  P.inv_ln_cols = ep->ln_cols > 0 ? 1.0f / (float)ep->ln_cols : 0.f;
+  P.ln_parts = ep->ln_cols / 128;
+  MT_REQUIRE(ep->mode != MT_EPI_LN_RESIDUAL || ep->ln_cols % 128 == 0, "linear_sm100: ln_cols must be a multiple of 128");
+  MT_REQUIRE(P.ld_f32 % 4 == 0 && P.ld_bf16 % 8 == 0 && P.ld_res % 4 == 0, "linear_sm100: output row strides must keep 16-byte alignment");
+  CUtensorMap map_a, map_b, map_c;
+  memset(&map_c, 0, sizeof(map_c));
+  int rc = gemm::encode_2d(&map_a, a, M, K, lda, gemm::BM);
+  if (rc) return rc;
+  rc = gemm::encode_2d(&map_b, w, N, K, ldw, gemm::BN);
+  if (rc) return rc;
+  if (ep->out_f32 != nullptr) {
+    MT_REQUIRE(((uintptr_t)ep->out_f32 & 15) == 0, "linear_sm100: the fp32 output must be 16-byte aligned");
+    rc = gemm::encode_out_f32(&map_c, ep->out_f32, M, N, P.ld_f32);
+    if (rc) return rc;
+  }
+  const int tiles = (int)((M + gemm::BM - 1) / gemm::BM * (N / gemm::BN));
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  MT_CUDA(cudaFuncSetAttribute(gemm::linear_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_TOTAL));
+  gemm::linear_sm100_kernel<<<grid, gemm::THREADS, gemm::SMEM_TOTAL, (cudaStream_t)stream>>>(map_a, map_b, map_c, P);
+  return check_launch("linear_sm100_kernel");
+}

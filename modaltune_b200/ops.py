@@ -322,6 +322,37 @@ def cross_attn_bwd(q, k, v, o, d_o, lse, heads: int):
     return dq, dk, dv
 
 
+def linear_sm100(a: torch.Tensor, w: torch.Tensor, mode: int = _lib.MT_EPI_PLAIN, bias=None, residual=None,
+                 want_f32: bool = True, want_bf16: bool = False, stats=None, col_c1=None, col_c2=None, ln_cols: int = 0,
+                 eps: float = LN_EPS, out_f32=None, out_bf16=None, ln_mean_out=None, ln_rstd_out=None):
+    """C = A W^T on the tcgen05 tensor cores with a fused epilogue (``mt_linear_sm100``): a [M, K] bf16, w [N, K] bf16
+    (nn.Linear layout).  Returns (out_f32 or None, out_bf16 or None).  See include/modaltune_b200.h for the modes."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    assert a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == w.shape[1]
+    M, K = a.shape
+    N = w.shape[0]
+    if out_f32 is None and want_f32:
+        out_f32 = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    if out_bf16 is None and want_bf16:
+        out_bf16 = torch.empty((M, N), device=a.device, dtype=torch.bfloat16)
+    ep = _lib.LinearEpilogue()
+    ep.mode, ep.ln_cols, ep.ln_eps = int(mode), int(ln_cols), float(eps)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    for t in (bias, residual, col_c1, col_c2, stats):
+        assert t is None or (t.is_cuda and t.dtype == torch.float32)
+    ep.bias, ep.residual, ep.col_c1, ep.col_c2, ep.stats = ptr(bias), ptr(residual), ptr(col_c1), ptr(col_c2), ptr(stats)
+    ep.out_f32, ep.out_bf16 = ptr(out_f32), ptr(out_bf16)
+    ep.ln_mean_out, ep.ln_rstd_out = ptr(ln_mean_out), ptr(ln_rstd_out)
+    ep.ld_out_f32 = out_f32.stride(0) if out_f32 is not None else 0
+    ep.ld_out_bf16 = out_bf16.stride(0) if out_bf16 is not None else 0
+    ep.ld_residual = residual.stride(0) if residual is not None else 0
+    with _timed("linear_sm100"):
+        rc = _lib.load().mt_linear_sm100(ctypes.c_void_p(a.data_ptr()), a.stride(0), ctypes.c_void_p(w.data_ptr()),
+                                         w.stride(0), M, N, K, ctypes.byref(ep), _stream())
+    _check(rc, "mt_linear_sm100")
+    return out_f32, out_bf16
+
+
 def embed_assemble(proj, bias, coords, table, cls, tile_size: float = 256.0):
     """proj [L, E] (GEMM output), coords [L, 2] -> x [L+1, E] fp32 with the sincos positions and the cls row."""
     L, E = proj.shape
@@ -531,6 +562,19 @@ class FrozenLayerWeights:
             self.ln2 = (f(layer.final_layer_norm.weight), f(layer.final_layer_norm.bias))
             self.ln_in = (f(sa.inner_attn_ln.weight), f(sa.inner_attn_ln.bias))
             self.ln_ffn = (f(ffn.ffn_layernorm.weight), f(ffn.ffn_layernorm.bias))
+            if dtype == torch.bfloat16:
+                # ffn_layernorm folded into fc2 (mt_linear_sm100, MT_EPI_LN_RESIDUAL): W2' = W2 diag(gamma), c1 = W2' 1
+                # (over the ROUNDED W2', what the tensor cores multiply), c2 = W2 beta + b2 in fp32
+                w2 = ffn.fc2.weight.detach().float()
+                self.w_2g = (w2 * self.ln_ffn[0][None, :]).to(dtype).contiguous()
+                self.c1_2 = self.w_2g.float().sum(1).contiguous()
+                self.c2_2 = (w2 @ self.ln_ffn[1] + self.b_2).contiguous()
+                self.b_qkv32 = self.b_qkv.float().contiguous()
+                # [in, out] copies: the B operand of the dX GEMMs (C = dY W  ==  dY (W^T)^T)
+                self.w_qkv_t = self.w_qkv.t().contiguous()
+                self.w_o_t = self.w_o.t().contiguous()
+                self.w_1_t = self.w_1.t().contiguous()
+                self.w_2_t = self.w_2.t().contiguous()
         self.key = key
         return self
 
@@ -566,10 +610,71 @@ def _qkv_project(h1: torch.Tensor, W: FrozenLayerWeights, geom: Geometry) -> tor
     return qkv
 
 
+def _use_sm100_gemm(cdt: torch.dtype, rng) -> bool:
+    """The fused-epilogue tensor-core GEMMs serve bf16 mode in eval (the train-mode dropout sits between a projection
+    and its residual add, where the fused epilogue has no mask: train mode keeps the library GEMM + element-wise path)."""
+    from . import config
+    return cdt == torch.bfloat16 and not rng and config.gemm_impl() == "sm100"
+
+
+def _encoder_layer_forward_sm100(x: torch.Tensor, W: FrozenLayerWeights, geom: Geometry, impl):
+    """EncoderLayer.forward with every frozen projection on ``mt_linear_sm100`` and its epilogues: bias + bf16 q/k/v into
+    the TMA-ready buffer; out_proj + bias + residual -> x1; fc1 + bias + GELU + LayerNorm(3072) statistics; fc2 with the
+    LayerNorm folded in + bias + residual -> y.  The [N, 3072] normalised tensor, the fp32 attention / FFN branch outputs
+    and the GELU+LN and residual kernels of the library path do not exist here."""
+    N = geom.n_tokens
+    cdt = torch.bfloat16
+    h1, mean1, rstd1 = layernorm_fwd(x, W.ln1[0], W.ln1[1], cdt)
+    qkv = torch.empty((geom.n_alloc, 3 * EMBED), device=x.device, dtype=cdt)
+    if geom.n_alloc > N:
+        qkv[N:].zero_()
+    linear_sm100(h1, W.w_qkv, bias=W.b_qkv32, want_f32=False, out_bf16=qkv[:N])
+    del h1
+    o_br, lse_br = dilated_attn_fwd(geom, qkv, impl[0])
+    a_ln, _, lse, mean_a, rstd_a = dilated_merge_ln_fwd(geom, o_br, lse_br, W.ln_in[0], W.ln_in[1])
+    x1, _ = linear_sm100(a_ln, W.w_o, bias=W.b_o, residual=x)                     # x1 = x + out_proj(a_ln)
+    del a_ln
+    h2, mean2, rstd2 = layernorm_fwd(x1, W.ln2[0], W.ln2[1], cdt)
+    stats = torch.empty((N, W.w_1.shape[0] // 128, 2), device=x.device, dtype=torch.float32)   # slab partials
+    f1, u = linear_sm100(h2, W.w_1, mode=_lib.MT_EPI_GELU_STATS, bias=W.b_1, want_f32=True, want_bf16=True, stats=stats)
+    del h2
+    mean_f = torch.empty(N, device=x.device, dtype=torch.float32)
+    rstd_f = torch.empty(N, device=x.device, dtype=torch.float32)
+    y, _ = linear_sm100(u, W.w_2g, mode=_lib.MT_EPI_LN_RESIDUAL, residual=x1, stats=stats, col_c1=W.c1_2, col_c2=W.c2_2,
+                        ln_cols=W.w_2g.shape[1], ln_mean_out=mean_f, ln_rstd_out=rstd_f)
+    del u
+    # f1 already contains fc1's bias here (the library path keeps it out and lets the GELU kernels add it)
+    saved = (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f)
+    return y, saved
+
+
+def _encoder_layer_backward_sm100(dy: torch.Tensor, saved, W: FrozenLayerWeights, geom: Geometry, impl):
+    (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f) = saved
+    cdt = torch.bfloat16
+    dy = dy.contiguous()
+    d_f2 = _as_compute(dy, cdt)
+    dg, _ = linear_sm100(d_f2, W.w_2_t)                                           # fp32 [N, 3072]
+    d_f1 = gelu_ln_bwd(dg, f1, W.ln_ffn[0], mean_f, rstd_f, cdt, hbias=None)
+    del dg
+    dh2, _ = linear_sm100(d_f1, W.w_1_t)                                          # fp32 [N, 768]
+    del d_f1
+    dx1, _, _ = layernorm_bwd(dh2, x1, W.ln2[0], mean2, rstd2, torch.float32, residual=dy, bf16_twin=True)
+    del dh2
+    d_aln, _ = linear_sm100(_as_compute(dx1, cdt), W.w_o_t)                       # fp32 [N, 768]
+    dattn, delta_br = dilated_merge_ln_bwd(geom, d_aln, o_br, lse_br, W.ln_in[0], mean_a, rstd_a)
+    del d_aln
+    dqkv = dilated_attn_bwd(geom, qkv, dattn, lse, delta_br, impl[1])             # fp32 [N, 2304]
+    dh1, _ = linear_sm100(cast(dqkv, cdt), W.w_qkv_t)
+    dx, _, _ = layernorm_bwd(dh1, x, W.ln1[0], mean1, rstd1, torch.float32, residual=dx1)
+    return dx
+
+
 def encoder_layer_forward(x: torch.Tensor, W: FrozenLayerWeights, geom: Geometry, cdt: torch.dtype, impl, rng=None):
     """x [N, 768] fp32 -> (y fp32, saved tensors); ``impl`` = (forward, backward) attention kernel selectors.
     EncoderLayer.forward (encoder.py:121-175); ``rng`` = (DropSpec of the attention branch, DropSpec of the FFN branch)
     in train mode, None in eval mode."""
+    if _use_sm100_gemm(cdt, rng):
+        return _encoder_layer_forward_sm100(x, W, geom, impl)
     h1, mean1, rstd1 = layernorm_fwd(x, W.ln1[0], W.ln1[1], cdt)
     qkv = _qkv_project(h1, W, geom)
     del h1
@@ -594,6 +699,8 @@ def encoder_layer_backward(dy: torch.Tensor, saved, W: FrozenLayerWeights, geom:
                            rng=None):
     """dX of the frozen layer (no weight gradients: every parameter of the slide encoder is frozen,
     longvit_adapter.py:78-80).  ``rng``: the DropSpecs of the forward (the masks are regenerated, not stored)."""
+    if _use_sm100_gemm(cdt, rng):
+        return _encoder_layer_backward_sm100(dy, saved, W, geom, impl)
     (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f) = saved
     dy = dy.contiguous()
     if rng:

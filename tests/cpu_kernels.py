@@ -224,7 +224,44 @@ def gated_residual_bwd(dy, a, b, g32, out=None):
     return da, (dy * g32).to(b.dtype), (dy * (a + b.float())).sum(0)
 
 
-_NAMES = ["layernorm_fwd", "layernorm_bwd", "add_layernorm_fwd", "gelu_ln_fwd", "gelu_ln_bwd", "dilated_attn_fwd",
+def linear_sm100(a, w, mode=0, bias=None, residual=None, want_f32=True, want_bf16=False, stats=None, col_c1=None,
+                 col_c2=None, ln_cols=0, eps=1e-5, out_f32=None, out_bf16=None, ln_mean_out=None, ln_rstd_out=None):
+    """mt_linear_sm100 (include/modaltune_b200.h): C = A W^T in fp32 math on the 16-bit operands + the epilogue."""
+    acc = a.float() @ w.float().t()
+    o32 = o16 = None
+    if mode == 3:       # MT_EPI_GELU_STATS
+        h = acc + bias
+        u = F.gelu(h).to(torch.bfloat16)
+        uf = u.float().reshape(u.shape[0], -1, 128)
+        stats[:, :, 0] = uf.sum(2)
+        stats[:, :, 1] = uf.square().sum(2)
+        o32, o16 = h, u
+    else:
+        if mode == 4:   # MT_EPI_LN_RESIDUAL
+            mean = stats[:, :, 0].sum(1, keepdim=True) / ln_cols
+            rstd = torch.rsqrt((stats[:, :, 1].sum(1, keepdim=True) / ln_cols - mean * mean).clamp(min=0) + eps)
+            acc = rstd * (acc - mean * col_c1) + col_c2
+            if ln_mean_out is not None:
+                ln_mean_out.copy_(mean[:, 0])
+                ln_rstd_out.copy_(rstd[:, 0])
+        elif bias is not None:
+            acc = acc + bias
+        if residual is not None:
+            acc = acc + residual
+        if want_f32 or out_f32 is not None:
+            o32 = acc
+        if want_bf16 or out_bf16 is not None:
+            o16 = acc.to(torch.bfloat16)
+    if out_f32 is not None and o32 is not None:
+        out_f32.copy_(o32)
+        o32 = out_f32
+    if out_bf16 is not None and o16 is not None:
+        out_bf16.copy_(o16)
+        o16 = out_bf16
+    return o32, o16
+
+
+_NAMES = ["linear_sm100", "layernorm_fwd", "layernorm_bwd", "add_layernorm_fwd", "gelu_ln_fwd", "gelu_ln_bwd", "dilated_attn_fwd",
           "dilated_merge_ln_fwd", "dilated_merge_ln_bwd", "dilated_attn_bwd", "cross_attn_fwd", "cross_attn_bwd",
           "embed_assemble", "cast", "gated_residual_fwd", "gated_residual_bwd", "residual_bias_add"]
 

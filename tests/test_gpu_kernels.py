@@ -305,3 +305,66 @@ def test_dilated_attention_tcgen05_backward(N, sl):
                 ct = torch.nn.functional.cosine_similarity(dq_t[:, sl_].flatten().double().cpu(),
                                                            dq_c[:, sl_].flatten().double(), dim=0)
                 assert float(ct) > 0.9995, (impl, name, float(ct))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tcgen05 GEMM of the frozen linear layers with fused epilogues (mt_linear_sm100) against plain PyTorch fp32
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(10001, 2304, 768), (777, 768, 3072), (128, 256, 64), (1, 768, 768), (4097, 3072, 768)])
+def test_linear_sm100_plain_bias_residual(M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    ref = a.float() @ w.float().t()
+    o32, o16 = ops.linear_sm100(a, w, want_f32=True, want_bf16=True)
+    assert rel(o32, ref) < 1e-5 and rel(o16, ref) < 1e-2
+    o32, _ = ops.linear_sm100(a, w, bias=bias, residual=res)
+    assert rel(o32, ref + bias + res) < 1e-5
+    # strided output: the QKV buffer has n_alloc rows, the GEMM writes the first M
+    buf = torch.zeros(M + 7, N, device=DEV, dtype=torch.bfloat16)
+    ops.linear_sm100(a, w, bias=bias, want_f32=False, out_bf16=buf[:M])
+    assert rel(buf[:M], ref + bias) < 1e-2 and float(buf[M:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("M", [10001, 513])
+def test_linear_sm100_ffn_epilogues(M):
+    """fc1 + GELU + LN statistics in one GEMM, fc2 with ffn_layernorm folded in + residual in the other: together they
+    must equal fc2(LN(gelu(fc1(x)))) + residual of feedforward_network.py:132-143 (fp32 math on the same bf16 operands)."""
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, 768, generator=g).to(torch.bfloat16).to(DEV)
+    w1 = (torch.randn(3072, 768, generator=g) * 0.04).to(DEV)
+    b1 = (torch.randn(3072, generator=g) * 0.1).to(DEV)
+    w2 = (torch.randn(768, 3072, generator=g) * 0.02).to(DEV)
+    b2 = (torch.randn(768, generator=g) * 0.1).to(DEV)
+    gam = (1 + 0.1 * torch.randn(3072, generator=g)).to(DEV)
+    bet = (0.1 * torch.randn(3072, generator=g)).to(DEV)
+    res = torch.randn(M, 768, generator=g).to(DEV)
+    w1b = w1.to(torch.bfloat16)
+    h_ref = x.float() @ w1b.float().t() + b1
+    u_ref = torch.nn.functional.gelu(h_ref)
+    stats = torch.full((M, 24, 2), float("nan"), device=DEV)     # every slab partial is written, nothing is accumulated
+    h, u = ops.linear_sm100(x, w1b, mode=_lib.MT_EPI_GELU_STATS, bias=b1, want_f32=True, want_bf16=True, stats=stats)
+    h2, u2 = ops.linear_sm100(x, w1b, mode=_lib.MT_EPI_GELU_STATS, bias=b1, want_f32=True, want_bf16=True, stats=stats.clone())
+    assert torch.equal(h, h2) and torch.equal(u, u2)             # bit-reproducible
+    assert rel(h, h_ref) < 1e-5
+    assert float((u.float() - u_ref).abs().max()) < 2e-2 * float(u_ref.abs().max())
+    assert float((u.float() - u_ref.to(torch.bfloat16).float()).abs().max()) < 1e-2 * float(u_ref.abs().max())  # <= 1 bf16 ulp
+    assert rel(stats[:, :, 0].sum(1), u.float().sum(1)) < 1e-4 and rel(stats[:, :, 1].sum(1), u.float().square().sum(1)) < 1e-4
+    w2g = (w2 * gam[None, :]).to(torch.bfloat16)
+    c1 = w2g.float().sum(1)
+    c2 = w2 @ bet + b2
+    y, _ = ops.linear_sm100(u, w2g, mode=_lib.MT_EPI_LN_RESIDUAL, residual=res, stats=stats, col_c1=c1, col_c2=c2,
+                            ln_cols=3072)
+    y2, _ = ops.linear_sm100(u, w2g, mode=_lib.MT_EPI_LN_RESIDUAL, residual=res, stats=stats, col_c1=c1, col_c2=c2,
+                             ln_cols=3072)
+    assert torch.equal(y, y2)
+    ln = torch.nn.functional.layer_norm(u_ref, (3072,), gam, bet, 1e-5)
+    y_ref = ln @ w2.t() + b2 + res
+    assert rel(y, y_ref) < 1e-2        # bf16 operands (u, W2 gamma) against the fp32 chain
+    # and against the same bf16 operands in fp32 math: the fold itself is exact up to fp32 rounding
+    mean = u.float().mean(1, keepdim=True)
+    rstd = torch.rsqrt(u.float().var(1, unbiased=False, keepdim=True) + 1e-5)
+    y_same = rstd * (u.float() @ w2g.float().t() - mean * c1) + c2 + res
+    assert rel(y, y_same) < 2e-4
