@@ -126,7 +126,7 @@ typedef struct {
   int32_t mode;
   int32_t ln_cols;          /* MT_EPI_LN_RESIDUAL: number of columns the statistics were taken over (3072)      */
   float ln_eps;
-  float reserved;
+  int32_t impl;             /* 0 = pick, 1 = one CTA per 128 x 256 tile, 2 = CTA pairs (cta_group::2, 256 x 256)   */
   const float* bias;        /* [N] or NULL                                                                        */
   const float* residual;    /* [M, N] f32 or NULL, row stride ld_residual                                        */
   const float* col_c1;      /* [N]                                                                                */

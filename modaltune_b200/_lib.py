@@ -39,7 +39,7 @@ class Dropout(Structure):
 class LinearEpilogue(Structure):
     """``mt_linear_epilogue`` (include/modaltune_b200.h): what the tensor-core GEMM does with its accumulator."""
 
-    _fields_ = [("mode", c_int32), ("ln_cols", c_int32), ("ln_eps", c_float), ("reserved", c_float),
+    _fields_ = [("mode", c_int32), ("ln_cols", c_int32), ("ln_eps", c_float), ("impl", c_int32),
                 ("bias", c_void_p), ("residual", c_void_p), ("col_c1", c_void_p), ("col_c2", c_void_p),
                 ("stats", c_void_p), ("ln_mean_out", c_void_p), ("ln_rstd_out", c_void_p), ("out_f32", c_void_p), ("out_bf16", c_void_p),
                 ("ld_out_f32", c_int64), ("ld_out_bf16", c_int64), ("ld_residual", c_int64)]

@@ -29,23 +29,35 @@ using namespace sm100;
 
 namespace gemm {
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;        // 16 KB
-constexpr int B_BYTES = BN * BK * 2;        // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int THREADS = 32 * 10;            // TMA, MMA, 8 epilogue warps
-constexpr int SMEM_STG = STAGES * STAGE_BYTES;          // 8 epilogue warps x [32 rows][32 floats], 128-byte swizzle
-constexpr int STG_BYTES = 32 * 128;
-constexpr int SMEM_BAR = SMEM_STG + 8 * STG_BYTES;
-constexpr int NBAR = 2 * STAGES + 4;        // full[S], empty[S], acc_full[2], acc_empty[2]
-constexpr int SMEM_TMEM_PTR = SMEM_BAR + NBAR * 8;
-constexpr int SMEM_TOTAL = SMEM_TMEM_PTR + 16;
+constexpr int STG_F32 = 32 * 128;           // per epilogue warp: [32 rows][32 floats], 128-byte swizzle
+constexpr int STG_BF16 = 32 * 64;           // per epilogue warp: [32 rows][32 bf16], 64-byte swizzle
+
+// PAIR = two CTAs of a cluster execute M = 256 MMAs (cta_group::2): every CTA keeps its own 128 rows of A and HALF of
+// the 256 rows of W in shared memory.  Measured on B200: the one-CTA kernel is bound by shared-memory bandwidth (per
+// 128 x 256 x 768 tile the tensor core reads 576 KB of operands, TMA writes 576 KB and the epilogue stages 256 KB:
+// 11 k cycles of the 128 B / clk pipe against 6.1 k cycles of MMA); the pair halves the W traffic of both kinds.
+template <bool PAIR>
+struct Cfg {
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;        // W rows held by one CTA
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = PAIR ? 5 : 3;
+  static constexpr int SMEM_STG32 = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_STG16 = SMEM_STG32 + 8 * STG_F32;
+  static constexpr int SMEM_BAR = SMEM_STG16 + 8 * STG_BF16;
+  static constexpr int NBAR = 2 * STAGES + 4;              // full[S], empty[S], acc_full[2], acc_empty[2]
+  static constexpr int SMEM_TMEM_PTR = SMEM_BAR + NBAR * 8;
+  static constexpr int SMEM_TOTAL = SMEM_TMEM_PTR + 16;
+};
+static_assert(Cfg<false>::SMEM_TOTAL <= 232448 && Cfg<true>::SMEM_TOTAL <= 232448, "shared memory of the GEMM kernels");
 
 struct Params {
   int M, N, K;
   int mode;
   const float* bias;        // [N] or null
-  const float* residual;    // [M, N] f32 (modes 2, 4)
+  const float* residual;    // [M, N] f32 (modes 0, 4)
   const float* col_c1;      // [N] (mode 4)
   const float* col_c2;      // [N] (mode 4)
   float* stats;             // [M, cols / 128, 2]: (sum, sum of squares) per 128-column slab: written in mode 3, read in mode 4
@@ -53,7 +65,7 @@ struct Params {
   float* rstd_out;
   float* out_f32;           // [M, N] or null
   __nv_bfloat16* out_bf16;  // [M, N] or null
-  int64_t ld_f32, ld_bf16, ld_res;
+  int64_t ld_res;
   float ln_eps;
   float inv_ln_cols;        // 1 / (number of columns the statistics were summed over)
   int ln_parts;             // mode 4: partial sums per row = ln_cols / 128
@@ -74,86 +86,119 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(copysignf(erf_abs, x), half_x, half_x);     // 0.5 x (1 + erf(x / sqrt 2))
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
-linear_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_c, const Params P) {
+template <bool PAIR>
+__device__ __forceinline__ void linear_body(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_c,
+                                            const CUtensorMap& map_c16, const Params& P) {
+  using C = Cfg<PAIR>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((sbase & 1023u) != 0) __trap();
-  const uint32_t bar_full = sbase + SMEM_BAR;
-  const uint32_t bar_empty = bar_full + 8 * STAGES;
-  const uint32_t bar_acc_full = bar_empty + 8 * STAGES;   // [2]
-  const uint32_t bar_acc_empty = bar_acc_full + 16;        // [2]
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_TMEM_PTR);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;      // 0 = leader of the pair
+  const uint32_t bar_full = sbase + C::SMEM_BAR;
+  const uint32_t bar_empty = bar_full + 8 * C::STAGES;
+  const uint32_t bar_acc_full = bar_empty + 8 * C::STAGES;   // [2]
+  const uint32_t bar_acc_empty = bar_acc_full + 16;          // [2] (PAIR: the leader's copy collects both CTAs)
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::SMEM_TMEM_PTR);
 
-  const int m_tiles = (P.M + BM - 1) / BM, n_tiles = P.N / BN, k_blocks = P.K / BK;
+  constexpr int TILE_M = PAIR ? 2 * BM : BM;                  // rows of one work item (both CTAs of a pair)
+  const int m_tiles = (P.M + TILE_M - 1) / TILE_M, n_tiles = P.N / BN, k_blocks = P.K / BK;
   const int tiles = m_tiles * n_tiles;
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(bar_full + 8 * i, 1);
       mbar_init(bar_empty + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, 256);
+      mbar_init(bar_acc_empty + 8 * i, PAIR ? 512 : 256);
     }
     fence_barrier_init();
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (P.out_f32 != nullptr) tma_prefetch_desc(&map_c);
+    if (P.out_bf16 != nullptr) tma_prefetch_desc(&map_c16);
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32((const void*)tmem_slot), 512);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(smem_u32((const void*)tmem_slot), 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer ===============================================================================================
+    // ===== TMA producer (both CTAs of a pair: each loads its own rows of A and its half of W) ========================
     if (lane == 0) {
       int it = 0;
-      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+      for (int t = worker; t < tiles; t += n_workers) {
+        const int m0 = (t / n_tiles) * TILE_M + (int)rank * BM, n0 = (t % n_tiles) * BN + (int)rank * C::B_ROWS;
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
-          const int st = it % STAGES;
-          mbar_wait(bar_empty + 8 * st, ((it / STAGES) & 1) ^ 1);
-          mbar_expect_tx(bar_full + 8 * st, STAGE_BYTES);
-          const uint32_t dst = sbase + st * STAGE_BYTES;
-          tma_load_2d(dst, &map_a, bar_full + 8 * st, kb * BK, m0);
-          tma_load_2d(dst + A_BYTES, &map_b, bar_full + 8 * st, kb * BK, n0);
+#ifdef MT_EXP_NO_TMA    // experiment builds only (wrong results): the tensor pipe alone, operands loaded once
+          if (it >= C::STAGES) continue;
+#endif
+          const int st = it % C::STAGES;
+          mbar_wait(bar_empty + 8 * st, ((it / C::STAGES) & 1) ^ 1);
+          const uint32_t dst = sbase + st * C::STAGE_BYTES;
+          if (PAIR) {
+            // the leader's barrier collects the bytes of both CTAs; only the leader arms it
+            if (rank == 0) mbar_expect_tx(bar_full + 8 * st, 2 * C::STAGE_BYTES);
+            tma_load_2d_pair(dst, &map_a, bar_full + 8 * st, kb * BK, m0);
+            tma_load_2d_pair(dst + A_BYTES, &map_b, bar_full + 8 * st, kb * BK, n0);
+          } else {
+            mbar_expect_tx(bar_full + 8 * st, C::STAGE_BYTES);
+            tma_load_2d(dst, &map_a, bar_full + 8 * st, kb * BK, m0);
+            tma_load_2d(dst + A_BYTES, &map_b, bar_full + 8 * st, kb * BK, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =================================================================================================
-    constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 0, 0);
-    const uint64_t a_desc0 = umma_smem_desc(sbase, 16, 1024);
-    const uint64_t b_desc0 = umma_smem_desc(sbase + A_BYTES, 16, 1024);
-    int it = 0, tl = 0;
-    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++tl) {
-      const int buf = tl & 1;
-      mbar_wait(bar_acc_empty + 8 * buf, ((tl >> 1) & 1) ^ 1);   // the epilogue has read this accumulator
-      tc_fence_after();
-      const uint32_t acc = tmem + buf * BN;
-      for (int kb = 0; kb < k_blocks; ++kb, ++it) {
-        const int st = it % STAGES;
-        mbar_wait(bar_full + 8 * st, (it / STAGES) & 1);
+    // ===== MMA issuer (the leader CTA of a pair) =======================================================================
+    if (!PAIR || rank == 0) {
+      constexpr uint32_t IDESC = umma_idesc_bf16(TILE_M, BN, 0, 0);
+      const uint64_t a_desc0 = umma_smem_desc(sbase, 16, 1024);
+      const uint64_t b_desc0 = umma_smem_desc(sbase + A_BYTES, 16, 1024);
+      int it = 0, tl = 0;
+      for (int t = worker; t < tiles; t += n_workers, ++tl) {
+        const int buf = tl & 1;
+        mbar_wait(bar_acc_empty + 8 * buf, ((tl >> 1) & 1) ^ 1);   // the epilogue(s) have read this accumulator
         tc_fence_after();
-        if (elect_one()) {
-          const uint64_t ad = umma_desc_adv(a_desc0, (uint32_t)st * STAGE_BYTES);
-          const uint64_t bd = umma_desc_adv(b_desc0, (uint32_t)st * STAGE_BYTES);
+        const uint32_t acc = tmem + buf * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int st = it % C::STAGES;
+#ifdef MT_EXP_NO_TMA
+          if (it < C::STAGES)
+#endif
+          mbar_wait(bar_full + 8 * st, (it / C::STAGES) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ad = umma_desc_adv(a_desc0, (uint32_t)st * C::STAGE_BYTES);
+            const uint64_t bd = umma_desc_adv(b_desc0, (uint32_t)st * C::STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_ss(acc, umma_desc_adv(ad, k * 32), umma_desc_adv(bd, k * 32), IDESC, (kb > 0) || (k > 0));
-          umma_commit(bar_empty + 8 * st);
-          if (kb == k_blocks - 1) umma_commit(bar_acc_full + 8 * buf);
+            for (int k = 0; k < BK / 16; ++k) {
+              if (PAIR) umma_ss_pair(acc, umma_desc_adv(ad, k * 32), umma_desc_adv(bd, k * 32), IDESC, (kb > 0) || (k > 0));
+              else umma_ss(acc, umma_desc_adv(ad, k * 32), umma_desc_adv(bd, k * 32), IDESC, (kb > 0) || (k > 0));
+            }
+            if (PAIR) {
+              umma_commit_pair(bar_empty + 8 * st);
+              if (kb == k_blocks - 1) umma_commit_pair(bar_acc_full + 8 * buf);
+            } else {
+              umma_commit(bar_empty + 8 * st);
+              if (kb == k_blocks - 1) umma_commit(bar_acc_full + 8 * buf);
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
@@ -163,33 +208,51 @@ linear_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int half = ew >> 2;                      // which 128 columns
     const int row_in_tile = lane_grp * 32 + lane;
     const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
-    // fp32 outputs leave through a per-warp staging tile and TMA stores: a thread owns a ROW of the accumulator, so
-    // direct stores touch 32 different rows per instruction (measured: the GEMM became epilogue-bound, 480 against
-    // cuBLAS's 620 TFLOP/s); staged, every global write is a full 128-byte line
-    uint8_t* stg = smem + SMEM_STG + ew * STG_BYTES;
-    const uint32_t stg_u32 = sbase + SMEM_STG + ew * STG_BYTES;
-    auto store_f32_chunk = [&](const float (&o)[32], int col, int row0) {
-      if (lane == 0) bulk_wait_group_read<0>();       // the previous store of this warp has read the staging tile
+    // Outputs leave through per-warp staging tiles and TMA stores: a thread owns a ROW of the accumulator, so direct
+    // stores touch 32 different rows per instruction (measured: 80 k of the epilogue's 90 k cycles with bf16 output);
+    // staged, every global write is a full line and asynchronous.
+    uint8_t* stg32 = smem + C::SMEM_STG32 + ew * STG_F32;
+    uint8_t* stg16 = smem + C::SMEM_STG16 + ew * STG_BF16;
+    const uint32_t stg32_u32 = sbase + C::SMEM_STG32 + ew * STG_F32;
+    const uint32_t stg16_u32 = sbase + C::SMEM_STG16 + ew * STG_BF16;
+    // one 32-column chunk of this warp's 32 rows: fp32 and / or bf16 copy
+    auto store_chunk = [&](const float (&o)[32], int col, int row0, bool f32, bool b16) {
+      if (lane == 0) bulk_wait_group_read<0>();       // the previous stores of this warp have read the staging tiles
       __syncwarp();
+      if (f32) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        *reinterpret_cast<float4*>(stg + lane * 128 + ((i ^ (lane & 7)) << 4)) =
-            make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(stg32 + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+              make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+      }
+      if (b16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(stg16 + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) =
+              make_uint4(pack_bf16(o[8 * i], o[8 * i + 1]), pack_bf16(o[8 * i + 2], o[8 * i + 3]),
+                         pack_bf16(o[8 * i + 4], o[8 * i + 5]), pack_bf16(o[8 * i + 6], o[8 * i + 7]));
+      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(&map_c, stg_u32, col, row0);
+        if (f32) tma_store_2d(&map_c, stg32_u32, col, row0);
+        if (b16) tma_store_2d(&map_c16, stg16_u32, col, row0);
         bulk_commit_group();
       }
     };
     int tl = 0;
-    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++tl) {
+    for (int t = worker; t < tiles; t += n_workers, ++tl) {
       const int buf = tl & 1;
-      const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN + half * 128;
+      const int m0 = (t / n_tiles) * TILE_M + (int)rank * BM, n0 = (t % n_tiles) * BN + half * 128;
       const int row = m0 + row_in_tile;
       const bool row_ok = row < P.M;
       mbar_wait(bar_acc_full + 8 * buf, (tl >> 1) & 1);
       tc_fence_after();
+#ifdef MT_EXP_NO_EPI    // experiment builds only (wrong results): main loop alone
+      tc_fence_before();
+      if (PAIR) mbar_arrive_leader(bar_acc_empty + 8 * buf); else mbar_arrive(bar_acc_empty + 8 * buf);
+      continue;
+#endif
       const uint32_t acc = tmem + buf * BN + half * 128 + t_lane;
       float mean = 0.f, rstd = 1.f;
       if (P.mode == 4 && row_ok) {
@@ -211,6 +274,7 @@ linear_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
       }
       float s1 = 0.f, s2 = 0.f;
+      const int row0 = m0 + lane_grp * 32;          // first row of this warp's 32-row slab (rows >= M are clipped by TMA)
 #pragma unroll 1
       for (int c = 0; c < 128; c += 32) {
         float v[32];
@@ -218,72 +282,54 @@ linear_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         tmem_ld_wait();
         if (c == 96) {                             // the whole accumulator is in registers: release it to the MMA warp
           tc_fence_before();
-          mbar_arrive(bar_acc_empty + 8 * buf);
+          if (PAIR) mbar_arrive_leader(bar_acc_empty + 8 * buf); else mbar_arrive(bar_acc_empty + 8 * buf);
         }
         const int col = n0 + c;
-        const int row0 = m0 + lane_grp * 32;      // first row of this warp's 32-row slab (rows >= M are clipped by TMA)
         if (P.mode == 3) {
           // h = acc + bias (kept in fp32 for the backward), u = gelu(h) in bf16 for fc2, row statistics of the ROUNDED u
-          float h[32];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 b = *reinterpret_cast<const float4*>(P.bias + col + i);
-            h[i] = v[i] + b.x; h[i + 1] = v[i + 1] + b.y; h[i + 2] = v[i + 2] + b.z; h[i + 3] = v[i + 3] + b.w;
+            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
           }
-          store_f32_chunk(h, col, row0);
-          if (!row_ok) continue;
-          __nv_bfloat16* ob = P.out_bf16 + (int64_t)row * P.ld_bf16 + col;
+          store_chunk(v, col, row0, true, false);
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint32_t w[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162 u2 = __floats2bfloat162_rn(gelu_erf(h[i + 2 * j]), gelu_erf(h[i + 2 * j + 1]));
-              const float2 f = __bfloat1622float2(u2);
-              s1 += f.x + f.y;
-              s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, s2));
-              w[j] = *reinterpret_cast<const uint32_t*>(&u2);
-            }
-            *reinterpret_cast<uint4*>(ob + i) = make_uint4(w[0], w[1], w[2], w[3]);
+          for (int i = 0; i < 32; i += 2) {
+            const __nv_bfloat162 u2 = __floats2bfloat162_rn(gelu_erf(v[i]), gelu_erf(v[i + 1]));
+            const float2 f = __bfloat1622float2(u2);
+            s1 += f.x + f.y;
+            s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, s2));
+            v[i] = f.x;
+            v[i + 1] = f.y;
           }
+          store_chunk(v, col, row0, false, true);
         } else {
-          float o[32];
           if (P.mode == 4) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               const float4 c1 = *reinterpret_cast<const float4*>(P.col_c1 + col + i);
               const float4 c2 = *reinterpret_cast<const float4*>(P.col_c2 + col + i);
-              o[i] = fmaf(rstd, fmaf(-mean, c1.x, v[i]), c2.x);
-              o[i + 1] = fmaf(rstd, fmaf(-mean, c1.y, v[i + 1]), c2.y);
-              o[i + 2] = fmaf(rstd, fmaf(-mean, c1.z, v[i + 2]), c2.z);
-              o[i + 3] = fmaf(rstd, fmaf(-mean, c1.w, v[i + 3]), c2.w);
+              v[i] = fmaf(rstd, fmaf(-mean, c1.x, v[i]), c2.x);
+              v[i + 1] = fmaf(rstd, fmaf(-mean, c1.y, v[i + 1]), c2.y);
+              v[i + 2] = fmaf(rstd, fmaf(-mean, c1.z, v[i + 2]), c2.z);
+              v[i + 3] = fmaf(rstd, fmaf(-mean, c1.w, v[i + 3]), c2.w);
             }
           } else if (P.bias != nullptr) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               const float4 b = *reinterpret_cast<const float4*>(P.bias + col + i);
-              o[i] = v[i] + b.x; o[i + 1] = v[i + 1] + b.y; o[i + 2] = v[i + 2] + b.z; o[i + 3] = v[i + 3] + b.w;
+              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = v[i];
           }
           if (P.residual != nullptr && row_ok) {
             const float* rs = P.residual + (int64_t)row * P.ld_res + col;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               const float4 r = *reinterpret_cast<const float4*>(rs + i);
-              o[i] += r.x; o[i + 1] += r.y; o[i + 2] += r.z; o[i + 3] += r.w;
+              v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
             }
           }
-          if (P.out_f32 != nullptr) store_f32_chunk(o, col, row0);
-          if (P.out_bf16 != nullptr && row_ok) {
-            __nv_bfloat16* ob = P.out_bf16 + (int64_t)row * P.ld_bf16 + col;
-#pragma unroll
-            for (int i = 0; i < 32; i += 8)
-              *reinterpret_cast<uint4*>(ob + i) = make_uint4(pack_bf16(o[i], o[i + 1]), pack_bf16(o[i + 2], o[i + 3]),
-                                                             pack_bf16(o[i + 4], o[i + 5]), pack_bf16(o[i + 6], o[i + 7]));
-          }
+          store_chunk(v, col, row0, P.out_f32 != nullptr, P.out_bf16 != nullptr);
         }
       }
       if (P.mode == 3 && row_ok)   // this thread's 128-column slab of the row: slab index = n0 / 128 of N / 128
@@ -292,8 +338,24 @@ linear_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (lane == 0) bulk_wait_group_read<0>();
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: no CTA may exit while its peer still signals its barriers
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair(tmem, 512);
+    else tmem_dealloc(tmem, 512);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+linear_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c16, const Params P) {
+  linear_body<false>(map_a, map_b, map_c, map_c16, P);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+linear_sm100_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c16,
+                         const Params P) {
+  linear_body<true>(map_a, map_b, map_c, map_c16, P);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -313,22 +375,23 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// row-major [rows, ld] fp32 output, box = [32 rows][32 columns] (one 128-byte swizzle atom per row)
-static int encode_out_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+// row-major [rows, ld] output, box = [32 rows][32 columns]: fp32 = one 128-byte swizzle atom per row, bf16 = 64-byte
+static int encode_out(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool bf16) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
     return MT_E_UNSUPPORTED;
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};
   cuuint32_t box[2] = {32, 32};
   cuuint32_t estr[2] = {1, 1};
-  CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+  CUresult rc = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) for a [%lld, %lld] fp32 output", (int)rc, (long long)rows, (long long)cols);
+    set_error("cuTensorMapEncodeTiled failed (%d) for a [%lld, %lld] output", (int)rc, (long long)rows, (long long)cols);
     return MT_E_BADARG;
   }
   return 0;
@@ -380,28 +443,50 @@ extern "C" int mt_linear_sm100(const void* a, int64_t lda, const void* w, int64_
   P.mean_out = ep->ln_mean_out; P.rstd_out = ep->ln_rstd_out;
   MT_REQUIRE((P.mean_out == nullptr) == (P.rstd_out == nullptr), "linear_sm100: ln_mean_out and ln_rstd_out go together");
   P.out_f32 = ep->out_f32; P.out_bf16 = (__nv_bfloat16*)ep->out_bf16;
-  P.ld_f32 = ep->ld_out_f32 ? ep->ld_out_f32 : N;
-  P.ld_bf16 = ep->ld_out_bf16 ? ep->ld_out_bf16 : N;
+  const int64_t ld_f32 = ep->ld_out_f32 ? ep->ld_out_f32 : N;
+  const int64_t ld_bf16 = ep->ld_out_bf16 ? ep->ld_out_bf16 : N;
   P.ld_res = ep->ld_residual ? ep->ld_residual : N;
   P.ln_eps = ep->ln_eps;
   P.inv_ln_cols = ep->ln_cols > 0 ? 1.0f / (float)ep->ln_cols : 0.f;
   P.ln_parts = ep->ln_cols / 128;
   MT_REQUIRE(ep->mode != MT_EPI_LN_RESIDUAL || ep->ln_cols % 128 == 0, "linear_sm100: ln_cols must be a multiple of 128");
-  MT_REQUIRE(P.ld_f32 % 4 == 0 && P.ld_bf16 % 8 == 0 && P.ld_res % 4 == 0, "linear_sm100: output row strides must keep 16-byte alignment");
-  CUtensorMap map_a, map_b, map_c;
+  MT_REQUIRE(ld_f32 % 4 == 0 && ld_bf16 % 8 == 0 && P.ld_res % 4 == 0, "linear_sm100: output row strides must keep 16-byte alignment");
+  // impl: 0 = pick (CTA pairs when there is more than one 256-row block), 1 = one CTA per tile, 2 = CTA pairs
+  int impl = ep->impl;
+  if (impl == 0) impl = M > gemm::BM ? 2 : 1;
+  MT_REQUIRE(impl == 1 || impl == 2, "linear_sm100: bad impl %d", ep->impl);
+  const bool pair = impl == 2;
+  CUtensorMap map_a, map_b, map_c, map_c16;
   memset(&map_c, 0, sizeof(map_c));
+  memset(&map_c16, 0, sizeof(map_c16));
   int rc = gemm::encode_2d(&map_a, a, M, K, lda, gemm::BM);
   if (rc) return rc;
-  rc = gemm::encode_2d(&map_b, w, N, K, ldw, gemm::BN);
+  rc = gemm::encode_2d(&map_b, w, N, K, ldw, pair ? gemm::BN / 2 : gemm::BN);
   if (rc) return rc;
   if (ep->out_f32 != nullptr) {
     MT_REQUIRE(((uintptr_t)ep->out_f32 & 15) == 0, "linear_sm100: the fp32 output must be 16-byte aligned");
-    rc = gemm::encode_out_f32(&map_c, ep->out_f32, M, N, P.ld_f32);
+    rc = gemm::encode_out(&map_c, ep->out_f32, M, N, ld_f32, false);
     if (rc) return rc;
+  }
+  if (ep->out_bf16 != nullptr) {
+    MT_REQUIRE(((uintptr_t)ep->out_bf16 & 15) == 0, "linear_sm100: the bf16 output must be 16-byte aligned");
+    rc = gemm::encode_out(&map_c16, ep->out_bf16, M, N, ld_bf16, true);
+    if (rc) return rc;
+  }
+  if (pair) {
+    const int tiles = (int)((M + 2 * gemm::BM - 1) / (2 * gemm::BM) * (N / gemm::BN));
+    const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
+    MT_CUDA(cudaFuncSetAttribute(gemm::linear_sm100_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 gemm::Cfg<true>::SMEM_TOTAL));
+    gemm::linear_sm100_pair_kernel<<<2 * pairs, gemm::THREADS, gemm::Cfg<true>::SMEM_TOTAL, (cudaStream_t)stream>>>(
+        map_a, map_b, map_c, map_c16, P);
+    return check_launch("linear_sm100_pair_kernel");
   }
   const int tiles = (int)((M + gemm::BM - 1) / gemm::BM * (N / gemm::BN));
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  MT_CUDA(cudaFuncSetAttribute(gemm::linear_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_TOTAL));
-  gemm::linear_sm100_kernel<<<grid, gemm::THREADS, gemm::SMEM_TOTAL, (cudaStream_t)stream>>>(map_a, map_b, map_c, P);
+  MT_CUDA(cudaFuncSetAttribute(gemm::linear_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               gemm::Cfg<false>::SMEM_TOTAL));
+  gemm::linear_sm100_kernel<<<grid, gemm::THREADS, gemm::Cfg<false>::SMEM_TOTAL, (cudaStream_t)stream>>>(
+      map_a, map_b, map_c, map_c16, P);
   return check_launch("linear_sm100_kernel");
 }

@@ -324,7 +324,7 @@ def cross_attn_bwd(q, k, v, o, d_o, lse, heads: int):
 
 def linear_sm100(a: torch.Tensor, w: torch.Tensor, mode: int = _lib.MT_EPI_PLAIN, bias=None, residual=None,
                  want_f32: bool = True, want_bf16: bool = False, stats=None, col_c1=None, col_c2=None, ln_cols: int = 0,
-                 eps: float = LN_EPS, out_f32=None, out_bf16=None, ln_mean_out=None, ln_rstd_out=None):
+                 eps: float = LN_EPS, out_f32=None, out_bf16=None, ln_mean_out=None, ln_rstd_out=None, impl: int = 0):
     """C = A W^T on the tcgen05 tensor cores with a fused epilogue (``mt_linear_sm100``): a [M, K] bf16, w [N, K] bf16
     (nn.Linear layout).  Returns (out_f32 or None, out_bf16 or None).  See include/modaltune_b200.h for the modes."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
@@ -336,7 +336,7 @@ def linear_sm100(a: torch.Tensor, w: torch.Tensor, mode: int = _lib.MT_EPI_PLAIN
     if out_bf16 is None and want_bf16:
         out_bf16 = torch.empty((M, N), device=a.device, dtype=torch.bfloat16)
     ep = _lib.LinearEpilogue()
-    ep.mode, ep.ln_cols, ep.ln_eps = int(mode), int(ln_cols), float(eps)
+    ep.mode, ep.ln_cols, ep.ln_eps, ep.impl = int(mode), int(ln_cols), float(eps), int(impl)
     ptr = lambda t: t.data_ptr() if t is not None else None
     for t in (bias, residual, col_c1, col_c2, stats):
         assert t is None or (t.is_cuda and t.dtype == torch.float32)

@@ -225,7 +225,7 @@ def gated_residual_bwd(dy, a, b, g32, out=None):
 
 
 def linear_sm100(a, w, mode=0, bias=None, residual=None, want_f32=True, want_bf16=False, stats=None, col_c1=None,
-                 col_c2=None, ln_cols=0, eps=1e-5, out_f32=None, out_bf16=None, ln_mean_out=None, ln_rstd_out=None):
+                 col_c2=None, ln_cols=0, eps=1e-5, out_f32=None, out_bf16=None, ln_mean_out=None, ln_rstd_out=None, impl=0):
     """mt_linear_sm100 (include/modaltune_b200.h): C = A W^T in fp32 math on the 16-bit operands + the epilogue."""
     acc = a.float() @ w.float().t()
     o32 = o16 = None

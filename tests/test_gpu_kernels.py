@@ -310,26 +310,29 @@ def test_dilated_attention_tcgen05_backward(N, sl):
 # ---------------------------------------------------------------------------------------------------------------------
 # tcgen05 GEMM of the frozen linear layers with fused epilogues (mt_linear_sm100) against plain PyTorch fp32
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("M,N,K", [(10001, 2304, 768), (777, 768, 3072), (128, 256, 64), (1, 768, 768), (4097, 3072, 768)])
-def test_linear_sm100_plain_bias_residual(M, N, K):
+@pytest.mark.parametrize("impl", [1, 2])      # 1 = one CTA per 128 x 256 tile, 2 = CTA pairs (cta_group::2)
+@pytest.mark.parametrize("M,N,K", [(10001, 2304, 768), (777, 768, 3072), (128, 256, 64), (1, 768, 768), (4097, 3072, 768),
+                                   (257, 256, 128), (32769, 768, 768)])
+def test_linear_sm100_plain_bias_residual(M, N, K, impl):
     g = torch.Generator().manual_seed(M + N + K)
     a = torch.randn(M, K, generator=g).to(torch.bfloat16).to(DEV)
     w = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).to(DEV)
     bias = torch.randn(N, generator=g).to(DEV)
     res = torch.randn(M, N, generator=g).to(DEV)
     ref = a.float() @ w.float().t()
-    o32, o16 = ops.linear_sm100(a, w, want_f32=True, want_bf16=True)
+    o32, o16 = ops.linear_sm100(a, w, want_f32=True, want_bf16=True, impl=impl)
     assert rel(o32, ref) < 1e-5 and rel(o16, ref) < 1e-2
-    o32, _ = ops.linear_sm100(a, w, bias=bias, residual=res)
+    o32, _ = ops.linear_sm100(a, w, bias=bias, residual=res, impl=impl)
     assert rel(o32, ref + bias + res) < 1e-5
     # strided output: the QKV buffer has n_alloc rows, the GEMM writes the first M
     buf = torch.zeros(M + 7, N, device=DEV, dtype=torch.bfloat16)
-    ops.linear_sm100(a, w, bias=bias, want_f32=False, out_bf16=buf[:M])
+    ops.linear_sm100(a, w, bias=bias, want_f32=False, out_bf16=buf[:M], impl=impl)
     assert rel(buf[:M], ref + bias) < 1e-2 and float(buf[M:].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("M", [10001, 513])
-def test_linear_sm100_ffn_epilogues(M):
+def test_linear_sm100_ffn_epilogues(M, impl):
     """fc1 + GELU + LN statistics in one GEMM, fc2 with ffn_layernorm folded in + residual in the other: together they
     must equal fc2(LN(gelu(fc1(x)))) + residual of feedforward_network.py:132-143 (fp32 math on the same bf16 operands)."""
     g = torch.Generator().manual_seed(M)
@@ -345,8 +348,8 @@ def test_linear_sm100_ffn_epilogues(M):
     h_ref = x.float() @ w1b.float().t() + b1
     u_ref = torch.nn.functional.gelu(h_ref)
     stats = torch.full((M, 24, 2), float("nan"), device=DEV)     # every slab partial is written, nothing is accumulated
-    h, u = ops.linear_sm100(x, w1b, mode=_lib.MT_EPI_GELU_STATS, bias=b1, want_f32=True, want_bf16=True, stats=stats)
-    h2, u2 = ops.linear_sm100(x, w1b, mode=_lib.MT_EPI_GELU_STATS, bias=b1, want_f32=True, want_bf16=True, stats=stats.clone())
+    h, u = ops.linear_sm100(x, w1b, mode=_lib.MT_EPI_GELU_STATS, bias=b1, want_f32=True, want_bf16=True, stats=stats, impl=impl)
+    h2, u2 = ops.linear_sm100(x, w1b, mode=_lib.MT_EPI_GELU_STATS, bias=b1, want_f32=True, want_bf16=True, stats=stats.clone(), impl=impl)
     assert torch.equal(h, h2) and torch.equal(u, u2)             # bit-reproducible
     assert rel(h, h_ref) < 1e-5
     assert float((u.float() - u_ref).abs().max()) < 2e-2 * float(u_ref.abs().max())
@@ -356,9 +359,9 @@ def test_linear_sm100_ffn_epilogues(M):
     c1 = w2g.float().sum(1)
     c2 = w2 @ bet + b2
     y, _ = ops.linear_sm100(u, w2g, mode=_lib.MT_EPI_LN_RESIDUAL, residual=res, stats=stats, col_c1=c1, col_c2=c2,
-                            ln_cols=3072)
+                            ln_cols=3072, impl=impl)
     y2, _ = ops.linear_sm100(u, w2g, mode=_lib.MT_EPI_LN_RESIDUAL, residual=res, stats=stats, col_c1=c1, col_c2=c2,
-                             ln_cols=3072)
+                             ln_cols=3072, impl=impl)
     assert torch.equal(y, y2)
     ln = torch.nn.functional.layer_norm(u_ref, (3072,), gam, bet, 1e-5)
     y_ref = ln @ w2.t() + b2 + res

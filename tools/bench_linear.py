@@ -33,10 +33,12 @@ for name, N, K in (("qkv", 2304, 768), ("out_proj", 768, 768), ("fc1", 3072, 768
     fl = 2.0 * M * N * K
     t_cublas32 = med(lambda: torch.mm(a, w.t(), out_dtype=torch.float32))
     t_cublas16 = med(lambda: torch.addmm(bias.to(torch.bfloat16), a, w.t()))
-    t_ours32 = med(lambda: ops.linear_sm100(a, w, out_f32=o32))
-    t_ours16 = med(lambda: ops.linear_sm100(a, w, bias=bias, want_f32=False, out_bf16=o16))
-    print(f"{name:9s} M={M} N={N} K={K}: cuBLAS f32-out {t_cublas32*1e3:7.1f} us ({fl/t_cublas32/1e9:6.0f} TF)  bf16+bias {t_cublas16*1e3:7.1f} us | "
-          f"ours f32-out {t_ours32*1e3:7.1f} us ({fl/t_ours32/1e9:6.0f} TF)  bf16+bias {t_ours16*1e3:7.1f} us ({fl/t_ours16/1e9:6.0f} TF)")
+    print(f"{name:9s} M={M} N={N} K={K}: cuBLAS f32-out {t_cublas32*1e3:7.1f} us ({fl/t_cublas32/1e9:6.0f} TF)  bf16+bias {t_cublas16*1e3:7.1f} us", end="")
+    for impl in (1, 2):
+        t_ours32 = med(lambda: ops.linear_sm100(a, w, out_f32=o32, impl=impl))
+        t_ours16 = med(lambda: ops.linear_sm100(a, w, bias=bias, want_f32=False, out_bf16=o16, impl=impl))
+        print(f" | ours[{'1cta' if impl == 1 else 'pair'}] f32-out {t_ours32*1e3:7.1f} us ({fl/t_ours32/1e9:6.0f} TF)  bf16+bias {t_ours16*1e3:7.1f} us ({fl/t_ours16/1e9:6.0f} TF)", end="")
+    print()
 # the FFN pair with fused epilogues against the current path (GEMM + gelu_ln kernel + GEMM + residual kernel)
 x = torch.randn(M, 768, generator=g).to(torch.bfloat16).to(dev)
 w1 = (torch.randn(3072, 768, generator=g) * 0.04).to(torch.bfloat16).to(dev)
@@ -55,12 +57,14 @@ def ffn_old():
     return ops.residual_bias_add(res, f2, b2)
 
 
-def ffn_new():
-    h, u = ops.linear_sm100(x, w1, mode=_lib.MT_EPI_GELU_STATS, bias=b1, want_f32=True, want_bf16=True, stats=stats)
-    return ops.linear_sm100(u, w2, mode=_lib.MT_EPI_LN_RESIDUAL, residual=res, stats=stats, col_c1=c1, col_c2=c2, ln_cols=3072)[0]
+def ffn_new(impl):
+    h, u = ops.linear_sm100(x, w1, mode=_lib.MT_EPI_GELU_STATS, bias=b1, want_f32=True, want_bf16=True, stats=stats, impl=impl)
+    return ops.linear_sm100(u, w2, mode=_lib.MT_EPI_LN_RESIDUAL, residual=res, stats=stats, col_c1=c1, col_c2=c2, ln_cols=3072, impl=impl)[0]
 
 
-t_old, t_new = med(ffn_old), med(ffn_new)
-err = float((ffn_old() - ffn_new()).abs().max() / ffn_old().abs().max())
-print(f"FFN forward (fc1, GELU, LN 3072, fc2, residual) M={M}: cuBLAS + element-wise kernels {t_old*1e3:.1f} us, fused tcgen05 GEMMs {t_new*1e3:.1f} us, "
-      f"speed-up {t_old/t_new:.2f}x, max rel diff {err:.2e}")
+t_old = med(ffn_old)
+for impl in (1, 2):
+    t_new = med(lambda: ffn_new(impl))
+    err = float((ffn_old() - ffn_new(impl)).abs().max() / ffn_old().abs().max())
+    print(f"FFN forward (fc1, GELU, LN 3072, fc2, residual) M={M}: cuBLAS + element-wise kernels {t_old*1e3:.1f} us, fused tcgen05 GEMMs "
+          f"[{'1cta' if impl == 1 else 'pair'}] {t_new*1e3:.1f} us, speed-up {t_old/t_new:.2f}x, max rel diff {err:.2e}")

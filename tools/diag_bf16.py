@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from modaltune_b200 import config, ops, synthetic, train_step, adapter_modules, slide_encoder
-from tests import helpers
+from modaltune_b200 import factory as helpers
 
 dev = "cuda"
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 520

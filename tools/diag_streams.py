@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from modaltune_b200 import config, synthetic, train_step
-from tests import helpers
+from modaltune_b200 import factory as helpers
 DEV = "cuda"
 config.set_pass_streams(os.environ.get("MODALTUNE_B200_PASS_STREAMS", "1") != "0")
 model = helpers.build_model(helpers.SMALL_GROUPS, device=DEV)

@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from modaltune_b200 import config, synthetic, train_step
-from tests import helpers
+from modaltune_b200 import factory as helpers
 dev = "cuda"
 model = helpers.build_model(helpers.SMALL_GROUPS, device=dev)
 proj = helpers.build_projector(0, dev)

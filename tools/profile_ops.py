@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import profile, ProfilerActivity
 from modaltune_b200 import synthetic, train_step
-from tests import helpers
+from modaltune_b200 import factory as helpers
 dev = "cuda"
 model = helpers.build_model(None, device=dev)
 proj = helpers.build_projector(0, dev)

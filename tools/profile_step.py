@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import profile, ProfilerActivity
 from modaltune_b200 import config, synthetic, train_step, ops
-from tests import helpers
+from modaltune_b200 import factory as helpers
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 dev = "cuda"
 model = helpers.build_model(None, device=dev)
