@@ -51,6 +51,9 @@ def parse():
 
 
 UNIT = "slides/s"
+# DRAM bytes of ONE launch of the default backward attention kernel at 10 001 tokens, from the committed `ncu --set full`
+# capture (profiles/r2_ncu_attention.txt); None until that capture exists for the current kernel
+NCU_TRAFFIC_BWD = None
 
 
 def metric_name(tiles: int) -> str:
@@ -232,6 +235,125 @@ class Clocks:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# extra records of the GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def extra_records(args, model, proj, flat, dev, world, rank, timed, barrier):
+    """Sub-records next to the headline (never part of `value`): (1) BASELINE config 3's slide size (32 768 tiles, every
+    LongNet branch active) through the same graph-replay step; (2) BASELINE config 5: a seeded log-uniform 2k-40k mix,
+    assigned to the ranks by `packing.pack_slides` (estimated cost, LPT) and stepped eagerly (one CUDA graph per token
+    count cannot serve arbitrary lengths), measured per-rank makespan against the cost model and against the reference's
+    equal-count sharding; (3) the train-mode step (`model.train()`: Dropout / DropPath of the frozen encoder and of the
+    adapter active, no sharing across the three task passes) + AdamW, which the reference's loop runs."""
+    import math
+    import random
+
+    import torch.distributed as dist
+
+    from modaltune_b200 import packing, synthetic, train_step
+
+    out = {}
+    # (1) 32 768-tile slides
+    try:
+        host = train_step.pack_host_slide(synthetic.synthetic_slide(32768, seed=3000 + rank))
+        res = {k: v.to(dev) for k, v in host[0].items()}
+        g32 = train_step.GraphedStep(model, proj, res, host[1], flat)
+        for _ in range(2):
+            g32(res)
+        ms = timed(lambda i: g32(res), 3)
+        out["c3_32k_tiles"] = {"tiles": 32768, "ms_per_step": ms / 3, "slides_per_s": world * 3 / (ms / 1e3), "steps": 3,
+                               "n_gpus": world, "execution": "cuda-graph replay", "config": "BASELINE.json configs[2] slide size"}
+        del g32, res, host
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["c3_32k_tiles"] = {"failed": f"{type(e).__name__}: {str(e)[:200]}"}
+    # (2) variable tile counts, packed
+    try:
+        per_gpu = 12
+        rnd = random.Random(5)
+        counts = [int(math.exp(rnd.uniform(math.log(2000), math.log(40000)))) for _ in range(per_gpu * world)]
+        shards, est = packing.pack_slides(counts, world)
+        _, est_rr = packing.round_robin(counts, world)
+        mine = shards[rank]
+
+        def run_shard(_):
+            flat.zero()
+            for i in mine:
+                slide = train_step.slide_to_device(synthetic.synthetic_slide(counts[i], seed=5000 + i), dev)
+                train_step.forward_backward(model, proj, slide)
+            flat.all_reduce()
+
+        hosts = [synthetic.synthetic_slide(counts[i], seed=5000 + i) for i in mine]   # generated before the timed region
+        train_step.forward_backward(model, proj, train_step.slide_to_device(hosts[0], dev))   # warm the allocator
+        flat.zero()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        flat.zero()
+        for h in hosts:
+            train_step.forward_backward(model, proj, train_step.slide_to_device(h, dev))
+        e1.record()
+        torch.cuda.synchronize()
+        own = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        allr = [torch.zeros_like(own) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allr, own)
+        else:
+            allr = [own]
+        flat.all_reduce()
+        per_rank = [float(t) for t in allr]
+        mean = sum(per_rank) / world
+        out["c5_variable_tiles"] = {
+            "slides": len(counts), "tile_range": [min(counts), max(counts)], "n_gpus": world, "execution": "eager (one shape per slide)",
+            "per_rank_ms": per_rank, "makespan_ms": max(per_rank), "measured_imbalance": max(per_rank) / mean - 1.0,
+            "slides_per_s": len(counts) / (max(per_rank) / 1e3),
+            "cost_model": {"packed_imbalance": est["imbalance"], "equal_count_imbalance": est_rr["imbalance"],
+                           "packed_makespan_ms": est["makespan_ms"]},
+            "note": "host slides pre-generated; each step copies its slide from pageable host memory (the reference's 331 + 4 copies)",
+            "config": "BASELINE.json configs[4] (seeded log-uniform 2k-40k tiles, packed by estimated cost)"}
+    except Exception as e:
+        out["c5_variable_tiles"] = {"failed": f"{type(e).__name__}: {str(e)[:200]}"}
+    # (3) train mode + optimizer
+    try:
+        host = train_step.pack_host_slide(synthetic.synthetic_slide(args.tiles, seed=4000 + rank))
+        slide = train_step.unpack_slide({k: v.to(dev) for k, v in host[0].items()}, host[1])
+        opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-6)
+        model.train()
+
+        def train_it(_):
+            opt.zero_grad()
+            train_step.forward_backward(model, proj, slide)
+            flat.all_reduce()
+            opt.step()
+
+        for _ in range(2):
+            train_it(0)
+        ms = timed(train_it, 3)
+        out["train_mode"] = {"tiles": args.tiles, "ms_per_step": ms / 3, "slides_per_s": world * 3 / (ms / 1e3), "steps": 3,
+                             "execution": "eager, model.train(): Dropout(0.25) / DropPath in the frozen encoder and the adapter, "
+                                          "fresh masks in each of the three task passes, AdamW step included"}
+        # the same step captured in a CUDA graph (the Philox seeds and DropPath factors are drawn on the device inside
+        # the graph, so every replay has fresh masks) + AdamW on the gradients the replay hands back
+        gtr = train_step.GraphedStep(model, proj, {k: v.to(dev) for k, v in host[0].items()}, host[1], flat)
+
+        def train_graph(_):
+            opt.zero_grad()
+            gtr()
+            opt.step()
+
+        for _ in range(2):
+            train_graph(0)
+        ms = timed(train_graph, 5)
+        out["train_mode"]["graph_replay"] = {"ms_per_step": ms / 5, "slides_per_s": world * 5 / (ms / 1e3), "steps": 5}
+        del gtr
+        model.eval()
+        flat.zero()
+    except Exception as e:
+        model.eval()
+        out["train_mode"] = {"failed": f"{type(e).__name__}: {str(e)[:200]}"}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
 def main():
@@ -331,6 +453,11 @@ def main():
     events, ops.kernel_events = ops.kernel_events, None
     clk = clocks.stop() if rank == 0 else None
 
+    # ---- extra records (all ranks take part: the steps all-reduce): BASELINE configs 3 and 5, train mode ---------------
+    extras = {}
+    if not args.no_extras:
+        extras = extra_records(args, model, proj, flat, dev, world, rank, timed, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -355,11 +482,11 @@ def main():
     # DRAM bytes per launch of the backward kernel from the committed `ncu --set full` capture (read + write); only valid
     # for the configuration that capture was taken on
     traffic, traffic_src = None, None
-    if args.tiles == 10000 and config.attn_impl("bwd") == 3:
-        traffic = 243.394560e6 + 97.534208e6
-        traffic_src = "profiles/r1_ncu_attention_final.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
-    bwd_names = {0: "simt", 1: "tcgen05", 2: "tcgen05-tmem", 3: "tcgen05-tmem-aug"}
-    fwd_names = {0: "simt", 1: "tcgen05", 2: "tcgen05-tmem-acc", 3: "tcgen05-tmem-acc-2tpr"}
+    if args.tiles == 10000 and config.attn_impl("bwd") == 2 and NCU_TRAFFIC_BWD is not None:
+        traffic = NCU_TRAFFIC_BWD
+        traffic_src = "profiles/r2_ncu_attention.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+    bwd_names = {0: "simt", 1: "tcgen05", 2: "tcgen05-persistent"}
+    fwd_names = {0: "simt", 1: "tcgen05", 2: "tcgen05-persistent"}
     roofline = {
         "bound": "tensor", "kernel": f"dilated_attn_bwd[{bwd_names[config.attn_impl('bwd')]}]", "achieved": ach_bwd,
         "peak": peak, "peak_source": peak_src, "unit": "TFLOP/s", "frac": ach_bwd / peak, "traffic": traffic,
@@ -384,7 +511,19 @@ def main():
         "attention_tflops": {"fwd": ach_fwd, "bwd": ach_bwd},
         "loss": out.get("loss"),
     }
+    if extras:
+        line["extras"] = extras
     if world == 1 and not args.no_extras:
+        # same-box END-TO-END comparator: the unmodified reference modules under fp16 autocast with the installed flash-attn
+        # (its real GPU path; staged under oracle/_ref/reference by __graft_entry__.build()), one training step at this size
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_reference_gpu
+
+            line["reference_gpu_path"] = bench_reference_gpu.run(args.tiles, steps=3, warmup=2, dev=dev)
+            line["reference_gpu_path"]["speedup_ours_e2e"] = e2e_value / line["reference_gpu_path"]["slides_per_s"]
+        except Exception as e:
+            line["reference_gpu_path"] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
         # same-box comparator: the kernel the reference runs (flash_attn_func, FA2 built for sm_100) on its five per-layer
         # shapes at this token count, next to our kernels (tools/bench_fa2_branches.py); library code, comparator only
         try:

@@ -144,15 +144,18 @@ class LongNetGeneAdapter(LongNetViT):
 
     def forward_tasks(self, x, coords, genes, clinical=None, task_tokens=()):
         """Several task-conditioned passes over ONE slide (what ``multitask_forward`` does with one ``forward`` per task,
-        train_modaltune.py:156-179) sharing the token embedding and the gene-encoder output, which do not depend on the
-        task.  Eval-mode only: in train mode the reference draws fresh dropout masks per pass."""
-        if self.training:
-            return torch.cat([self._adapter_forward(x, coords, genes, clinical, t, None, None, None)
-                              for t in task_tokens], 0)
-        shared = self._shared_inputs(x, coords, genes)
-        if not (config.pass_streams() and shared[0].is_cuda and len(task_tokens) > 1):
-            return torch.cat([self._adapter_forward(None, None, None, clinical, t, None, None, None, shared=shared)
-                              for t in task_tokens], 0)
+        train_modaltune.py:156-179).  The token embedding (frozen, deterministic: its dropout sits after it, in
+        ``prepare_forward``) is computed once; the gene-encoder output is shared in eval mode and recomputed per pass in
+        train mode, where the reference draws fresh dropout masks in every ``model(...)`` call."""
+        emb = self.embed(x, coords)
+        gene = None if self.training else self.gene_encoder(genes)
+
+        def one_pass(t):
+            shared = (emb, gene if gene is not None else self.gene_encoder(genes))
+            return self._adapter_forward(None, None, None, clinical, t, None, None, None, shared=shared)
+
+        if not (config.pass_streams() and emb.is_cuda and len(task_tokens) > 1):
+            return torch.cat([one_pass(t) for t in task_tokens], 0)
         # The task passes are independent until the loss: each one runs on its own CUDA stream (autograd replays the
         # backward of every node on the stream of its forward), so kernels of different passes overlap -- the tails of
         # the attention launches and the hundreds of tiny modal-token kernels fill each other's gaps.  Under CUDA-graph
@@ -160,6 +163,7 @@ class LongNetGeneAdapter(LongNetViT):
         cur = torch.cuda.current_stream()
         streams = self._task_streams(len(task_tokens) - 1)
         outs = [None] * len(task_tokens)
+        gene_inputs = list(genes.values()) if isinstance(genes, dict) else list(genes)
         for k, t in enumerate(task_tokens):
             if k == 0:
                 continue
@@ -169,12 +173,12 @@ class LongNetGeneAdapter(LongNetViT):
             # saved tensors) must be known to the allocator as in use on the side stream: otherwise its block can be
             # handed out again on the calling stream while a side-stream kernel is still queued to read it (seen as a
             # wrong task_weight gradient: the 12-byte one-hot task token was recycled during the backward).
-            for tns in (*shared, clinical, t):
+            for tns in (emb, gene, clinical, t, *(gene_inputs if gene is None else ())):
                 if torch.is_tensor(tns) and tns.is_cuda:
                     tns.record_stream(st)
             with torch.cuda.stream(st):
-                outs[k] = self._adapter_forward(None, None, None, clinical, t, None, None, None, shared=shared)
-        outs[0] = self._adapter_forward(None, None, None, clinical, task_tokens[0], None, None, None, shared=shared)
+                outs[k] = one_pass(t)
+        outs[0] = one_pass(task_tokens[0])
         for k in range(1, len(task_tokens)):
             cur.wait_stream(streams[k - 1])
             outs[k].record_stream(cur)   # allocated on the side stream, read by the cat below on the calling stream
