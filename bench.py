@@ -52,8 +52,8 @@ def parse():
 
 UNIT = "slides/s"
 # DRAM bytes of ONE launch of the default backward attention kernel at 10 001 tokens, from the committed `ncu --set full`
-# capture (profiles/r2_ncu_attention.txt); None until that capture exists for the current kernel
-NCU_TRAFFIC_BWD = None
+# capture (profiles/r2_ncu_attention.txt)
+NCU_TRAFFIC_BWD = 243.571712e6 + 96.210176e6
 
 
 def metric_name(tiles: int) -> str:

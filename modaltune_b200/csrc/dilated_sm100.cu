@@ -908,13 +908,24 @@ int dilated_attn_fwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int
     MT_REQUIRE(counter != nullptr, "dilated_attn_fwd: cannot allocate the work counters");
     const int items = P.item_prefix[P.geo.nb];
     const int grid = items < 2 * kNumSMs ? items : 2 * kNumSMs;
-    MT_CUDA(cudaFuncSetAttribute(dilated_fwd_sm100_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 FwdPSmem::TOTAL));
+    {
+    static bool attr_set = false;   // once per process: the call is not free and never changes
+    if (!attr_set) {
+      MT_CUDA(cudaFuncSetAttribute(dilated_fwd_sm100_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdPSmem::TOTAL));
+      attr_set = true;
+    }
+  }
     dilated_fwd_sm100_persistent_kernel<<<grid, FWD_THREADS, FwdPSmem::TOTAL, st>>>(maps, P, (__nv_bfloat16*)o_br, lse_br,
                                                                                    counter);
     return check_launch("dilated_fwd_sm100_persistent_kernel");
   }
-  MT_CUDA(cudaFuncSetAttribute(dilated_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
+  {
+    static bool attr_set = false;   // once per process: the call is not free and never changes
+    if (!attr_set) {
+      MT_CUDA(cudaFuncSetAttribute(dilated_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
+      attr_set = true;
+    }
+  }
   dilated_fwd_sm100_kernel<<<P.item_prefix[P.geo.nb], FWD_THREADS, FwdSmem::TOTAL, st>>>(
       maps, P, (__nv_bfloat16*)o_br, lse_br);
   return check_launch("dilated_fwd_sm100_kernel");
@@ -2054,13 +2065,24 @@ int dilated_attn_bwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int
     MT_REQUIRE(counter != nullptr, "dilated_attn_bwd: cannot allocate the work counters");
     const int items = P.item_prefix[P.geo.nb];
     const int grid = items < kNumSMs ? items : kNumSMs;
-    MT_CUDA(cudaFuncSetAttribute(dilated_bwd_sm100_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 BwdPSmem::TOTAL));
+    {
+    static bool attr_set = false;   // once per process: the call is not free and never changes
+    if (!attr_set) {
+      MT_CUDA(cudaFuncSetAttribute(dilated_bwd_sm100_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdPSmem::TOTAL));
+      attr_set = true;
+    }
+  }
     dilated_bwd_sm100_persistent_kernel<<<grid, BWD3_THREADS, BwdPSmem::TOTAL, st>>>(maps, do_maps, dq32_maps, dq16_maps, P,
                                                                                     lse, delta_br, counter);
     return check_launch("dilated_bwd_sm100_persistent_kernel");
   }
-  MT_CUDA(cudaFuncSetAttribute(dilated_bwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd3Smem::TOTAL));
+  {
+    static bool attr_set = false;   // once per process: the call is not free and never changes
+    if (!attr_set) {
+      MT_CUDA(cudaFuncSetAttribute(dilated_bwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd3Smem::TOTAL));
+      attr_set = true;
+    }
+  }
   dilated_bwd_sm100_kernel<<<P.item_prefix[P.geo.nb], BWD3_THREADS, Bwd3Smem::TOTAL, st>>>(
       maps, do_maps, dq32_maps, dq16_maps, P, lse, delta_br);
   return check_launch("dilated_bwd_sm100_kernel");

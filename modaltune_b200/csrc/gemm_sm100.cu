@@ -476,16 +476,26 @@ extern "C" int mt_linear_sm100(const void* a, int64_t lda, const void* w, int64_
   if (pair) {
     const int tiles = (int)((M + 2 * gemm::BM - 1) / (2 * gemm::BM) * (N / gemm::BN));
     const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
-    MT_CUDA(cudaFuncSetAttribute(gemm::linear_sm100_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 gemm::Cfg<true>::SMEM_TOTAL));
+    {
+    static bool attr_set = false;   // once per process: the call is not free and never changes
+    if (!attr_set) {
+      MT_CUDA(cudaFuncSetAttribute(gemm::linear_sm100_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Cfg<true>::SMEM_TOTAL));
+      attr_set = true;
+    }
+  }
     gemm::linear_sm100_pair_kernel<<<2 * pairs, gemm::THREADS, gemm::Cfg<true>::SMEM_TOTAL, (cudaStream_t)stream>>>(
         map_a, map_b, map_c, map_c16, P);
     return check_launch("linear_sm100_pair_kernel");
   }
   const int tiles = (int)((M + gemm::BM - 1) / gemm::BM * (N / gemm::BN));
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  MT_CUDA(cudaFuncSetAttribute(gemm::linear_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               gemm::Cfg<false>::SMEM_TOTAL));
+  {
+    static bool attr_set = false;   // once per process: the call is not free and never changes
+    if (!attr_set) {
+      MT_CUDA(cudaFuncSetAttribute(gemm::linear_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Cfg<false>::SMEM_TOTAL));
+      attr_set = true;
+    }
+  }
   gemm::linear_sm100_kernel<<<grid, gemm::THREADS, gemm::Cfg<false>::SMEM_TOTAL, (cudaStream_t)stream>>>(
       map_a, map_b, map_c, map_c16, P);
   return check_launch("linear_sm100_kernel");
