@@ -3,7 +3,7 @@
     python -m modaltune_b200.launcher [launcher options] train_modaltune.py [the script's own arguments ...]
 
     launcher options
-      --reference DIR        the reference checkout (default: $MODALTUNE_REFERENCE, /root/reference, oracle/_ref/reference)
+      --reference DIR        the reference checkout (default: $MODALTUNE_REFERENCE, then /root/reference)
       --classes ours|reference   whose ``LongNetGene*Adapter`` classes ``Aggregator.create`` hands to the script
       --synthetic DIR        write a synthetic dataset (json splits, feature bags, text / clinical dicts, genomics csv) to
                              DIR and append the matching ``--train_json ... --clinical_location ...`` script arguments
@@ -49,12 +49,11 @@ TITAN_SNAPSHOT = "b2fb4f475256eb67c6e9ccbf2d6c9c3f25f20791"   # utils/constants.
 
 
 def find_reference(explicit: Optional[str] = None) -> str:
-    for cand in (explicit, os.environ.get("MODALTUNE_REFERENCE"), "/root/reference",
-                 os.path.join(REPO, "oracle", "_ref", "reference")):
+    for cand in (explicit, os.environ.get("MODALTUNE_REFERENCE"), "/root/reference"):
         if cand and os.path.isfile(os.path.join(cand, "train_modaltune.py")):
             return os.path.abspath(cand)
     raise FileNotFoundError("no reference checkout found: pass --reference DIR or set MODALTUNE_REFERENCE "
-                            "(the build container has /root/reference; `python oracle/stage_reference.py` stages a copy)")
+                            "(a checkout of martellab-sri/ModalTune)")
 
 
 # ---------------------------------------------------------------------------------------------------------------------

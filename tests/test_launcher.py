@@ -31,7 +31,8 @@ SCRIPT_ARGS = ["--mil_name", "longnetvit_gene_clinical_adapter", "--model_config
 
 def _reference_or_skip():
     try:
-        return launcher.find_reference()
+        staged = os.path.join(ROOT, "oracle", "_ref", "reference")   # test infrastructure: staged by build()
+        return launcher.find_reference(staged if os.path.isdir(staged) and not os.path.isdir("/root/reference") else None)
     except FileNotFoundError:
         pytest.skip("no reference checkout (build container: /root/reference; GPU box: oracle/_ref/reference)")
 
