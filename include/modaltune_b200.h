@@ -180,14 +180,20 @@ int mt_dilated_attn_bwd(const mt_dilated_geometry* geom, const void* qkv, int64_
 /* ---- A7/A8: Injector / Extractor cross-attention core (12 heads x 16) ---------------------------------------------
  * replaces: the softmax(QK^T/4)V inside nn.MultiheadAttention called from CrossAttentionLayer.forward_pre
  * (models/vitadapter/adapter_modules.py:225-229); the projections around it stay GEMMs.
- * q [Lq, E'] , k,v [Lk, E'] (E' = heads*head_dim = 192), o [Lq, E'], lse [Lq, heads] f32.  Any Lq/Lk: few-query/many-key
- * (Extractor) runs split-K over Lk with an LSE combine, many-query/few-key (Injector) keeps K/V in shared memory. */
-int mt_cross_attn_fwd(const void* q, const void* k, const void* v, int dtype, void* o, float* lse, int64_t lq,
-                      int64_t lk, int heads, int head_dim, float* workspace, int64_t workspace_floats, void* stream);
-int mt_cross_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
-                      int dtype, float* dq_f32, float* dk_f32, float* dv_f32, int64_t lq, int64_t lk, int heads,
-                      int head_dim, void* stream);
-int64_t mt_cross_attn_workspace_floats(int64_t lq, int64_t lk, int heads, int head_dim);
+ * q [Lq, E'] (row stride ldq elements), k, v [Lk, E'] (row stride ldkv: the two halves of one [Lk, 2E'] projection buffer
+ * are fine), o [Lq, E'] (row stride ldo; d_o uses the same stride), lse [Lq, heads] f32; E' = heads*head_dim = 192.
+ * Any Lq/Lk: few-query/many-key (Extractor) runs split-K over Lk with an LSE combine, many-query/few-key (Injector)
+ * keeps K/V in shared memory.  impl: 0 = SIMT fp32 math (exact: the fp32 parity mode; f32 or bf16 tensors),
+ * 1 = mma.sync tensor cores with TF32 operands and fp32 accumulation (f32 tensors; bf16 tensors fall back to 0).
+ * Backward: dq [Lq, E'] (row stride lddq), dk, dv [Lk, E'] (row stride lddkv) f32, written (not accumulated). */
+int mt_cross_attn_fwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int dtype, void* o,
+                      int64_t ldo, float* lse, int64_t lq, int64_t lk, int heads, int head_dim, float* workspace,
+                      int64_t workspace_floats, int impl, void* stream);
+int mt_cross_attn_bwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* o,
+                      const void* d_o, int64_t ldo, const float* lse, int dtype, float* dq_f32, int64_t lddq,
+                      float* dk_f32, float* dv_f32, int64_t lddkv, int64_t lq, int64_t lk, int heads, int head_dim,
+                      int impl, void* stream);
+int64_t mt_cross_attn_workspace_floats(int64_t lq, int64_t lk, int heads, int head_dim, int dtype, int impl);
 
 /* ---- small fused element-wise pieces ------------------------------------------------------------------------------
  * y[r, c] = a[r, c] + gate[c] * (a[r, c] + b[r, c])      Injector tail `query + gamma * attn` (adapter_modules.py:362)
@@ -195,9 +201,10 @@ int64_t mt_cross_attn_workspace_floats(int64_t lq, int64_t lk, int heads, int he
 int mt_gated_residual(const float* a, const void* b, int b_dtype, const float* gate, float* y, int64_t rows,
                       int64_t cols, void* stream);
 /* backward of mt_gated_residual: da = dy * (1 + gate), db = dy * gate (dtype of b), dgate[c] = sum_r dy * (a + b)
- * (dgate is zeroed by the call and accumulated with atomics). */
+ * (dgate is zeroed by the call and accumulated with atomics);  dysum [cols] or NULL: sum_r dy, from which the caller
+ * gets the bias gradient of the projection that produced b (gate * dysum) without a reduction pass over db. */
 int mt_gated_residual_bwd(const float* dy, const float* a, const void* b, int b_dtype, const float* gate, float* da,
-                          void* db, int db_dtype, float* dgate, int64_t rows, int64_t cols, void* stream);
+                          void* db, int db_dtype, float* dgate, float* dysum, int64_t rows, int64_t cols, void* stream);
 /* y = x + D(a + bias): residual add after fc2 (torchscale/architecture/encoder.py:169-175), bias [cols] f32 or NULL,
  * D = dropout + DropPath of the branch (drop NULL = identity). */
 int mt_residual_bias_add(const float* x, const void* a, int a_dtype, const float* bias, float* y, int64_t rows,

@@ -68,11 +68,12 @@ SIGNATURES = {
     "mt_dilated_merge_ln_fwd": (c_int, [_G, _P, _P, c_int, _P, _P, _P, _P, c_float, _P, _P, _P, _P]),
     "mt_dilated_merge_ln_bwd": (c_int, [_G, _P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
     "mt_dilated_attn_bwd": (c_int, [_G, _P, _I64, _I64, _P, _P, _P, c_int, _P, c_int, _P]),
-    "mt_cross_attn_fwd": (c_int, [_P, _P, _P, c_int, _P, _P, _I64, _I64, c_int, c_int, _P, _I64, _P]),
-    "mt_cross_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _I64, _I64, c_int, c_int, _P]),
-    "mt_cross_attn_workspace_floats": (_I64, [_I64, _I64, c_int, c_int]),
+    "mt_cross_attn_fwd": (c_int, [_P, _I64, _P, _P, _I64, c_int, _P, _I64, _P, _I64, _I64, c_int, c_int, _P, _I64, c_int, _P]),
+    "mt_cross_attn_bwd": (c_int, [_P, _I64, _P, _P, _I64, _P, _P, _I64, _P, c_int, _P, _I64, _P, _P, _I64, _I64, _I64, c_int,
+                                  c_int, c_int, _P]),
+    "mt_cross_attn_workspace_floats": (_I64, [_I64, _I64, c_int, c_int, c_int, c_int]),
     "mt_gated_residual": (c_int, [_P, _P, c_int, _P, _P, _I64, _I64, _P]),
-    "mt_gated_residual_bwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, _P, _I64, _I64, _P]),
+    "mt_gated_residual_bwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, _P, _P, _I64, _I64, _P]),
     "mt_residual_bias_add": (c_int, [_P, _P, c_int, _P, _P, _I64, _I64, _D, _P]),
     "mt_dropout_bwd_cast": (c_int, [_P, c_int, _P, c_int, _I64, _D, _P]),
     "mt_cast": (c_int, [_P, c_int, _P, c_int, _I64, _P]),

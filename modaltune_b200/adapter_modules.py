@@ -64,11 +64,11 @@ def _mha_core(mha: nn.MultiheadAttention, query, key, value):
     q = _lin(query, mha.q_proj_weight, b[:e])
     if key is value:
         kv = _lin(key, torch.cat([mha.k_proj_weight, mha.v_proj_weight], 0), b[e:])
-        k, v = kv[:, :e].contiguous(), kv[:, e:].contiguous()
+        o = ops.cross_attention_kv(q, kv, mha.num_heads)   # k | v read in place, gradient returned as one tensor
     else:
         k = _lin(key, mha.k_proj_weight, b[e:2 * e])
         v = _lin(value, mha.v_proj_weight, b[2 * e:])
-    o = ops.cross_attention(q, k, v, mha.num_heads)
+        o = ops.cross_attention(q, k, v, mha.num_heads)
     return _lin(o, mha.out_proj.weight, mha.out_proj.bias)
 
 

@@ -449,17 +449,17 @@ __global__ void __launch_bounds__(768) gated_residual_bwd_kernel(const float* __
                                                                  const TB* __restrict__ b,
                                                                  const float* __restrict__ gate, float* __restrict__ da,
                                                                  TB* __restrict__ db, float* __restrict__ dgate,
-                                                                 int64_t rows, int cols) {
+                                                                 float* __restrict__ dysum, int64_t rows, int cols) {
   // thread t owns column chunk (t % chunks) for rows (blockIdx.x * rpb + t / chunks) + k * gridDim.x * rpb;
   // blockDim.x == chunks * rpb
   extern __shared__ float gr_red[];
   const int chunks = cols / 8;
   const int rpb = blockDim.x / chunks;
   const int ch = threadIdx.x % chunks, rib = threadIdx.x / chunks;
-  float gv[8], acc[8];
+  float gv[8], acc[8], dsum[8];
   load8(gate + ch * 8, gv);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int j = 0; j < 8; ++j) acc[j] = dsum[j] = 0.f;
 #pragma unroll 2
   for (int64_t row = (int64_t)blockIdx.x * rpb + rib; row < rows; row += (int64_t)gridDim.x * rpb) {
     const int64_t off = row * cols + ch * 8;
@@ -472,23 +472,32 @@ __global__ void __launch_bounds__(768) gated_residual_bwd_kernel(const float* __
       oa[j] = d[j] * (1.f + gv[j]);
       ob[j] = d[j] * gv[j];
       acc[j] = fmaf(d[j], av[j] + bv[j], acc[j]);
+      dsum[j] += d[j];
     }
     store8(da + off, oa);
     store8(db + off, ob);
   }
-  if (rib > 0) {
+  // block-level column sums first (one reduce-add per column and block), for dgate and then, if wanted, for sum_r dy
+  for (int pass = 0; pass < (dysum != nullptr ? 2 : 1); ++pass) {
+    if (pass == 1) {
+      __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) gr_red[((rib - 1) * chunks + ch) * 8 + j] = acc[j];
-  }
-  __syncthreads();
-  if (rib == 0) {
-    for (int r = 0; r + 1 < rpb; ++r) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += gr_red[(r * chunks + ch) * 8 + j];
+      for (int j = 0; j < 8; ++j) acc[j] = dsum[j];
     }
-    float4* dst = reinterpret_cast<float4*>(dgate + ch * 8);
-    atomicAdd(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
-    atomicAdd(dst + 1, make_float4(acc[4], acc[5], acc[6], acc[7]));
+    if (rib > 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gr_red[((rib - 1) * chunks + ch) * 8 + j] = acc[j];
+    }
+    __syncthreads();
+    if (rib == 0) {
+      for (int r = 0; r + 1 < rpb; ++r) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += gr_red[(r * chunks + ch) * 8 + j];
+      }
+      float4* dst = reinterpret_cast<float4*>((pass == 0 ? dgate : dysum) + ch * 8);
+      atomicAdd(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      atomicAdd(dst + 1, make_float4(acc[4], acc[5], acc[6], acc[7]));
+    }
   }
 }
 
@@ -742,13 +751,14 @@ extern "C" int mt_add_layernorm_fwd(const float* x, const void* a, int a_dtype, 
 }
 
 extern "C" int mt_gated_residual_bwd(const float* dy, const float* a, const void* b, int b_dtype, const float* gate,
-                                     float* da, void* db, int db_dtype, float* dgate, int64_t rows, int64_t cols,
-                                     void* stream) {
+                                     float* da, void* db, int db_dtype, float* dgate, float* dysum, int64_t rows,
+                                     int64_t cols, void* stream) {
   MT_REQUIRE(cols % 8 == 0 && cols / 8 <= 256, "gated_residual_bwd: cols must be a multiple of 8, at most 2048");
   MT_REQUIRE(b_dtype == db_dtype, "gated_residual_bwd: db must have the dtype of b");
   MT_REQUIRE(gate != nullptr && dgate != nullptr, "gated_residual_bwd: gate and dgate are required");
   cudaStream_t st = (cudaStream_t)stream;
   MT_CUDA(cudaMemsetAsync(dgate, 0, sizeof(float) * (size_t)cols, st));
+  if (dysum != nullptr) MT_CUDA(cudaMemsetAsync(dysum, 0, sizeof(float) * (size_t)cols, st));
   if (rows == 0) return 0;
   const int chunks = (int)(cols / 8);
   const int rpb = 768 / chunks;                  // >= 3 (chunks <= 256)
@@ -756,11 +766,12 @@ extern "C" int mt_gated_residual_bwd(const float* dy, const float* a, const void
   int grid = grid_for(rows, rpb);
   if (grid > kNumSMs) grid = kNumSMs;            // one 768-thread block per SM; bounds the number of reduce-add flushes
   const size_t smem = sizeof(float) * 8 * (size_t)chunks * (rpb - 1);
-  MT_REQUIRE((reinterpret_cast<uintptr_t>(dgate) & 15) == 0, "gated_residual_bwd: dgate must be 16-byte aligned");
+  MT_REQUIRE(((reinterpret_cast<uintptr_t>(dgate) | reinterpret_cast<uintptr_t>(dysum)) & 15) == 0,
+             "gated_residual_bwd: dgate / dysum must be 16-byte aligned");
   if (b_dtype == MT_F32)
-    gated_residual_bwd_kernel<float><<<grid, threads, smem, st>>>(dy, a, (const float*)b, gate, da, (float*)db, dgate, rows, (int)cols);
+    gated_residual_bwd_kernel<float><<<grid, threads, smem, st>>>(dy, a, (const float*)b, gate, da, (float*)db, dgate, dysum, rows, (int)cols);
   else
-    gated_residual_bwd_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(dy, a, (const __nv_bfloat16*)b, gate, da, (__nv_bfloat16*)db, dgate, rows, (int)cols);
+    gated_residual_bwd_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(dy, a, (const __nv_bfloat16*)b, gate, da, (__nv_bfloat16*)db, dgate, dysum, rows, (int)cols);
   return check_launch("gated_residual_bwd_kernel");
 }
 

@@ -295,29 +295,60 @@ def dilated_attn_bwd(geom: Geometry, qkv, dattn, lse, delta_br, impl: int):
     return dqkv[:N]
 
 
-def cross_attn_fwd(q, k, v, heads: int):
+def _rows_ok(t: torch.Tensor) -> None:
+    assert t.is_cuda and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0, \
+        "cross-attention operands: CUDA [rows, cols] views with unit column stride and 16-byte aligned rows"
+
+
+def _ptr(t: torch.Tensor):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def cross_impl(t: torch.Tensor) -> int:
+    """``impl`` of mt_cross_attn_*: TF32 tensor cores for fp32 tensors in bf16 mode, exact fp32 SIMT math otherwise."""
+    from . import config
+    return 1 if (config.mode() == "bf16" and t.dtype == torch.float32) else 0
+
+
+def cross_attn_fwd(q, k, v, heads: int, impl: Optional[int] = None):
+    """q [Lq, E'], k / v [Lk, E'] (row-strided views allowed: e.g. the halves of one [Lk, 2E'] buffer) -> o, lse."""
     lq, e = q.shape
     lk = k.shape[0]
     hd = e // heads
-    o = torch.empty_like(q)
+    for t in (q, k, v):
+        _rows_ok(t)
+    assert k.stride(0) == v.stride(0) and k.dtype == q.dtype == v.dtype
+    impl = cross_impl(q) if impl is None else impl
+    o = torch.empty((lq, e), device=q.device, dtype=q.dtype)
     lse = torch.empty((lq, heads), device=q.device, dtype=torch.float32)
     lib = _lib.load()
-    nws = lib.mt_cross_attn_workspace_floats(lq, lk, heads, hd)
+    nws = lib.mt_cross_attn_workspace_floats(lq, lk, heads, hd, _dt(q), impl)
     ws = torch.empty(max(int(nws), 1), device=q.device, dtype=torch.float32)
-    rc = lib.mt_cross_attn_fwd(_p(q), _p(k), _p(v), _dt(q), _p(o), _p(lse), lq, lk, heads, hd, _p(ws), int(nws),
-                               _stream())
+    rc = lib.mt_cross_attn_fwd(_ptr(q), q.stride(0), _ptr(k), _ptr(v), k.stride(0), _dt(q), _ptr(o), o.stride(0), _p(lse),
+                               lq, lk, heads, hd, _p(ws), int(nws), impl, _stream())
     _check(rc, "mt_cross_attn_fwd", 2 if nws else 1)
     return o, lse
 
 
-def cross_attn_bwd(q, k, v, o, d_o, lse, heads: int):
+def cross_attn_bwd(q, k, v, o, d_o, lse, heads: int, impl: Optional[int] = None, packed_kv: bool = False):
+    """-> dq [Lq, E'], dk, dv [Lk, E'] fp32.  ``packed_kv``: dk / dv are the two halves of ONE [Lk, 2E'] buffer (returned
+    as views), the layout the gradient of a fused k|v projection wants."""
     lq, e = q.shape
     lk = k.shape[0]
+    for t in (q, k, v, o, d_o):
+        _rows_ok(t)
+    assert k.stride(0) == v.stride(0) and o.stride(0) == d_o.stride(0)
+    impl = cross_impl(q) if impl is None else impl
     dq = torch.empty((lq, e), device=q.device, dtype=torch.float32)
-    dk = torch.empty((lk, e), device=q.device, dtype=torch.float32)
-    dv = torch.empty((lk, e), device=q.device, dtype=torch.float32)
-    rc = _lib.load().mt_cross_attn_bwd(_p(q), _p(k), _p(v), _p(o), _p(d_o), _p(lse), _dt(q), _p(dq), _p(dk), _p(dv), lq,
-                                       lk, heads, e // heads, _stream())
+    if packed_kv:
+        dkv = torch.empty((lk, 2 * e), device=q.device, dtype=torch.float32)
+        dk, dv = dkv[:, :e], dkv[:, e:]
+    else:
+        dk = torch.empty((lk, e), device=q.device, dtype=torch.float32)
+        dv = torch.empty((lk, e), device=q.device, dtype=torch.float32)
+    rc = _lib.load().mt_cross_attn_bwd(_ptr(q), q.stride(0), _ptr(k), _ptr(v), k.stride(0), _ptr(o), _ptr(d_o), o.stride(0),
+                                       _p(lse), _dt(q), _ptr(dq), dq.stride(0), _ptr(dk), _ptr(dv), dk.stride(0), lq, lk,
+                                       heads, e // heads, impl, _stream())
     _check(rc, "mt_cross_attn_bwd", 5)
     return dq, dk, dv
 
@@ -416,25 +447,42 @@ def layer_norm(x, gamma, beta, add=None, out_dtype=None, row0: int = 0):
 
 
 class CrossAttnFn(torch.autograd.Function):
-    """softmax(q k^T / sqrt(hd)) v over [L, heads*hd] operands; the core of nn.MultiheadAttention in the adapter."""
+    """softmax(q k^T / sqrt(hd)) v over [L, heads*hd] operands; the core of nn.MultiheadAttention in the adapter.
+    ``kv`` None: separate k, v.  Otherwise k | v are the two halves of ``kv`` [Lk, 2 E'] (the output of one fused
+    projection GEMM), read in place through row strides, and the gradient comes back as one [Lk, 2 E'] tensor: no split /
+    concat copies on either side."""
 
     @staticmethod
-    def forward(ctx, q, k, v, heads):
-        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    def forward(ctx, q, k, v, kv, heads):
+        q = q.contiguous()
+        if kv is not None:
+            kv = kv.contiguous()
+            e = q.shape[1]
+            k, v = kv[:, :e], kv[:, e:]
+        else:
+            k, v = k.contiguous(), v.contiguous()
         o, lse = cross_attn_fwd(q, k, v, heads)
         ctx.save_for_backward(q, k, v, o, lse)
-        ctx.heads = heads
+        ctx.heads, ctx.packed = heads, kv is not None
         return o
 
     @staticmethod
     def backward(ctx, d_o):
         q, k, v, o, lse = ctx.saved_tensors
-        dq, dk, dv = cross_attn_bwd(q, k, v, o, d_o.contiguous().to(q.dtype), lse, ctx.heads)
-        return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None
+        dq, dk, dv = cross_attn_bwd(q, k, v, o, d_o.contiguous().to(q.dtype), lse, ctx.heads, packed_kv=ctx.packed)
+        if ctx.packed:
+            dkv = dk._base if dk._base is not None else torch.cat([dk, dv], 1)
+            return dq.to(q.dtype), None, None, dkv.to(k.dtype), None
+        return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None, None
 
 
 def cross_attention(q, k, v, heads: int):
-    return CrossAttnFn.apply(q, k, v, heads)
+    return CrossAttnFn.apply(q, k, v, None, heads)
+
+
+def cross_attention_kv(q, kv, heads: int):
+    """``cross_attention`` with k | v given as one [Lk, 2 E'] tensor."""
+    return CrossAttnFn.apply(q, None, None, kv, heads)
 
 
 def gated_residual_fwd(a, b, g32, out=None):
@@ -445,15 +493,17 @@ def gated_residual_fwd(a, b, g32, out=None):
     return y
 
 
-def gated_residual_bwd(dy, a, b, g32, out=None):
+def gated_residual_bwd(dy, a, b, g32, out=None, want_dysum: bool = False):
+    """-> (da, db, dgate[, dysum = sum_r dy when asked for])"""
     rows, cols = a.shape
     da = out if out is not None else torch.empty_like(a)
     db = torch.empty_like(b)
     dgate = torch.empty(cols, device=a.device, dtype=torch.float32)
+    dysum = torch.empty(cols, device=a.device, dtype=torch.float32) if want_dysum else None
     rc = _lib.load().mt_gated_residual_bwd(_p(dy), _p(a), _p(b), _dt(b), _p(g32), _p(da), _p(db), _dt(db), _p(dgate),
-                                           rows, cols, _stream())
+                                           _p(dysum), rows, cols, _stream())
     _check(rc, "mt_gated_residual_bwd")
-    return da, db, dgate
+    return (da, db, dgate, dysum) if want_dysum else (da, db, dgate)
 
 
 class _tf32:

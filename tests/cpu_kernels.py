@@ -182,7 +182,7 @@ def _heads(t, heads):
     return t.float().reshape(t.shape[0], heads, -1).transpose(0, 1)
 
 
-def cross_attn_fwd(q, k, v, heads):
+def cross_attn_fwd(q, k, v, heads, impl=None):
     qh, kh, vh = _heads(q, heads), _heads(k, heads), _heads(v, heads)
     s = qh @ kh.transpose(1, 2) / (qh.shape[-1] ** 0.5)
     lse = torch.logsumexp(s, -1)
@@ -190,11 +190,15 @@ def cross_attn_fwd(q, k, v, heads):
     return o.to(q.dtype), lse.t().contiguous()
 
 
-def cross_attn_bwd(q, k, v, o, d_o, lse, heads):
+def cross_attn_bwd(q, k, v, o, d_o, lse, heads, impl=None, packed_kv=False):
     qq, kk, vv = (t.float().detach().requires_grad_(True) for t in (q, k, v))
     with torch.enable_grad():
         out, _ = cross_attn_fwd(qq, kk, vv, heads)
-        return torch.autograd.grad(out, [qq, kk, vv], d_o.float())
+        dq, dk, dv = torch.autograd.grad(out, [qq, kk, vv], d_o.float())
+    if packed_kv:   # the two halves of one [Lk, 2E'] buffer, like the kernel wrapper
+        dkv = torch.cat([dk, dv], 1)
+        dk, dv = dkv[:, :dk.shape[1]], dkv[:, dk.shape[1]:]
+    return dq, dk, dv
 
 
 def embed_assemble(proj, bias, coords, table, cls, tile_size=256.0):
@@ -216,12 +220,15 @@ def gated_residual_fwd(a, b, g32, out=None):
     return y
 
 
-def gated_residual_bwd(dy, a, b, g32, out=None):
+def gated_residual_bwd(dy, a, b, g32, out=None, want_dysum=False):
     da = dy * (1 + g32)
+    dgate = (dy * (a + b.float())).sum(0)   # before the write below: ``out`` may alias ``dy``
+    db = (dy * g32).to(b.dtype)
+    dysum = dy.sum(0)
     if out is not None:
         out.copy_(da)
         da = out
-    return da, (dy * g32).to(b.dtype), (dy * (a + b.float())).sum(0)
+    return (da, db, dgate, dysum) if want_dysum else (da, db, dgate)
 
 
 def linear_sm100(a, w, mode=0, bias=None, residual=None, want_f32=True, want_bf16=False, stats=None, col_c1=None,

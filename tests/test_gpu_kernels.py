@@ -143,16 +143,50 @@ def test_embed_assemble_follows_the_reference_flat_index():
 @pytest.mark.parametrize("lq,lk", [(700, 66), (66, 700), (66, 10000), (5000, 13), (1, 1), (129, 65)])
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_cross_attention_core(lq, lk, dt):
+    """impl 0: the exact fp32-math SIMT kernels (fp32 parity mode) against the oracle-built stand-in."""
     g = torch.Generator().manual_seed(lq * 31 + lk)
     q, k, v = (torch.randn(n, 192, generator=g).to(dt) for n in (lq, lk, lk))
     d_o = torch.randn(lq, 192, generator=g).to(dt)
     o_c, lse_c = C.cross_attn_fwd(q, k, v, 12)
-    o, lse = ops.cross_attn_fwd(q.to(DEV), k.to(DEV), v.to(DEV), 12)
+    o, lse = ops.cross_attn_fwd(q.to(DEV), k.to(DEV), v.to(DEV), 12, impl=0)
     assert rel(o, o_c) < tol(dt) and rel(lse, lse_c) < 1e-5
     dq_c, dk_c, dv_c = C.cross_attn_bwd(q, k, v, o_c, d_o, lse_c, 12)
-    dq, dk, dv = ops.cross_attn_bwd(q.to(DEV), k.to(DEV), v.to(DEV), o, d_o.to(DEV), lse, 12)
+    dq, dk, dv = ops.cross_attn_bwd(q.to(DEV), k.to(DEV), v.to(DEV), o, d_o.to(DEV), lse, 12, impl=0)
     t = 5e-5 if dt == torch.float32 else 3e-2  # bf16: delta = dO.o uses the rounded o
     assert rel(dq, dq_c) < t and rel(dk, dk_c) < t and rel(dv, dv_c) < t
+
+
+@pytest.mark.parametrize("lq,lk", [(700, 66), (66, 700), (66, 10000), (10000, 66), (5000, 13), (1, 1), (129, 65), (66, 66),
+                                   (73, 145), (40000, 67)])
+@pytest.mark.parametrize("packed", [False, True])
+def test_cross_attention_tensor_core(lq, lk, packed):
+    """impl 1 (the bf16-mode default): mma.sync TF32 operands / fp32 accumulation, against the fp64-accurate stand-in
+    within TF32 rounding (2^-11 per operand), and the strided k | v layout of a fused projection buffer."""
+    g = torch.Generator().manual_seed(lq * 31 + lk + 7)
+    q, d_o = torch.randn(lq, 192, generator=g), torch.randn(lq, 192, generator=g)
+    kv = torch.randn(lk, 384, generator=g)
+    k, v = kv[:, :192].contiguous(), kv[:, 192:].contiguous()
+    o_c, lse_c = C.cross_attn_fwd(q, k, v, 12)
+    dq_c, dk_c, dv_c = C.cross_attn_bwd(q, k, v, o_c, d_o, lse_c, 12)
+    if packed:
+        kvd = kv.to(DEV)
+        kd, vd = kvd[:, :192], kvd[:, 192:]
+    else:
+        kd, vd = k.to(DEV), v.to(DEV)
+    qd = q.to(DEV)
+    o, lse = ops.cross_attn_fwd(qd, kd, vd, 12, impl=1)
+    assert rel(o, o_c) < 3e-3 and rel(lse, lse_c) < 1e-3
+    dq, dk, dv = ops.cross_attn_bwd(qd, kd, vd, o, d_o.to(DEV), lse, 12, impl=1, packed_kv=packed)
+    if packed:
+        assert dk._base is dv._base and dk._base.shape == (lk, 384)
+    # relative to the larger of the gradient and what feeds it: with a single key the exact dq / dk are zero (P = 1)
+    # and TF32 leaves rounding noise of the size of d_o * 2^-11
+    scale = lambda ref: max(float(ref.abs().max()), 0.1 * float(d_o.abs().max()))
+    for got, ref in ((dq, dq_c), (dk, dk_c), (dv, dv_c)):
+        assert float((got.cpu().double() - ref.double()).abs().max()) < 5e-3 * scale(ref)
+    # and against the SIMT kernels on the same device inputs (tighter on the statistics)
+    o0, lse0 = ops.cross_attn_fwd(qd, kd, vd, 12, impl=0)
+    assert rel(lse, lse0) < 1e-3 and rel(o, o0) < 3e-3
 
 
 GEOMS = [  # (N, segment lengths) -- the reference's edge geometries (SURVEY.md §4): N around segment lengths,
