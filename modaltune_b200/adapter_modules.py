@@ -243,12 +243,39 @@ class Injector(nn.Module):
 
     def forward(self, query, feat, pos=None):
         x = _rows(query).float()
+        if self._can_fuse():
+            return self._fused(x, feat, pos, 0).unsqueeze(0)
         a = self.attn.attend(x, _rows(feat).float(), pos, None)
         return ops.gated_residual(x, a, self.gamma).unsqueeze(0)
+
+    def _fused(self, x, feat, pos, row0):
+        """One autograd node for the [L, 768] side (``ops.InjectorFn``); the 66 modal tokens and the weight compositions
+        stay ordinary autograd ops (they are weight-sized)."""
+        cl = self.attn
+        mha = cl.multihead_attn
+        e = mha.embed_dim
+        b = mha.in_proj_bias
+        mem = _rows(feat).float()
+        mem = ops.layer_norm(mem, cl.norm_kq.weight, cl.norm_kq.bias, add=_pos_rows(pos, mem.shape[0]))
+        kv = _lin(mem, torch.cat([mha.k_proj_weight, mha.v_proj_weight], 0), b[e:])
+        if cl.with_cffn:   # q = (t2 Wc^T + bc) Wm^T + bm  and  a = (o Wo^T + bo) Wout^T + bout as single maps
+            wq = mha.q_proj_weight @ cl.q_proj.weight
+            bq = torch.addmv(b[:e], mha.q_proj_weight, cl.q_proj.bias)
+            wo = cl.output_proj.weight @ mha.out_proj.weight
+            bo = torch.addmv(cl.output_proj.bias, cl.output_proj.weight, mha.out_proj.bias)
+        else:
+            wq, bq, wo, bo = mha.q_proj_weight, b[:e], mha.out_proj.weight, mha.out_proj.bias
+        return ops.injector(x, kv, cl.norm.weight, cl.norm.bias, wq, bq, wo, bo, self.gamma, row0, mha.num_heads)
+
+    def _can_fuse(self):
+        cl = self.attn
+        return cl.normalize_before and not (self.training and (cl.dropout.p > 0.0 or cl.multihead_attn.dropout > 0.0))
 
     def forward_full(self, xfull, feat, pos=None):
         """Same as ``forward`` on the tile rows (1..) of the [1, N, 768] [cls | tiles] buffer; the cls row passes through."""
         x = _rows(xfull)
+        if self._can_fuse():
+            return self._fused(x, feat, pos, 1).unsqueeze(0)
         a = self.attn.attend(x, _rows(feat).float(), pos, None, tgt_row0=1)
         return ops.gated_residual(x, a, self.gamma, row0=1).unsqueeze(0)
 

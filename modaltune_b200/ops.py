@@ -579,6 +579,85 @@ def gated_residual(a, b, gate, row0: int = 0):
     return GatedResidualFn.apply(a, b, gate, row0)
 
 
+def _adapter_mm(a, b):
+    """a @ b for the adapter's skinny GEMMs: TF32 tensor cores in bf16 mode, exact fp32 in fp32 mode."""
+    from . import config
+    if config.mode() == "bf16" and a.is_cuda:
+        with _tf32():
+            return a @ b
+    return a @ b
+
+
+def _adapter_addmm(bias, a, bt):
+    from . import config
+    if config.mode() == "bf16" and a.is_cuda:
+        with _tf32():
+            return torch.addmm(bias, a, bt)
+    return torch.addmm(bias, a, bt)
+
+
+class InjectorFn(torch.autograd.Function):
+    """The whole Injector on the [cls | tiles] buffer as ONE autograd node (adapter_modules.py:338-369 with the
+    CrossAttentionLayer of :130-245 inlined):
+
+        y[row0:] = x + gate * (x + attn(LN(x), k, v) Wo^T + bo),   y[:row0] = x[:row0],   x = xfull[row0:]
+
+    ``wq`` [192, 768] / ``bq`` and ``wo`` [768, 192] / ``bo`` are the COMPOSED projections (cffn q_proj then the MHA
+    in-projection; MHA out_proj then cffn output_proj: two linear maps with nothing between them), formed by the caller
+    with differentiable [192 x 192 x 768] products, so the two [L, 192] intermediates, four of the six backward GEMMs over
+    L rows and their bias reductions never exist.  ``kv`` [M, 384] = k | v of the modal tokens.  The backward writes the
+    gradient of the residual stream once: the gated tail's ``dy (1 + gate)`` goes into the buffer the LayerNorm backward
+    then adds its part to in place (no [N, 768] autograd add, no zero fill), and the bias gradient of the output
+    projection comes from the column sums the gated-residual kernel already forms."""
+
+    @staticmethod
+    def forward(ctx, x, kv, ln_w, ln_b, wq, bq, wo, bo, gate, row0, heads):
+        x = x.contiguous()
+        xv = x[row0:]
+        kv = kv.contiguous()
+        e = wq.shape[0]
+        g32, w32, b32 = _f32(gate).contiguous(), _f32(ln_w).contiguous(), _f32(ln_b).contiguous()
+        t2, mean, rstd = layernorm_fwd(xv, w32, b32, torch.float32)
+        q = _adapter_addmm(bq, t2, wq.t())
+        o, lse = cross_attn_fwd(q, kv[:, :e], kv[:, e:], heads)
+        a = _adapter_addmm(bo, o, wo.t())
+        y = torch.empty_like(x)
+        if row0:
+            y[:row0].copy_(x[:row0])
+        gated_residual_fwd(xv, a, g32, out=y[row0:])
+        ctx.save_for_backward(x, kv, w32, wq, wo, g32, mean, rstd, t2, q, o, lse, a)
+        ctx.row0, ctx.heads = row0, heads
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, kv, w32, wq, wo, g32, mean, rstd, t2, q, o, lse, a = ctx.saved_tensors
+        row0, e = ctx.row0, wq.shape[0]
+        dy = dy.contiguous()
+        xv = x[row0:]
+        dx = torch.empty_like(x)
+        if row0:
+            dx[:row0].copy_(dy[:row0])
+        _, db, dgate, dysum = gated_residual_bwd(dy[row0:], xv, a, g32, out=dx[row0:], want_dysum=True)
+        dbo = g32 * dysum
+        dwo = _adapter_mm(db.t(), o)                       # [768, 192]
+        d_o = _adapter_mm(db, wo)                          # [L, 192]
+        del db
+        dq, dk, dv = cross_attn_bwd(q, kv[:, :e], kv[:, e:], o, d_o, lse, ctx.heads, packed_kv=True)
+        dkv = dk._base if dk._base is not None else torch.cat([dk, dv], 1)
+        dbq = dq.sum(0)
+        dwq = _adapter_mm(dq.t(), t2)                      # [192, 768]
+        dt2 = _adapter_mm(dq, wq)                          # [L, 768]
+        # dx[row0:] = dy (1 + gate) (written above) + LN'(dt2): residual and output are the same buffer
+        _, dlnw, dlnb = layernorm_bwd(dt2, xv, w32, mean, rstd, torch.float32, residual=dx[row0:], want_wgrad=True,
+                                      out=dx[row0:])
+        return dx, dkv, dlnw, dlnb, dwq, dbq, dwo, dbo, dgate, None, None
+
+
+def injector(x, kv, ln_w, ln_b, wq, bq, wo, bo, gate, row0: int, heads: int):
+    return InjectorFn.apply(x, kv, ln_w, ln_b, wq, bq, wo, bo, gate, row0, heads)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # the frozen LongNet encoder layer: one autograd node, dX-only backward
 # ---------------------------------------------------------------------------------------------------------------------
@@ -715,7 +794,8 @@ def _encoder_layer_backward_sm100(dy: torch.Tensor, saved, W: FrozenLayerWeights
     del d_aln
     dqkv = dilated_attn_bwd(geom, qkv, dattn, lse, delta_br, impl[1])             # fp32 [N, 2304]
     dh1, _ = linear_sm100(cast(dqkv, cdt), W.w_qkv_t)
-    dx, _, _ = layernorm_bwd(dh1, x, W.ln1[0], mean1, rstd1, torch.float32, residual=dx1)
+    # the bf16 twin rides along for the layer below (its first dX GEMM takes it instead of a cast pass over dy)
+    dx, _, _ = layernorm_bwd(dh1, x, W.ln1[0], mean1, rstd1, torch.float32, residual=dx1, bf16_twin=True)
     return dx
 
 

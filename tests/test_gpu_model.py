@@ -323,8 +323,9 @@ def test_graphed_step_drives_an_optimizer_across_replays():
             if not a.requires_grad or (n.startswith("gene_encoder.") and n.endswith(dead)):
                 continue
             moved = max(moved, float((a - ref[n]).abs().max()))
-            # Adam normalises the step: a gradient entry at the noise floor may move by up to 2 * lr either way
-            assert float((a - b).abs().max()) <= 2.5e-3, n
+            # Adam normalises the step: a gradient entry at the noise floor (split-K reduce-adds arrive in a different
+            # order in every run) may move by up to 2 * lr either way in EACH of the two steps
+            assert float((a - b).abs().max()) <= 4.5e-3, n
             assert _cos(a - ref[n], b - ref[n]) > 0.98 or float((a - ref[n]).norm()) < 1e-6, n
         assert moved > 5e-4                          # the optimizer really stepped on the graph's gradients
         # frozen weights replaced after capture: the next call must re-capture (new derived bf16 copies), not crash / go stale
