@@ -113,15 +113,22 @@ int mt_gelu_ln_bwd(const void* dy, int dy_dtype, const void* h, int h_dtype, con
  * C[M, N] = A[M, K] . W[N, K]^T with bf16 operands (row strides lda / ldw in elements), fp32 accumulation in TMEM;
  * N must be a multiple of 256 and K of 64.  What happens to the accumulator is the epilogue `mode`:
  *   MT_EPI_PLAIN        out = acc [+ bias] [+ residual]                       (f32 and / or bf16 output)
- *   MT_EPI_GELU_STATS   out_f32 = h = acc + bias;  out_bf16 = u = gelu_erf(h);  stats[row][slab] = (sum u, sum u^2) of the
+ *   MT_EPI_GELU_STATS   h = acc + bias (out_f32, optional);  out_bf16 = u = gelu_erf(h);  out_aux_bf16 = gelu'(h) (optional);
+ *                       stats[row][slab] = (sum u, sum u^2) of the
  *                       ROUNDED u over each 128-column slab (`stats` is [M, N / 128, 2], every entry written once, no
  *                       atomics: deterministic): fc1 + GELU + the statistics of ffn_layernorm
  *   MT_EPI_LN_RESIDUAL  out = residual + rstd[row] * (acc - mean[row] * col_c1) + col_c2 with mean / rstd from the
  *                       ln_cols / 128 slab partials of `stats` (added in a fixed order) over `ln_cols` columns: fc2 applied to LayerNorm(u) WITHOUT materialising it, for
- *                       W = W2 diag(gamma), col_c1 = W 1, col_c2 = W2 beta + b2, + the residual add. */
+ *                       W = W2 diag(gamma), col_c1 = W 1, col_c2 = W2 beta + b2, + the residual add.
+ *   MT_EPI_GELU_LN_BWD  out = gelu'(h) * rstd * (acc - m1 - uhat * m2), uhat = (gelu(h) - mean) * rstd: the backward of
+ *                       GELU + ffn_layernorm applied to the accumulator of fc2's dX GEMM, for W = (W2 diag(gamma))^T
+ *                       (acc_j = gamma_j dn_j); h = `residual` (fc1's fp32 output incl. bias), `stats` = [M, 4] rows of
+ *                       (mean, rstd, m1, m2) from mt_ffn_bwd_prep.  The [M, 3072] fp32 gradient of the LayerNorm output
+ *                       and the separate GELU'-LN' kernel do not exist on this path. */
 #define MT_EPI_PLAIN 0
 #define MT_EPI_GELU_STATS 3
 #define MT_EPI_LN_RESIDUAL 4
+#define MT_EPI_GELU_LN_BWD 5
 typedef struct {
   int32_t mode;
   int32_t ln_cols;          /* MT_EPI_LN_RESIDUAL: number of columns the statistics were taken over (3072)      */
@@ -137,9 +144,26 @@ typedef struct {
   float* out_f32;           /* [M, N] or NULL, row stride ld_out_f32 (0 = N)                                     */
   void* out_bf16;           /* [M, N] or NULL, row stride ld_out_bf16 (0 = N)                                    */
   int64_t ld_out_f32, ld_out_bf16, ld_residual;
+  void* out_aux_bf16;       /* MT_EPI_GELU_STATS: [M, N] gelu'(h) in bf16 or NULL (then out_f32 = h is required): with  */
+                            /*   it the backward needs neither h nor a second erf / exp per element                    */
+  const void* in_u_bf16;    /* MT_EPI_GELU_LN_BWD: gelu(h) and gelu'(h) [M, N] bf16 as written by MT_EPI_GELU_STATS,   */
+  const void* in_g_bf16;    /*   used instead of h (`residual` NULL)                                                   */
 } mt_linear_epilogue;
 int mt_linear_sm100(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t M, int64_t N, int64_t K,
                     const mt_linear_epilogue* epilogue, void* stream);
+
+/* Row means of the LayerNorm(3072) backward, formed BEFORE fc2's dX GEMM from [rows, 768] tensors only (backward of
+ * feedforward_network.py:135-143 with ffn_layernorm folded into fc2): with dn = dy W2,
+ *   m1 = mean_j(gamma_j dn_j)       = dy . c1 / ln_cols,              c1 = (W2 diag gamma) 1   (what the forward used)
+ *   m2 = mean_j(gamma_j dn_j uhat_j) = dy . (y - x1 - c2) / ln_cols,  because fc2's folded forward IS
+ *                                      y - x1 - c2 = (W2 diag gamma) uhat.
+ * dy [rows, cols] f32 = gradient of the layer output, y = layer output, x1 = the FFN's residual input (f32), c1, c2
+ * [cols]; mean, rstd [rows] = the statistics of ffn_layernorm.  Writes rowv [rows, 4] = (mean, rstd, m1, m2) for
+ * MT_EPI_GELU_LN_BWD and dy_bf16 [rows, cols] (the A operand of that GEMM; the dots use these ROUNDED values so that
+ * m1 is exactly the mean of the accumulator row).  cols = 768. */
+int mt_ffn_bwd_prep(const float* dy, const float* y, const float* x1, const float* c1, const float* c2,
+                    const float* mean, const float* rstd, float* rowv, void* dy_bf16, int64_t rows, int64_t cols,
+                    int64_t ln_cols, void* stream);
 
 /* ---- A3/A4: dilated attention, all branches, per-branch outputs ---------------------------------------------------
  * replaces: DilatedAttention.gathering x3 + attention_ops -> flash_attn_func, 5 times per layer

@@ -42,10 +42,11 @@ class LinearEpilogue(Structure):
     _fields_ = [("mode", c_int32), ("ln_cols", c_int32), ("ln_eps", c_float), ("impl", c_int32),
                 ("bias", c_void_p), ("residual", c_void_p), ("col_c1", c_void_p), ("col_c2", c_void_p),
                 ("stats", c_void_p), ("ln_mean_out", c_void_p), ("ln_rstd_out", c_void_p), ("out_f32", c_void_p), ("out_bf16", c_void_p),
-                ("ld_out_f32", c_int64), ("ld_out_bf16", c_int64), ("ld_residual", c_int64)]
+                ("ld_out_f32", c_int64), ("ld_out_bf16", c_int64), ("ld_residual", c_int64),
+                ("out_aux_bf16", c_void_p), ("in_u_bf16", c_void_p), ("in_g_bf16", c_void_p)]
 
 
-MT_EPI_PLAIN, MT_EPI_GELU_STATS, MT_EPI_LN_RESIDUAL = 0, 3, 4
+MT_EPI_PLAIN, MT_EPI_GELU_STATS, MT_EPI_LN_RESIDUAL, MT_EPI_GELU_LN_BWD = 0, 3, 4, 5
 
 _G = POINTER(DilatedGeometry)
 _D = POINTER(Dropout)
@@ -64,6 +65,7 @@ SIGNATURES = {
     "mt_gelu_ln_fwd": (c_int, [_P, c_int, _P, _P, _P, _P, c_int, _P, _P, _I64, _I64, c_float, _P]),
     "mt_gelu_ln_bwd": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, _P, c_int, _I64, _I64, _P]),
     "mt_linear_sm100": (c_int, [_P, _I64, _P, _I64, _I64, _I64, _I64, POINTER(LinearEpilogue), _P]),
+    "mt_ffn_bwd_prep": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
     "mt_dilated_attn_fwd": (c_int, [_G, _P, _I64, _I64, c_int, _P, _P, c_int, _P]),
     "mt_dilated_merge_ln_fwd": (c_int, [_G, _P, _P, c_int, _P, _P, _P, _P, c_float, _P, _P, _P, _P]),
     "mt_dilated_merge_ln_bwd": (c_int, [_G, _P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),

@@ -24,7 +24,18 @@ _state = {
     # frozen linear layers of the encoder in bf16 mode: "sm100" = the hand-written tcgen05 GEMM with fused epilogues
     # (mt_linear_sm100), "cublas" = library GEMMs + separate element-wise kernels (the round-1 path, kept for comparison)
     "gemm": os.environ.get("MODALTUNE_B200_GEMM", "sm100"),
+    # backward of GELU + ffn_layernorm inside the epilogue of fc2's dX GEMM (MT_EPI_GELU_LN_BWD); "0" = the separate
+    # GELU'-LN' kernel between two plain dX GEMMs (the path before, kept for comparison)
+    "ffn_bwd_fused": os.environ.get("MODALTUNE_B200_FFN_BWD_FUSED", "1") != "0",
 }
+
+
+def ffn_bwd_fused() -> bool:
+    return _state["ffn_bwd_fused"]
+
+
+def set_ffn_bwd_fused(on: bool) -> None:
+    _state["ffn_bwd_fused"] = bool(on)
 
 
 def gemm_impl() -> str:

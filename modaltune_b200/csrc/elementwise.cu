@@ -555,6 +555,42 @@ __global__ void __launch_bounds__(256) cast_kernel(const TS* __restrict__ s, TD*
   }
 }
 
+// Row means of the LayerNorm(3072) backward formed before fc2's dX GEMM (see mt_ffn_bwd_prep in the header): per row
+// m1 = dy16 . c1 / C, m2 = dy16 . (y - x1 - c2) / C with dy16 = dy rounded to bf16 (also written: the GEMM's A operand).
+__global__ void __launch_bounds__(RowCfg<768>::THREADS, RowCfg<768>::MINB)
+ffn_bwd_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x1,
+                    const float* __restrict__ c1, const float* __restrict__ c2, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, float4* __restrict__ rowv, __nv_bfloat16* __restrict__ dy16,
+                    int64_t rows, float inv_ln_cols) {
+  using C = RowCfg<768>;
+  __shared__ float red[C::RPB * (C::TPR / 32) + 1];
+  const int t = threadIdx.x % C::TPR, rib = threadIdx.x / C::TPR;
+  float a1[8], a2[8];
+  load8(c1 + t * 8, a1);
+  load8(c2 + t * 8, a2);
+  for (int64_t row0 = (int64_t)blockIdx.x * C::RPB; row0 < rows; row0 += (int64_t)gridDim.x * C::RPB) {
+    const int64_t row = row0 + rib;
+    const bool live = row < rows;
+    float s1 = 0.f, s2 = 0.f;
+    if (live) {
+      float d[8], yv[8], xv[8];
+      load8(dy + row * 768 + t * 8, d);
+      load8(y + row * 768 + t * 8, yv);
+      load8(x1 + row * 768 + t * 8, xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        d[j] = __bfloat162float(__float2bfloat16_rn(d[j]));
+        s1 = fmaf(d[j], a1[j], s1);
+        s2 = fmaf(d[j], (yv[j] - xv[j]) - a2[j], s2);
+      }
+      store8(dy16 + row * 768 + t * 8, d);
+    }
+    const float m1 = row_sum<C::TPR>(s1, red, rib, t) * inv_ln_cols;
+    const float m2 = row_sum<C::TPR>(s2, red, rib, t) * inv_ln_cols;
+    if (live && t == 0) rowv[row] = make_float4(mean[row], rstd[row], m1, m2);
+  }
+}
+
 static inline int grid_for(int64_t work_items, int per_block) {
   int64_t blocks = (work_items + per_block - 1) / per_block;
   int64_t cap = (int64_t)kNumSMs * 8;
@@ -810,6 +846,20 @@ extern "C" int mt_dropout_bwd_cast(const void* src, int src_dtype, void* dst, in
   else
     dropout_bwd_cast_kernel<bf, float><<<grid, 256, 0, st>>>((const bf*)src, (float*)dst, n8, D);
   return check_launch("dropout_bwd_cast_kernel");
+}
+
+extern "C" int mt_ffn_bwd_prep(const float* dy, const float* y, const float* x1, const float* c1, const float* c2,
+                               const float* mean, const float* rstd, float* rowv, void* dy_bf16, int64_t rows,
+                               int64_t cols, int64_t ln_cols, void* stream) {
+  MT_REQUIRE(cols == 768 && ln_cols > 0, "ffn_bwd_prep: cols must be 768 (got %lld)", (long long)cols);
+  MT_REQUIRE(dy && y && x1 && c1 && c2 && mean && rstd && rowv && dy_bf16, "ffn_bwd_prep: NULL argument");
+  MT_REQUIRE(((uintptr_t)rowv & 15) == 0, "ffn_bwd_prep: rowv must be 16-byte aligned");
+  if (rows == 0) return 0;
+  using C = RowCfg<768>;
+  const int grid = grid_for(rows, C::RPB);
+  ffn_bwd_prep_kernel<<<grid, C::THREADS, 0, (cudaStream_t)stream>>>(dy, y, x1, c1, c2, mean, rstd, (float4*)rowv,
+                                                                     (__nv_bfloat16*)dy_bf16, rows, 1.0f / (float)ln_cols);
+  return check_launch("ffn_bwd_prep_kernel");
 }
 
 extern "C" int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream) {

@@ -61,10 +61,14 @@ struct Params {
   const float* col_c1;      // [N] (mode 4)
   const float* col_c2;      // [N] (mode 4)
   float* stats;             // [M, cols / 128, 2]: (sum, sum of squares) per 128-column slab: written in mode 3, read in mode 4
+  const float4* rowv;       // mode 5: [M] (mean, rstd, m1, m2) per row (mt_ffn_bwd_prep)
   float* mean_out;          // mode 4: [M] or null
   float* rstd_out;
   float* out_f32;           // [M, N] or null
   __nv_bfloat16* out_bf16;  // [M, N] or null
+  __nv_bfloat16* out_aux;   // mode 3: [M, N] gelu'(h) in bf16 or null
+  const __nv_bfloat16* in_u;   // mode 5 without h: [M, N] gelu(h) and gelu'(h) in bf16 as written by mode 3
+  const __nv_bfloat16* in_g;
   int64_t ld_res;
   float ln_eps;
   float inv_ln_cols;        // 1 / (number of columns the statistics were summed over)
@@ -86,9 +90,25 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(copysignf(erf_abs, x), half_x, half_x);     // 0.5 x (1 + erf(x / sqrt 2))
 }
 
+// u = gelu(x) and gelu'(x) = Phi(x) + x phi(x) from one erf evaluation (same two MUFU ops as gelu_erf)
+__device__ __forceinline__ void gelu_erf_val_grad(float x, float& u, float& du) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = ex2(-z * z * 1.4426950408889634f);    // exp(-x^2 / 2)
+  const float erf_abs = 1.f - p * t * e;
+  const float cdf = fmaf(copysignf(erf_abs, x), 0.5f, 0.5f);
+  u = x * cdf;
+  du = fmaf(x * 0.3989422804014327f, e, cdf);
+}
+
 template <bool PAIR>
 __device__ __forceinline__ void linear_body(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_c,
-                                            const CUtensorMap& map_c16, const Params& P) {
+                                            const CUtensorMap& map_c16, const CUtensorMap& map_aux, const Params& P) {
   using C = Cfg<PAIR>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -121,6 +141,7 @@ __device__ __forceinline__ void linear_body(const CUtensorMap& map_a, const CUte
     tma_prefetch_desc(&map_b);
     if (P.out_f32 != nullptr) tma_prefetch_desc(&map_c);
     if (P.out_bf16 != nullptr) tma_prefetch_desc(&map_c16);
+    if (P.out_aux != nullptr) tma_prefetch_desc(&map_aux);
   }
   if (warp == 1) {
     if (PAIR) {
@@ -216,7 +237,7 @@ __device__ __forceinline__ void linear_body(const CUtensorMap& map_a, const CUte
     const uint32_t stg32_u32 = sbase + C::SMEM_STG32 + ew * STG_F32;
     const uint32_t stg16_u32 = sbase + C::SMEM_STG16 + ew * STG_BF16;
     // one 32-column chunk of this warp's 32 rows: fp32 and / or bf16 copy
-    auto store_chunk = [&](const float (&o)[32], int col, int row0, bool f32, bool b16) {
+    auto store_chunk = [&](const float (&o)[32], int col, int row0, bool f32, bool b16, bool aux = false) {
       if (lane == 0) bulk_wait_group_read<0>();       // the previous stores of this warp have read the staging tiles
       __syncwarp();
       if (f32) {
@@ -236,7 +257,7 @@ __device__ __forceinline__ void linear_body(const CUtensorMap& map_a, const CUte
       __syncwarp();
       if (lane == 0) {
         if (f32) tma_store_2d(&map_c, stg32_u32, col, row0);
-        if (b16) tma_store_2d(&map_c16, stg16_u32, col, row0);
+        if (b16) tma_store_2d(aux ? &map_aux : &map_c16, stg16_u32, col, row0);
         bulk_commit_group();
       }
     };
@@ -273,6 +294,8 @@ __device__ __forceinline__ void linear_body(const CUtensorMap& map_a, const CUte
           P.rstd_out[row] = rstd;
         }
       }
+      float4 rv = make_float4(0.f, 1.f, 0.f, 0.f);
+      if (P.mode == 5 && row_ok) rv = P.rowv[row];
       float s1 = 0.f, s2 = 0.f;
       const int row0 = m0 + lane_grp * 32;          // first row of this warp's 32-row slab (rows >= M are clipped by TMA)
 #pragma unroll 1
@@ -292,10 +315,14 @@ __device__ __forceinline__ void linear_body(const CUtensorMap& map_a, const CUte
             const float4 b = *reinterpret_cast<const float4*>(P.bias + col + i);
             v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
           }
-          store_chunk(v, col, row0, true, false);
+          if (P.out_f32 != nullptr) store_chunk(v, col, row0, true, false);
+          float gd[32];   // gelu'(h): costs one FMA more than gelu(h) alone (the exponential is shared)
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const __nv_bfloat162 u2 = __floats2bfloat162_rn(gelu_erf(v[i]), gelu_erf(v[i + 1]));
+            float u0, u1;
+            gelu_erf_val_grad(v[i], u0, gd[i]);
+            gelu_erf_val_grad(v[i + 1], u1, gd[i + 1]);
+            const __nv_bfloat162 u2 = __floats2bfloat162_rn(u0, u1);
             const float2 f = __bfloat1622float2(u2);
             s1 += f.x + f.y;
             s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, s2));
@@ -303,6 +330,44 @@ __device__ __forceinline__ void linear_body(const CUtensorMap& map_a, const CUte
             v[i + 1] = f.y;
           }
           store_chunk(v, col, row0, false, true);
+          if (P.out_aux != nullptr) store_chunk(gd, col, row0, false, true, true);
+        } else if (P.mode == 5) {
+          // backward of GELU + LayerNorm(3072) on the accumulator of the dX GEMM of fc2 (W = (W2 diag gamma)^T, so
+          // acc_j = gamma_j dn_j): d_h_j = gelu'(h_j) rstd (acc_j - m1 - uhat_j m2), uhat_j = (gelu(h_j) - mean) rstd,
+          // with h = fc1's fp32 output (P.residual) and the row means m1, m2 formed BEFORE the GEMM (mt_ffn_bwd_prep)
+          if (row_ok && P.in_u != nullptr) {
+            // gelu(h) (the ROUNDED values the forward's statistics were taken over) and gelu'(h) saved by the forward
+            const uint4* us = reinterpret_cast<const uint4*>(P.in_u + (int64_t)row * P.N + col);
+            const uint4* gs = reinterpret_cast<const uint4*>(P.in_g + (int64_t)row * P.N + col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 uu = us[i], gg = gs[i];
+              const __nv_bfloat162* up = reinterpret_cast<const __nv_bfloat162*>(&uu);
+              const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&gg);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 uf = __bfloat1622float2(up[j]), gf = __bfloat1622float2(gp[j]);
+                const int e = 8 * i + 2 * j;
+                v[e] = gf.x * rv.y * (v[e] - rv.z - (uf.x - rv.x) * rv.y * rv.w);
+                v[e + 1] = gf.y * rv.y * (v[e + 1] - rv.z - (uf.y - rv.x) * rv.y * rv.w);
+              }
+            }
+          } else if (row_ok) {
+            const float* hs = P.residual + (int64_t)row * P.ld_res + col;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 h4 = *reinterpret_cast<const float4*>(hs + i);
+              const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float u, du;
+                gelu_erf_val_grad(hv[j], u, du);
+                const float uh = (u - rv.x) * rv.y;
+                v[i + j] = du * rv.y * (v[i + j] - rv.z - uh * rv.w);
+              }
+            }
+          }
+          store_chunk(v, col, row0, P.out_f32 != nullptr, P.out_bf16 != nullptr);
         } else {
           if (P.mode == 4) {
 #pragma unroll
@@ -347,15 +412,16 @@ __device__ __forceinline__ void linear_body(const CUtensorMap& map_a, const CUte
 
 __global__ void __launch_bounds__(THREADS, 1)
 linear_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c16, const Params P) {
-  linear_body<false>(map_a, map_b, map_c, map_c16, P);
+                    const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c16,
+                    const __grid_constant__ CUtensorMap map_aux, const Params P) {
+  linear_body<false>(map_a, map_b, map_c, map_c16, map_aux, P);
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 linear_sm100_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c16,
-                         const Params P) {
-  linear_body<true>(map_a, map_b, map_c, map_c16, P);
+                         const __grid_constant__ CUtensorMap map_aux, const Params P) {
+  linear_body<true>(map_a, map_b, map_c, map_c16, map_aux, P);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -430,19 +496,30 @@ extern "C" int mt_linear_sm100(const void* a, int64_t lda, const void* w, int64_
              (long long)N, (long long)K);
   MT_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)w & 15) == 0,
              "linear_sm100: operands must be 16-byte aligned with row strides that are multiples of 8 elements");
-  MT_REQUIRE(ep->mode == MT_EPI_PLAIN || ep->mode == MT_EPI_GELU_STATS || ep->mode == MT_EPI_LN_RESIDUAL, "linear_sm100: bad epilogue mode %d", ep->mode);
+  MT_REQUIRE(ep->mode == MT_EPI_PLAIN || ep->mode == MT_EPI_GELU_STATS || ep->mode == MT_EPI_LN_RESIDUAL ||
+                 ep->mode == MT_EPI_GELU_LN_BWD, "linear_sm100: bad epilogue mode %d", ep->mode);
   MT_REQUIRE(ep->out_f32 != nullptr || ep->out_bf16 != nullptr, "linear_sm100: no output");
   if (ep->mode == MT_EPI_GELU_STATS)
-    MT_REQUIRE(ep->bias && ep->out_f32 && ep->out_bf16 && ep->stats, "linear_sm100: GELU epilogue needs bias, both outputs, stats");
+    MT_REQUIRE(ep->bias && ep->out_bf16 && ep->stats && (ep->out_f32 || ep->out_aux_bf16),
+               "linear_sm100: GELU epilogue needs bias, the bf16 output, stats and h (out_f32) or gelu' (out_aux_bf16)");
+  MT_REQUIRE(ep->out_aux_bf16 == nullptr || ep->mode == MT_EPI_GELU_STATS, "linear_sm100: out_aux_bf16 belongs to the GELU epilogue");
   if (ep->mode == MT_EPI_LN_RESIDUAL)
     MT_REQUIRE(ep->col_c1 && ep->col_c2 && ep->stats && ep->ln_cols > 0, "linear_sm100: LN-fold epilogue needs c1, c2, stats, ln_cols");
+  if (ep->mode == MT_EPI_GELU_LN_BWD)
+    MT_REQUIRE((ep->residual || (ep->in_u_bf16 && ep->in_g_bf16)) && ep->stats && ((uintptr_t)ep->stats & 15) == 0 &&
+                   ep->bias == nullptr && (((uintptr_t)ep->in_u_bf16 | (uintptr_t)ep->in_g_bf16) & 15) == 0,
+               "linear_sm100: GELU-LN backward epilogue needs h (residual) or gelu / gelu' (in_u_bf16, in_g_bf16), "
+               "stats = [M, 4] row vector, no bias");
   gemm::Params P;
   P.M = (int)M; P.N = (int)N; P.K = (int)K;
+  P.rowv = reinterpret_cast<const float4*>(ep->stats);
   P.mode = ep->mode;
   P.bias = ep->bias; P.residual = ep->residual; P.col_c1 = ep->col_c1; P.col_c2 = ep->col_c2; P.stats = ep->stats;
   P.mean_out = ep->ln_mean_out; P.rstd_out = ep->ln_rstd_out;
   MT_REQUIRE((P.mean_out == nullptr) == (P.rstd_out == nullptr), "linear_sm100: ln_mean_out and ln_rstd_out go together");
   P.out_f32 = ep->out_f32; P.out_bf16 = (__nv_bfloat16*)ep->out_bf16;
+  P.out_aux = (__nv_bfloat16*)ep->out_aux_bf16;
+  P.in_u = (const __nv_bfloat16*)ep->in_u_bf16; P.in_g = (const __nv_bfloat16*)ep->in_g_bf16;
   const int64_t ld_f32 = ep->ld_out_f32 ? ep->ld_out_f32 : N;
   const int64_t ld_bf16 = ep->ld_out_bf16 ? ep->ld_out_bf16 : N;
   P.ld_res = ep->ld_residual ? ep->ld_residual : N;
@@ -456,9 +533,10 @@ extern "C" int mt_linear_sm100(const void* a, int64_t lda, const void* w, int64_
   if (impl == 0) impl = M > gemm::BM ? 2 : 1;
   MT_REQUIRE(impl == 1 || impl == 2, "linear_sm100: bad impl %d", ep->impl);
   const bool pair = impl == 2;
-  CUtensorMap map_a, map_b, map_c, map_c16;
+  CUtensorMap map_a, map_b, map_c, map_c16, map_aux;
   memset(&map_c, 0, sizeof(map_c));
   memset(&map_c16, 0, sizeof(map_c16));
+  memset(&map_aux, 0, sizeof(map_aux));
   int rc = gemm::encode_2d(&map_a, a, M, K, lda, gemm::BM);
   if (rc) return rc;
   rc = gemm::encode_2d(&map_b, w, N, K, ldw, pair ? gemm::BN / 2 : gemm::BN);
@@ -473,6 +551,11 @@ extern "C" int mt_linear_sm100(const void* a, int64_t lda, const void* w, int64_
     rc = gemm::encode_out(&map_c16, ep->out_bf16, M, N, ld_bf16, true);
     if (rc) return rc;
   }
+  if (ep->out_aux_bf16 != nullptr) {
+    MT_REQUIRE(((uintptr_t)ep->out_aux_bf16 & 15) == 0, "linear_sm100: the auxiliary bf16 output must be 16-byte aligned");
+    rc = gemm::encode_out(&map_aux, ep->out_aux_bf16, M, N, N, true);
+    if (rc) return rc;
+  }
   if (pair) {
     const int tiles = (int)((M + 2 * gemm::BM - 1) / (2 * gemm::BM) * (N / gemm::BN));
     const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
@@ -484,7 +567,7 @@ extern "C" int mt_linear_sm100(const void* a, int64_t lda, const void* w, int64_
     }
   }
     gemm::linear_sm100_pair_kernel<<<2 * pairs, gemm::THREADS, gemm::Cfg<true>::SMEM_TOTAL, (cudaStream_t)stream>>>(
-        map_a, map_b, map_c, map_c16, P);
+        map_a, map_b, map_c, map_c16, map_aux, P);
     return check_launch("linear_sm100_pair_kernel");
   }
   const int tiles = (int)((M + gemm::BM - 1) / gemm::BM * (N / gemm::BN));
@@ -497,6 +580,6 @@ extern "C" int mt_linear_sm100(const void* a, int64_t lda, const void* w, int64_
     }
   }
   gemm::linear_sm100_kernel<<<grid, gemm::THREADS, gemm::Cfg<false>::SMEM_TOTAL, (cudaStream_t)stream>>>(
-      map_a, map_b, map_c, map_c16, P);
+      map_a, map_b, map_c, map_c16, map_aux, P);
   return check_launch("linear_sm100_kernel");
 }

@@ -355,7 +355,8 @@ def cross_attn_bwd(q, k, v, o, d_o, lse, heads: int, impl: Optional[int] = None,
 
 def linear_sm100(a: torch.Tensor, w: torch.Tensor, mode: int = _lib.MT_EPI_PLAIN, bias=None, residual=None,
                  want_f32: bool = True, want_bf16: bool = False, stats=None, col_c1=None, col_c2=None, ln_cols: int = 0,
-                 eps: float = LN_EPS, out_f32=None, out_bf16=None, ln_mean_out=None, ln_rstd_out=None, impl: int = 0):
+                 eps: float = LN_EPS, out_f32=None, out_bf16=None, ln_mean_out=None, ln_rstd_out=None, impl: int = 0,
+                 out_aux=None, in_u=None, in_g=None):
     """C = A W^T on the tcgen05 tensor cores with a fused epilogue (``mt_linear_sm100``): a [M, K] bf16, w [N, K] bf16
     (nn.Linear layout).  Returns (out_f32 or None, out_bf16 or None).  See include/modaltune_b200.h for the modes."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
@@ -374,6 +375,9 @@ def linear_sm100(a: torch.Tensor, w: torch.Tensor, mode: int = _lib.MT_EPI_PLAIN
     ep.bias, ep.residual, ep.col_c1, ep.col_c2, ep.stats = ptr(bias), ptr(residual), ptr(col_c1), ptr(col_c2), ptr(stats)
     ep.out_f32, ep.out_bf16 = ptr(out_f32), ptr(out_bf16)
     ep.ln_mean_out, ep.ln_rstd_out = ptr(ln_mean_out), ptr(ln_rstd_out)
+    for t in (out_aux, in_u, in_g):
+        assert t is None or (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape == (M, N))
+    ep.out_aux_bf16, ep.in_u_bf16, ep.in_g_bf16 = ptr(out_aux), ptr(in_u), ptr(in_g)
     ep.ld_out_f32 = out_f32.stride(0) if out_f32 is not None else 0
     ep.ld_out_bf16 = out_bf16.stride(0) if out_bf16 is not None else 0
     ep.ld_residual = residual.stride(0) if residual is not None else 0
@@ -382,6 +386,19 @@ def linear_sm100(a: torch.Tensor, w: torch.Tensor, mode: int = _lib.MT_EPI_PLAIN
                                          w.stride(0), M, N, K, ctypes.byref(ep), _stream())
     _check(rc, "mt_linear_sm100")
     return out_f32, out_bf16
+
+
+def ffn_bwd_prep(dy, y, x1, c1, c2, mean, rstd, ln_cols: int):
+    """-> (rowv [rows, 4] = (mean, rstd, m1, m2), dy in bf16): the per-row inputs of the MT_EPI_GELU_LN_BWD epilogue."""
+    rows, cols = dy.shape
+    for t in (dy, y, x1):
+        assert t.dtype == torch.float32 and t.shape == (rows, cols)
+    rowv = torch.empty((rows, 4), device=dy.device, dtype=torch.float32)
+    dy16 = torch.empty((rows, cols), device=dy.device, dtype=torch.bfloat16)
+    rc = _lib.load().mt_ffn_bwd_prep(_p(dy), _p(y), _p(x1), _p(c1), _p(c2), _p(mean), _p(rstd), _p(rowv), _p(dy16), rows,
+                                     cols, int(ln_cols), _stream())
+    _check(rc, "mt_ffn_bwd_prep")
+    return rowv, dy16
 
 
 def embed_assemble(proj, bias, coords, table, cls, tile_size: float = 256.0):
@@ -704,6 +721,7 @@ class FrozenLayerWeights:
                 self.w_o_t = self.w_o.t().contiguous()
                 self.w_1_t = self.w_1.t().contiguous()
                 self.w_2_t = self.w_2.t().contiguous()
+                self.w_2g_t = self.w_2g.t().contiguous()       # [3072, 768]: dX of fc2 with the LayerNorm scale folded in
         self.key = key
         return self
 
@@ -765,26 +783,43 @@ def _encoder_layer_forward_sm100(x: torch.Tensor, W: FrozenLayerWeights, geom: G
     del a_ln
     h2, mean2, rstd2 = layernorm_fwd(x1, W.ln2[0], W.ln2[1], cdt)
     stats = torch.empty((N, W.w_1.shape[0] // 128, 2), device=x.device, dtype=torch.float32)   # slab partials
-    f1, u = linear_sm100(h2, W.w_1, mode=_lib.MT_EPI_GELU_STATS, bias=W.b_1, want_f32=True, want_bf16=True, stats=stats)
+    from . import config
+    fused_bwd = config.ffn_bwd_fused()
+    if fused_bwd:
+        # the backward runs inside fc2's dX GEMM (MT_EPI_GELU_LN_BWD): it wants gelu(h) and gelu'(h) in bf16 (the same
+        # bytes as the fp32 h, no erf / exp per element in the backward, and the forward writes 61 MB less)
+        f1 = torch.empty((N, W.w_1.shape[0]), device=x.device, dtype=cdt)          # gelu'(h)
+        u = torch.empty((N, W.w_1.shape[0]), device=x.device, dtype=cdt)
+        linear_sm100(h2, W.w_1, mode=_lib.MT_EPI_GELU_STATS, bias=W.b_1, want_f32=False, out_bf16=u, out_aux=f1, stats=stats)
+    else:
+        f1, u = linear_sm100(h2, W.w_1, mode=_lib.MT_EPI_GELU_STATS, bias=W.b_1, want_f32=True, want_bf16=True, stats=stats)
     del h2
     mean_f = torch.empty(N, device=x.device, dtype=torch.float32)
     rstd_f = torch.empty(N, device=x.device, dtype=torch.float32)
     y, _ = linear_sm100(u, W.w_2g, mode=_lib.MT_EPI_LN_RESIDUAL, residual=x1, stats=stats, col_c1=W.c1_2, col_c2=W.c2_2,
                         ln_cols=W.w_2g.shape[1], ln_mean_out=mean_f, ln_rstd_out=rstd_f)
-    del u
-    # f1 already contains fc1's bias here (the library path keeps it out and lets the GELU kernels add it)
-    saved = (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f)
+    # saved for the backward: f1 = fc1's fp32 output incl. bias (separate GELU'-LN' kernel) or gelu'(h) in bf16 with
+    # u = gelu(h) (fused epilogue); y rides along (it is the next layer's saved input anyway: no extra memory)
+    saved = (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f, y,
+             u if fused_bwd else None)
     return y, saved
 
 
 def _encoder_layer_backward_sm100(dy: torch.Tensor, saved, W: FrozenLayerWeights, geom: Geometry, impl):
-    (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f) = saved
+    (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f, y, u) = saved
     cdt = torch.bfloat16
     dy = dy.contiguous()
-    d_f2 = _as_compute(dy, cdt)
-    dg, _ = linear_sm100(d_f2, W.w_2_t)                                           # fp32 [N, 3072]
-    d_f1 = gelu_ln_bwd(dg, f1, W.ln_ffn[0], mean_f, rstd_f, cdt, hbias=None)
-    del dg
+    if u is not None:
+        # GELU' . LayerNorm' inside the epilogue of fc2's dX GEMM: the two row means of the LayerNorm backward are dot
+        # products of [N, 768] tensors (mt_ffn_bwd_prep), so the fp32 [N, 3072] gradient is never written or read
+        rowv, d_f2 = ffn_bwd_prep(dy, y, x1, W.c1_2, W.c2_2, mean_f, rstd_f, W.w_2g.shape[1])
+        _, d_f1 = linear_sm100(d_f2, W.w_2g_t, mode=_lib.MT_EPI_GELU_LN_BWD, in_u=u, in_g=f1, stats=rowv, want_f32=False,
+                               want_bf16=True)
+    else:
+        d_f2 = _as_compute(dy, cdt)
+        dg, _ = linear_sm100(d_f2, W.w_2_t)                                       # fp32 [N, 3072]
+        d_f1 = gelu_ln_bwd(dg, f1, W.ln_ffn[0], mean_f, rstd_f, cdt, hbias=None)
+        del dg
     dh2, _ = linear_sm100(d_f1, W.w_1_t)                                          # fp32 [N, 768]
     del d_f1
     dx1, _, _ = layernorm_bwd(dh2, x1, W.ln2[0], mean2, rstd2, torch.float32, residual=dy, bf16_twin=True)

@@ -231,18 +231,38 @@ def gated_residual_bwd(dy, a, b, g32, out=None, want_dysum=False):
     return (da, db, dgate, dysum) if want_dysum else (da, db, dgate)
 
 
+def _gelu_val_grad(h):
+    h = h.detach().float().requires_grad_(True)
+    with torch.enable_grad():
+        u = F.gelu(h)
+        (du,) = torch.autograd.grad(u, h, torch.ones_like(u))
+    return u.detach(), du
+
+
 def linear_sm100(a, w, mode=0, bias=None, residual=None, want_f32=True, want_bf16=False, stats=None, col_c1=None,
-                 col_c2=None, ln_cols=0, eps=1e-5, out_f32=None, out_bf16=None, ln_mean_out=None, ln_rstd_out=None, impl=0):
+                 col_c2=None, ln_cols=0, eps=1e-5, out_f32=None, out_bf16=None, ln_mean_out=None, ln_rstd_out=None, impl=0,
+                 out_aux=None, in_u=None, in_g=None):
     """mt_linear_sm100 (include/modaltune_b200.h): C = A W^T in fp32 math on the 16-bit operands + the epilogue."""
     acc = a.float() @ w.float().t()
     o32 = o16 = None
-    if mode == 3:       # MT_EPI_GELU_STATS
+    if mode == 5:       # MT_EPI_GELU_LN_BWD: h (residual) or gelu / gelu' in bf16; stats = [M, 4] (mean, rstd, m1, m2)
+        if in_u is not None:
+            u, du = in_u.float(), in_g.float()
+        else:
+            u, du = _gelu_val_grad(residual)
+        mean, rstd, m1, m2 = (stats[:, i:i + 1] for i in range(4))
+        uh = (u.detach() - mean) * rstd
+        acc = du * rstd * (acc - m1 - uh * m2)
+        o32, o16 = (acc if (want_f32 or out_f32 is not None) else None), acc.to(torch.bfloat16)
+    elif mode == 3:     # MT_EPI_GELU_STATS
         h = acc + bias
         u = F.gelu(h).to(torch.bfloat16)
+        if out_aux is not None:
+            out_aux.copy_(_gelu_val_grad(h)[1].to(torch.bfloat16))
         uf = u.float().reshape(u.shape[0], -1, 128)
         stats[:, :, 0] = uf.sum(2)
         stats[:, :, 1] = uf.square().sum(2)
-        o32, o16 = h, u
+        o32, o16 = (h if (want_f32 or out_f32 is not None) else None), u
     else:
         if mode == 4:   # MT_EPI_LN_RESIDUAL
             mean = stats[:, :, 0].sum(1, keepdim=True) / ln_cols
@@ -268,7 +288,15 @@ def linear_sm100(a, w, mode=0, bias=None, residual=None, want_f32=True, want_bf1
     return o32, o16
 
 
-_NAMES = ["linear_sm100", "layernorm_fwd", "layernorm_bwd", "add_layernorm_fwd", "gelu_ln_fwd", "gelu_ln_bwd", "dilated_attn_fwd",
+def ffn_bwd_prep(dy, y, x1, c1, c2, mean, rstd, ln_cols):
+    d16 = dy.to(torch.bfloat16)
+    d = d16.float()
+    m1 = (d * c1).sum(1) / ln_cols
+    m2 = (d * (y - x1 - c2)).sum(1) / ln_cols
+    return torch.stack([mean, rstd, m1, m2], 1).contiguous(), d16
+
+
+_NAMES = ["linear_sm100", "ffn_bwd_prep", "layernorm_fwd", "layernorm_bwd", "add_layernorm_fwd", "gelu_ln_fwd", "gelu_ln_bwd", "dilated_attn_fwd",
           "dilated_merge_ln_fwd", "dilated_merge_ln_bwd", "dilated_attn_bwd", "cross_attn_fwd", "cross_attn_bwd",
           "embed_assemble", "cast", "gated_residual_fwd", "gated_residual_bwd", "residual_bias_add"]
 

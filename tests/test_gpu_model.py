@@ -93,6 +93,31 @@ def test_encoder_layer_golden(model, fixture, mode, attn, t_out, t_grad):
     assert _cos(gx[0].cpu()[rows], gold["gx_rows"]) > (0.999999 if mode == "fp32" else 0.9995)
 
 
+def test_ffn_backward_fused_in_the_gemm_epilogue(model):
+    """GELU' . LayerNorm(3072)' inside the epilogue of fc2's dX GEMM (MT_EPI_GELU_LN_BWD + mt_ffn_bwd_prep, the default)
+    against the separate GELU'-LN' kernel between two plain dX GEMMs, and against the REFERENCE's gradient."""
+    gold = torch.load(os.path.join(helpers.GOLDEN, "encoder_layer_10k.pt"))
+    N = gold["N"]
+    g = torch.Generator().manual_seed(gold["seed"])
+    x = torch.randn(1, N, 768, generator=g, dtype=torch.float32).to(DEV).requires_grad_(True)
+    dy = torch.randn(1, N, 768, generator=g, dtype=torch.float32).to(DEV)
+    out = {}
+    for fused in (True, False):
+        old = config.ffn_bwd_fused()
+        config.set_ffn_bwd_fused(fused)
+        try:
+            with config.using(mode="bf16", attn_impl="auto"):
+                y, _ = model.encoder.layers[gold["layer"]](x, encoder_padding_mask=torch.zeros(1, N, dtype=torch.bool, device=DEV))
+                (gx,) = torch.autograd.grad(y, x, dy)
+        finally:
+            config.set_ffn_bwd_fused(old)
+        out[fused] = gx.detach()
+        assert _cos(gx[0].cpu()[gold["rows"]], gold["gx_rows"]) > 0.9995, fused
+        assert helpers.relerr(gx[0].cpu()[gold["rows"]], gold["gx_rows"]) < 5e-2, fused
+    assert _cos(out[True], out[False]) > 0.99995
+    assert helpers.relerr(out[True], out[False]) < 1e-2
+
+
 def test_encoder_layer_fused_gemm_path_agrees_with_library_path(model):
     """bf16 mode: the layer on the hand-written tcgen05 GEMMs with fused epilogues (default) against the same layer on
     cuBLAS GEMMs + separate element-wise kernels (round-1 path, config gemm='cublas'), and both against the reference."""
