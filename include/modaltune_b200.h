@@ -234,6 +234,9 @@ int mt_gated_residual_bwd(const float* dy, const float* a, const void* b, int b_
 int mt_residual_bias_add(const float* x, const void* a, int a_dtype, const float* bias, float* y, int64_t rows,
                          int64_t cols, const mt_dropout* drop, void* stream);
 int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* out[c] = sum_r x[r, c]: the bias gradient `dy.sum(0)` of the adapter's projections (autograd of nn.Linear in
+ * models/vitadapter/adapter_modules.py:210-234); x [rows, cols] f32 with row stride ld, cols % 4 == 0, <= 4096. */
+int mt_colsum(const float* x, int64_t ld, float* out, int64_t rows, int64_t cols, void* stream);
 /* backward of D: dst[i] = src[i] * keep_mask(i) / (1 - p) * path_scale, converted to dst_dtype (the gradient that
  * enters the dX GEMM of the branch).  drop must not be NULL. */
 int mt_dropout_bwd_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, const mt_dropout* drop,

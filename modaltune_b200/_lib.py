@@ -79,6 +79,7 @@ SIGNATURES = {
     "mt_residual_bias_add": (c_int, [_P, _P, c_int, _P, _P, _I64, _I64, _D, _P]),
     "mt_dropout_bwd_cast": (c_int, [_P, c_int, _P, c_int, _I64, _D, _P]),
     "mt_cast": (c_int, [_P, c_int, _P, c_int, _I64, _P]),
+    "mt_colsum": (c_int, [_P, _I64, _P, _I64, _I64, _P]),
 }
 
 _lib = None

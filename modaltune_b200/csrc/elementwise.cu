@@ -591,6 +591,31 @@ ffn_bwd_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y, c
   }
 }
 
+// out[c] = sum_r x[r, c] (bias gradients of the adapter's projections): float4 column quads, RL row lanes per block,
+// shared-memory combine, ONE 16-byte reduce-add per column quad and block into the zeroed output
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ x, int64_t ld, float* __restrict__ out,
+                                                      int64_t rows, int quads, int row_lanes) {
+  extern __shared__ float4 cs_red[];
+  const int qd = threadIdx.x % quads, rl = threadIdx.x / quads;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rl < row_lanes) {
+#pragma unroll 4
+    for (int64_t r = (int64_t)blockIdx.x * row_lanes + rl; r < rows; r += (int64_t)gridDim.x * row_lanes) {
+      const float4 v = *reinterpret_cast<const float4*>(x + r * ld + qd * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (rl > 0) cs_red[(rl - 1) * quads + qd] = acc;
+  }
+  __syncthreads();
+  if (rl == 0) {
+    for (int i = 0; i + 1 < row_lanes; ++i) {
+      const float4 v = cs_red[i * quads + qd];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    atomicAdd(reinterpret_cast<float4*>(out) + qd, acc);
+  }
+}
+
 static inline int grid_for(int64_t work_items, int per_block) {
   int64_t blocks = (work_items + per_block - 1) / per_block;
   int64_t cap = (int64_t)kNumSMs * 8;
@@ -860,6 +885,25 @@ extern "C" int mt_ffn_bwd_prep(const float* dy, const float* y, const float* x1,
   ffn_bwd_prep_kernel<<<grid, C::THREADS, 0, (cudaStream_t)stream>>>(dy, y, x1, c1, c2, mean, rstd, (float4*)rowv,
                                                                      (__nv_bfloat16*)dy_bf16, rows, 1.0f / (float)ln_cols);
   return check_launch("ffn_bwd_prep_kernel");
+}
+
+extern "C" int mt_colsum(const float* x, int64_t ld, float* out, int64_t rows, int64_t cols, void* stream) {
+  MT_REQUIRE(x != nullptr && out != nullptr && rows >= 0, "colsum: NULL argument");
+  MT_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 4096 && ld >= cols && ld % 4 == 0, "colsum: cols must be a multiple of 4, at most 4096");
+  MT_REQUIRE((((uintptr_t)x | (uintptr_t)out) & 15) == 0, "colsum: 16-byte alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  MT_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)cols, st));
+  if (rows == 0) return 0;
+  const int quads = (int)(cols / 4);
+  int row_lanes = 1024 / quads;
+  if (row_lanes > 8) row_lanes = 8;
+  if (row_lanes > rows) row_lanes = (int)rows;
+  int64_t grid = (rows + (int64_t)row_lanes * 4 - 1) / ((int64_t)row_lanes * 4);   // >= 4 rows per lane
+  if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
+  if (grid < 1) grid = 1;
+  const size_t smem = sizeof(float4) * (size_t)quads * (size_t)(row_lanes > 1 ? row_lanes - 1 : 1);
+  colsum_kernel<<<(unsigned)grid, quads * row_lanes, smem, st>>>(x, ld, out, rows, quads, row_lanes);
+  return check_launch("colsum_kernel");
 }
 
 extern "C" int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream) {

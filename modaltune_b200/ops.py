@@ -411,6 +411,18 @@ def embed_assemble(proj, bias, coords, table, cls, tile_size: float = 256.0):
     return x
 
 
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """x.sum(0) for an fp32 [rows, cols] CUDA tensor (row-strided views allowed): the adapter's bias gradients."""
+    rows, cols = x.shape
+    if not (x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1 and cols % 4 == 0 and cols <= 4096
+            and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0):
+        return x.sum(0)
+    out = torch.empty(cols, device=x.device, dtype=torch.float32)
+    rc = _lib.load().mt_colsum(ctypes.c_void_p(x.data_ptr()), x.stride(0), _p(out), rows, cols, _stream())
+    _check(rc, "mt_colsum")
+    return out
+
+
 def cast(src: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     dst = torch.empty(src.shape, device=src.device, dtype=dtype)
     rc = _lib.load().mt_cast(_p(src), _dt(src), _p(dst), _dt(dst), src.numel(), _stream())
@@ -551,7 +563,7 @@ class LinearTF32Fn(torch.autograd.Function):
         with _tf32():
             dx = dy @ w if ctx.needs_input_grad[0] else None
             dw = dy.t() @ x if ctx.needs_input_grad[1] else None
-        db = dy.sum(0) if ctx.has_b and ctx.needs_input_grad[2] else None
+        db = colsum(dy) if ctx.has_b and ctx.needs_input_grad[2] else None
         return dx, dw, db
 
 
@@ -662,7 +674,7 @@ class InjectorFn(torch.autograd.Function):
         del db
         dq, dk, dv = cross_attn_bwd(q, kv[:, :e], kv[:, e:], o, d_o, lse, ctx.heads, packed_kv=True)
         dkv = dk._base if dk._base is not None else torch.cat([dk, dv], 1)
-        dbq = dq.sum(0)
+        dbq = colsum(dq)
         dwq = _adapter_mm(dq.t(), t2)                      # [192, 768]
         dt2 = _adapter_mm(dq, wq)                          # [L, 768]
         # dx[row0:] = dy (1 + gate) (written above) + LN'(dt2): residual and output are the same buffer

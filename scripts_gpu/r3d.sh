@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -15 > gpurun_out/r3d_pytest.log
+timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | grep -v Warning | tail -60 > gpurun_out/r3d_pytest.log
 ( time timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras ) > gpurun_out/r3d_bench.log 2>&1
 tail -5 gpurun_out/r3d_pytest.log
 python - <<'PY'

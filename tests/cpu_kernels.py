@@ -296,7 +296,11 @@ def ffn_bwd_prep(dy, y, x1, c1, c2, mean, rstd, ln_cols):
     return torch.stack([mean, rstd, m1, m2], 1).contiguous(), d16
 
 
-_NAMES = ["linear_sm100", "ffn_bwd_prep", "layernorm_fwd", "layernorm_bwd", "add_layernorm_fwd", "gelu_ln_fwd", "gelu_ln_bwd", "dilated_attn_fwd",
+def colsum(x):
+    return x.sum(0)
+
+
+_NAMES = ["linear_sm100", "ffn_bwd_prep", "colsum", "layernorm_fwd", "layernorm_bwd", "add_layernorm_fwd", "gelu_ln_fwd", "gelu_ln_bwd", "dilated_attn_fwd",
           "dilated_merge_ln_fwd", "dilated_merge_ln_bwd", "dilated_attn_bwd", "cross_attn_fwd", "cross_attn_bwd",
           "embed_assemble", "cast", "gated_residual_fwd", "gated_residual_bwd", "residual_bias_add"]
 

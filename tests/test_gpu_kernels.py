@@ -189,6 +189,14 @@ def test_cross_attention_tensor_core(lq, lk, packed):
     assert rel(lse, lse0) < 1e-3 and rel(o, o0) < 3e-3
 
 
+@pytest.mark.parametrize("rows,cols", [(10000, 384), (10000, 192), (66, 768), (1, 4), (7, 3072), (40001, 768)])
+def test_colsum(rows, cols):
+    g = torch.Generator().manual_seed(rows + cols)
+    x = torch.randn(rows, cols + 8, generator=g)
+    got = ops.colsum(x.to(DEV)[:, :cols])            # a row-strided view, like the halves of a k | v gradient
+    assert rel(got, x[:, :cols].double().sum(0)) < 1e-5
+
+
 GEOMS = [  # (N, segment lengths) -- the reference's edge geometries: N around segment lengths,
     # N % r != 0, N < 16, tails that are almost all padding
     (7, [16, 24, 32, 64, 128]), (75, [16, 24, 32, 64, 128]), (97, [8, 32, 64, 96, 256]),

@@ -347,11 +347,19 @@ def test_graphed_step_drives_an_optimizer_across_replays():
         for (n, a), (_, b) in zip(m_g.named_parameters(), m_e.named_parameters()):
             if not a.requires_grad or (n.startswith("gene_encoder.") and n.endswith(dead)):
                 continue
-            moved = max(moved, float((a - ref[n]).abs().max()))
+            if n.endswith("in_proj_bias"):
+                # the key bias of an attention layer has a structurally zero gradient (a constant added to every key
+                # shifts all scores of a query alike): what arrives is reduce-order noise, which Adam turns into +-lr
+                e = a.shape[0] // 3
+                keep = torch.cat([torch.arange(0, e), torch.arange(2 * e, 3 * e)]).to(a.device)
+                a, b, r0 = a[keep], b[keep], ref[n][keep]
+            else:
+                r0 = ref[n]
+            moved = max(moved, float((a - r0).abs().max()))
             # Adam normalises the step: a gradient entry at the noise floor (split-K reduce-adds arrive in a different
             # order in every run) may move by up to 2 * lr either way in EACH of the two steps
             assert float((a - b).abs().max()) <= 4.5e-3, n
-            assert _cos(a - ref[n], b - ref[n]) > 0.98 or float((a - ref[n]).norm()) < 1e-6, n
+            assert _cos(a - r0, b - r0) > 0.98 or float((a - r0).norm()) < 1e-6, n
         assert moved > 5e-4                          # the optimizer really stepped on the graph's gradients
         # frozen weights replaced after capture: the next call must re-capture (new derived bf16 copies), not crash / go stale
         sd = {k: v.clone() for k, v in m_g.state_dict().items()}
