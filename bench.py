@@ -310,6 +310,46 @@ def extra_records(args, model, proj, flat, dev, world, rank, timed, barrier):
                            "packed_makespan_ms": est["makespan_ms"]},
             "note": "host slides pre-generated; each step copies its slide from pageable host memory (the reference's 331 + 4 copies)",
             "config": "BASELINE.json configs[4] (seeded log-uniform 2k-40k tiles, packed by estimated cost)"}
+        try:
+            # the same shard through train_step.GraphCache: one captured step per tile count in a shared memory pool.  Epoch 1
+            # captures every shape (all misses), epoch 2 revisits the same slides (what training does): all hits.
+            packed = [train_step.pack_host_slide(h) for h in hosts]
+            cache = train_step.GraphCache(model, proj, flat, packed[0][1], max_tiles=max(counts) + 1)
+            accum = torch.zeros(flat.numel, device=dev)
+
+            def epoch():
+                accum.zero_()
+                for pk in packed:
+                    cache(pk[0])
+                    accum.add_(cache.steps[int(pk[0]["x"].shape[-2])].grads)   # consumed before the next replay
+                if world > 1:
+                    dist.all_reduce(accum)
+
+            ep = []
+            for _ in range(2):
+                torch.cuda.synchronize()
+                e0.record()
+                epoch()
+                e1.record()
+                torch.cuda.synchronize()
+                own = torch.tensor([e0.elapsed_time(e1)], device=dev)
+                allr = [torch.zeros_like(own) for _ in range(world)]
+                if world > 1:
+                    dist.all_gather(allr, own)
+                else:
+                    allr = [own]
+                ep.append([float(t) for t in allr])
+            mean2 = sum(ep[1]) / world
+            out["c5_variable_tiles"]["graph_cache"] = {
+                "execution": "train_step.GraphCache: one captured step per tile count, shared memory pool and input buffers",
+                "epoch1_capture_ms": max(ep[0]), "epoch2_replay_per_rank_ms": ep[1], "epoch2_makespan_ms": max(ep[1]),
+                "epoch2_measured_imbalance": max(ep[1]) / mean2 - 1.0, "epoch2_slides_per_s": len(counts) / (max(ep[1]) / 1e3),
+                "hits": cache.hits, "misses": cache.misses, "distinct_shapes": len(cache.steps)}
+            del cache, packed, accum
+            flat.zero()
+            torch.cuda.empty_cache()
+        except Exception as e:
+            out["c5_variable_tiles"]["graph_cache"] = {"failed": f"{type(e).__name__}: {str(e)[:300]}"}
     except Exception as e:
         out["c5_variable_tiles"] = {"failed": f"{type(e).__name__}: {str(e)[:200]}"}
     # (3) train mode + optimizer

@@ -154,12 +154,21 @@ class GraphedStep:
     all-reduce of the flat gradient buffer runs after it.  Gradients live in ``flat.flat`` / ``p.grad`` views."""
 
     def __init__(self, model, projector, packed_example: Dict, sizes: Sequence[int], flat: FlatGradAllReduce,
-                 warmup: int = 3):
+                 warmup: int = 3, pool=None, static: Optional[Dict] = None):
+        """``pool``: a ``torch.cuda.graph_pool_handle()`` shared with other captured steps that are never replayed
+        concurrently (``GraphCache``); ``static``: pre-allocated device input buffers of the captured shapes (views of a
+        buffer shared by such steps) instead of private copies."""
         self.model, self.projector, self.flat, self.sizes = model, projector, flat, list(sizes)
         dev = next(model.parameters()).device
-        self.static = {k: v.to(dev).clone() for k, v in packed_example.items()}
+        if static is None:
+            self.static = {k: v.to(dev).clone() for k, v in packed_example.items()}
+        else:
+            self.static = static
+            for k, v in self.static.items():
+                assert v.shape == packed_example[k].shape and v.device == dev
+                v.copy_(packed_example[k], non_blocking=True)
         self._copy_stream, self._staging, self._staged_for = None, None, None
-        self._warmup = warmup
+        self._warmup, self._pool = warmup, pool
         self._capture()
 
     def _frozen_signature(self):
@@ -180,7 +189,7 @@ class GraphedStep:
         torch.cuda.synchronize()
         flat.zero()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, pool=self._pool):
             self.loss, self.logits = forward_backward(model, projector, slide)
             self.grads = flat.gather()
         # views of the captured flat buffer, handed back to ``p.grad`` after every replay
@@ -234,3 +243,60 @@ class GraphedStep:
         for p, g in zip(self.flat.params, self._grad_views):
             p.grad = g
         return self.loss, self.logits
+
+
+class GraphCache:
+    """Captured steps for VARIABLE-length slides (pan-cancer training, BASELINE config 5: 2k-40k tiles per slide).
+
+    A CUDA graph is shape-specific and the eager step is host-bound (~3 000 launches from Python: twice the graph's
+    time at 10k tiles, worse below), but training visits the same slides every epoch: the cache keeps one captured step
+    per token count.  All steps share ONE memory pool and ONE set of static input buffers sized for ``max_tiles`` --
+    they are replayed one at a time and their outputs (loss, logits, flat gradients) are consumed before the next
+    replay -- so a cached shape costs only its graph object, not its 13-50 GB of activations.  The first visit of a shape
+    captures (about the cost of an eager step); every later visit is one graph launch.  ``hits`` / ``misses`` count."""
+
+    def __init__(self, model, projector, flat: FlatGradAllReduce, sizes: Sequence[int], in_chans: int = 1536,
+                 max_tiles: int = 40960, max_entries: int = 4096):
+        from collections import OrderedDict
+        self.model, self.projector, self.flat, self.sizes = model, projector, flat, list(sizes)
+        dev = next(model.parameters()).device
+        self.pool = torch.cuda.graph_pool_handle()
+        self.max_tiles, self.max_entries = max_tiles, max_entries
+        self._x = torch.empty((max_tiles, in_chans), device=dev, dtype=torch.float32)
+        self._coords = torch.empty((max_tiles, 2), device=dev, dtype=torch.float32)
+        self._small: Dict[str, torch.Tensor] = {}
+        self.steps: "OrderedDict[int, GraphedStep]" = OrderedDict()
+        self.hits = self.misses = 0
+
+    def _static_for(self, packed: Dict) -> Dict:
+        L = packed["x"].shape[-2]
+        assert L <= self.max_tiles, f"slide of {L} tiles exceeds max_tiles={self.max_tiles}"
+        out = {}
+        for k, v in packed.items():
+            if k == "x":
+                out[k] = self._x[:L].view(v.shape)
+            elif k == "coords":
+                out[k] = self._coords[:L].view(v.shape)
+            else:
+                if k not in self._small:
+                    self._small[k] = torch.empty(v.shape, device=self._x.device, dtype=v.dtype)
+                out[k] = self._small[k]
+        return out
+
+    def __call__(self, packed: Dict):
+        """One slide step (packed host or device tensors, ``pack_host_slide``): (loss, logits); the gradients of THIS
+        slide are in ``p.grad`` (views of the captured step's flat buffer, valid until the next call)."""
+        L = int(packed["x"].shape[-2])
+        step = self.steps.get(L)
+        if step is None:
+            self.misses += 1
+            if len(self.steps) >= self.max_entries:
+                self.steps.popitem(last=False)
+            self.flat.zero()
+            step = GraphedStep(self.model, self.projector, packed, self.sizes, self.flat,
+                               warmup=1 if not self.steps else 0, pool=self.pool, static=self._static_for(packed))
+            self.steps[L] = step
+            return step()
+        self.hits += 1
+        self.steps.move_to_end(L)
+        return step(packed)

@@ -315,6 +315,38 @@ def test_graphed_step_equals_eager_step(model):
     assert helpers.relerr(g_graph, g_eager) < 1e-3
 
 
+def test_graph_cache_serves_variable_length_slides(model):
+    """``train_step.GraphCache`` (pan-cancer slides of different tile counts, BASELINE config 5): one captured step per
+    token count in ONE shared memory pool and ONE set of input buffers; shapes revisited in any order replay their graph
+    and reproduce the eager step of the same slide."""
+    proj = helpers.build_projector(0, DEV)
+    flat = train_step.FlatGradAllReduce([p for p in model.parameters() if p.requires_grad])
+    tiles = (700, 333, 1201)
+    first = [train_step.pack_host_slide(synthetic.synthetic_slide(n, seed=60 + n, group_sizes=helpers.SMALL_GROUPS)) for n in tiles]
+    again = [train_step.pack_host_slide(synthetic.synthetic_slide(n, seed=90 + n, group_sizes=helpers.SMALL_GROUPS)) for n in tiles]
+    sizes = first[0][1]
+    with config.using(mode="bf16"):
+        cache = train_step.GraphCache(model, proj, flat, sizes, max_tiles=2048)
+        for p in first:                                   # epoch 1: every shape is new -> capture
+            cache(p[0])
+        assert (cache.hits, cache.misses) == (0, 3)
+        for k in (2, 0, 1, 0):                            # later visits in another order, NEW slides of the known shapes
+            loss_g, logits_g = cache(again[k][0])
+            torch.cuda.synchronize()
+            g_graph = torch.cat([p.grad.reshape(-1) for p in flat.params]).clone()
+            loss_g, logits_g = float(loss_g), logits_g.clone()
+            flat.zero()
+            dev_slide = train_step.unpack_slide({n: v.to(DEV) for n, v in again[k][0].items()}, sizes)
+            loss_e, logits_e = train_step.forward_backward(model, proj, dev_slide)
+            g_eager = flat.gather().clone()
+            flat.zero()
+            assert abs(loss_g - float(loss_e)) < 1e-5 * abs(float(loss_e)) + 1e-7, k
+            assert helpers.relerr(logits_g, logits_e) < 1e-5, k
+            assert _cos(g_graph, g_eager) > 0.999999, k
+        assert (cache.hits, cache.misses) == (4, 3)
+        assert len(cache.steps) == 3
+
+
 def test_graphed_step_drives_an_optimizer_across_replays():
     """``optimizer.zero_grad()`` (set_to_none, the reference's loop: train_modaltune.py:236-238) between replays must not
     detach the parameters from the captured flat gradient buffer: two graph steps + AdamW equal two eager steps + AdamW,
