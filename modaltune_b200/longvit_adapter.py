@@ -142,20 +142,35 @@ class LongNetGeneAdapter(LongNetViT):
         """The task-independent part of a forward: embedded slide tokens [1, N, 768] and the gene-encoder tokens."""
         return self.embed(x, coords), self.gene_encoder(genes)
 
-    def forward_tasks(self, x, coords, genes, clinical=None, task_tokens=()):
+    def forward_tasks(self, x, coords, genes, clinical=None, task_tokens=(), split_grads: bool = False):
         """Several task-conditioned passes over ONE slide (what ``multitask_forward`` does with one ``forward`` per task,
         train_modaltune.py:156-179).  The token embedding (frozen, deterministic: its dropout sits after it, in
         ``prepare_forward``) is computed once; the gene-encoder output is shared in eval mode and recomputed per pass in
-        train mode, where the reference draws fresh dropout masks in every ``model(...)`` call."""
+        train mode, where the reference draws fresh dropout masks in every ``model(...)`` call.
+
+        ``split_grads``: every pass reads the trainable parameters through its OWN leaf aliases (same storage, listed in
+        ``self._pass_aliases`` for the caller, ``train_step.forward_backward``).  The autograd engine then delivers one
+        gradient per (parameter, pass) instead of summing the passes' contributions with two tiny add kernels per
+        parameter (~700 launches per step); the caller sums them with two multi-tensor adds."""
         emb = self.embed(x, coords)
         gene = None if self.training else self.gene_encoder(genes)
+        self._pass_aliases = None
+        if split_grads and torch.is_grad_enabled() and len(task_tokens) > 1:
+            named = [(n, p) for n, p in self.named_parameters()
+                     if p.requires_grad and (gene is None or not n.startswith("gene_encoder."))]
+            self._pass_aliases = [{n: p.detach().requires_grad_(True) for n, p in named} for _ in task_tokens]
 
-        def one_pass(t):
+        def one_pass(t, k=0):
+            if self._pass_aliases is not None:
+                from torch.nn.utils.stateless import _reparametrize_module
+                with _reparametrize_module(self, self._pass_aliases[k]):
+                    shared = (emb, gene if gene is not None else self.gene_encoder(genes))
+                    return self._adapter_forward(None, None, None, clinical, t, None, None, None, shared=shared)
             shared = (emb, gene if gene is not None else self.gene_encoder(genes))
             return self._adapter_forward(None, None, None, clinical, t, None, None, None, shared=shared)
 
         if not (config.pass_streams() and emb.is_cuda and len(task_tokens) > 1):
-            return torch.cat([one_pass(t) for t in task_tokens], 0)
+            return torch.cat([one_pass(t, k) for k, t in enumerate(task_tokens)], 0)
         # The task passes are independent until the loss: each one runs on its own CUDA stream (autograd replays the
         # backward of every node on the stream of its forward), so kernels of different passes overlap -- the tails of
         # the attention launches and the hundreds of tiny modal-token kernels fill each other's gaps.  Under CUDA-graph
@@ -177,8 +192,8 @@ class LongNetGeneAdapter(LongNetViT):
                 if torch.is_tensor(tns) and tns.is_cuda:
                     tns.record_stream(st)
             with torch.cuda.stream(st):
-                outs[k] = one_pass(t)
-        outs[0] = one_pass(task_tokens[0])
+                outs[k] = one_pass(t, k)
+        outs[0] = one_pass(task_tokens[0], 0)
         for k in range(1, len(task_tokens)):
             cur.wait_stream(streams[k - 1])
             outs[k].record_stream(cur)   # allocated on the side stream, read by the cat below on the calling stream

@@ -36,12 +36,14 @@ def text_targets(projector: nn.Module, text: torch.Tensor) -> torch.Tensor:
     return t / t.norm(dim=-1, keepdim=True)
 
 
-def multitask_forward(model, slide: Dict, task_ids: Sequence[int] = (0, 1, 2)) -> torch.Tensor:
-    """[len(task_ids), 256] task-conditioned embeddings (train_modaltune.py:156-179)."""
+def multitask_forward(model, slide: Dict, task_ids: Sequence[int] = (0, 1, 2), split_grads: bool = False) -> torch.Tensor:
+    """[len(task_ids), 256] task-conditioned embeddings (train_modaltune.py:156-179).  ``split_grads``: see
+    ``LongNetGeneAdapter.forward_tasks`` (only for callers that collect the per-pass gradients, ``forward_backward``)."""
     eye = torch.eye(NUM_TASKS, device=slide["x"].device)
     clinical = slide.get("clinical") if getattr(model, "_HAS_CLINICAL", False) else None
     if hasattr(model, "forward_tasks"):
-        return model.forward_tasks(slide["x"], slide["coords"], slide["genes"], clinical, [eye[t] for t in task_ids])
+        return model.forward_tasks(slide["x"], slide["coords"], slide["genes"], clinical, [eye[t] for t in task_ids],
+                                   split_grads=split_grads)
     outs = []
     for t in task_ids:
         kw = {"clinical": clinical} if clinical is not None else {}
@@ -63,12 +65,38 @@ def forward_backward(model, projector, slide: Dict):
     The gradients are taken with ``torch.autograd.grad`` and assigned, not accumulated by ``loss.backward()``: an
     AccumulateGrad node remembers the CUDA stream of the step that created it, and a node kept alive from an earlier
     (eager, default-stream) step silently breaks a later multi-stream CUDA-graph capture of the same model."""
-    logits = multitask_forward(model, slide)
+    logits = multitask_forward(model, slide, split_grads=True)
     loss = distill_loss(logits, text_targets(projector, slide["text"]))
-    params = [p for p in model.parameters() if p.requires_grad]
-    grads = torch.autograd.grad(loss, params, allow_unused=True)
-    if hasattr(model, "join_pass_streams"):
-        model.join_pass_streams()     # the backward of a task pass runs on the stream of its forward
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    params = [p for _, p in named]
+    aliases = getattr(model, "_pass_aliases", None)
+    if aliases:
+        # one gradient per (parameter, task pass): the passes read the parameters through their own leaf aliases, so the
+        # engine does not sum their contributions one tiny kernel at a time; two multi-tensor adds do it here
+        targets, owner = [], []
+        for i, (n, p) in enumerate(named):
+            for t in ([a[n] for a in aliases] if n in aliases[0] else [p]):
+                targets.append(t)
+                owner.append(i)
+        model._pass_aliases = None
+        raw = torch.autograd.grad(loss, targets, allow_unused=True)
+        if hasattr(model, "join_pass_streams"):
+            model.join_pass_streams()
+        per = [[] for _ in params]
+        for i, g in zip(owner, raw):
+            if g is not None:
+                per[i].append(g)
+        grads = [gs[0] if gs else None for gs in per]
+        depth = max((len(gs) for gs in per), default=0)
+        for d in range(1, depth):      # out of place: a gradient the engine returns may alias another one
+            idx = [i for i, gs in enumerate(per) if len(gs) > d]
+            if idx:
+                for i, g in zip(idx, torch._foreach_add([grads[i] for i in idx], [per[i][d] for i in idx])):
+                    grads[i] = g
+    else:
+        grads = torch.autograd.grad(loss, params, allow_unused=True)
+        if hasattr(model, "join_pass_streams"):
+            model.join_pass_streams()     # the backward of a task pass runs on the stream of its forward
     for p, g in zip(params, grads):
         if g is not None:
             p.grad = g if p.grad is None else p.grad + g
