@@ -153,8 +153,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx_dtype, residual=None, want_wgrad:
     twin = torch.empty((rows, cols), device=x.device, dtype=torch.bfloat16) if bf16_twin else None
     dgamma = dbeta = None
     if want_wgrad:
-        dgamma = torch.zeros(cols, device=x.device, dtype=torch.float32)
-        dbeta = torch.zeros(cols, device=x.device, dtype=torch.float32)
+        dgb = torch.zeros((2, cols), device=x.device, dtype=torch.float32)   # one fill for both accumulators
+        dgamma, dbeta = dgb[0], dgb[1]
     rc = _lib.load().mt_layernorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(mean), _p(rstd), _p(residual),
                                       _dt(residual) if residual is not None else 0, _p(dx), _dt(dx), _p(twin),
                                       _p(dgamma), _p(dbeta), rows, cols, _stream())
@@ -415,8 +415,8 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
     """x.sum(0) for an fp32 [rows, cols] CUDA tensor (row-strided views allowed): the adapter's bias gradients."""
     rows, cols = x.shape
     if not (x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1 and cols % 4 == 0 and cols <= 4096
-            and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0):
-        return x.sum(0)
+            and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and rows >= 1024):
+        return x.sum(0)            # short inputs (the 66 modal tokens): one library launch instead of memset + kernel
     out = torch.empty(cols, device=x.device, dtype=torch.float32)
     rc = _lib.load().mt_colsum(ctypes.c_void_p(x.data_ptr()), x.stride(0), _p(out), rows, cols, _stream())
     _check(rc, "mt_colsum")

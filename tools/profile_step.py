@@ -26,7 +26,7 @@ ev = prof.key_averages()
 rows = sorted(((e.device_time_total, e.count, e.key) for e in ev if e.device_time_total > 0 and e.device_type.name == "CUDA"), reverse=True)
 tot = sum(r[0] for r in rows)
 print(f"GPU kernel time total {tot/1e3:.2f} ms over {sum(r[1] for r in rows)} kernels")
-for t, c, k in rows[:45]:
+for t, c, k in rows[:70]:
     print(f"{t/1e3:9.3f} ms {c:6d}x {100*t/tot:5.1f}%  {k[:110]}")
 if "--ops" in sys.argv:   # ATen operators by device time, grouped by input shape: where the autograd glue comes from
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof2:
