@@ -11,13 +11,16 @@ rank processes its own slides (weak scaling, no data-path collective).  Prints O
 * ``value``: device-resident slides/s (inputs already in HBM), CUDA events, max over ranks.
 * ``e2e``: the same step driven from pinned HOST buffers through the module API, H2D copy of the slide and D2H read of
   loss / logits inside the timed region (every step copies its slide; the copy of slide i + 1 is issued on a copy stream
-  while step i runs, ``GraphedStep.prefetch``).
+  while step i runs, ``GraphedStep.prefetch``; the loss / logits of step i are copied to pinned memory behind the step
+  and read by the host after step i + 1 has been launched, ``GraphedStep.read_back_async``: every step's result is
+  read, none of them stalls the GPU).
 * ``roofline``: the dilated-attention backward kernel (the dominant kernel), timed live with CUDA events on its stream
   inside the timed region; algorithmic FLOPs = 2.5 * 4*d*sum c^2 per launch against the measured bf16
   tensor peak of MEASURED_PEAKS.json.
 * ``cpu_baseline`` / ``--impl reference``: the oracle port of the reference's CPU arithmetic (the reference is pure
-  Python and does not travel to the GPU box) on the host cores, on a bounded sample: ONE encoder-layer forward+backward
-  at the same token count, scaled by the 36 layer passes of a slide step.
+  Python and has no CPU attention of its own) on the host cores: ``cpu_baseline`` = SURVEY.md 8(d)'s C1 protocol (COMPLETE
+  oracle training steps at 1 024 tiles, 1 warm-up + 3 timed, median); ``--impl reference`` = complete oracle training
+  steps at the bench tile count, as many as fit the CPU budget, reporting the true ``steps`` it ran (never a scaled figure).
 """
 import argparse
 import json
@@ -470,16 +473,29 @@ def main():
     # ---- end to end: pinned host -> device, step, loss/logits back to the host ---------------------------------------
     out = {}
 
-    def e2e_step(i):
+    pending = []
+
+    def read(ev, lh, gh):
+        ev.synchronize()
+        out["loss"], out["logits"] = float(lh), gh.clone()
+
+    def e2e_step(i, last=None):
         h = hosts[i % n_slides][0]
         if graphed is None:
             loss, logits = eager_step({k: v.to(dev, non_blocking=True) for k, v in h.items()})
-        else:
-            loss, logits = graphed(h)
-            graphed.prefetch(hosts[(i + 1) % n_slides][0])   # the next slide's H2D copy overlaps this step
-        out["loss"], out["logits"] = float(loss), logits.float().cpu()   # D2H reads (synchronising, like loss.item())
+            out["loss"], out["logits"] = float(loss), logits.float().cpu()   # D2H reads (synchronising, like loss.item())
+            return
+        graphed(h)
+        graphed.prefetch(hosts[(i + 1) % n_slides][0])   # the next slide's H2D copy overlaps this step
+        # D2H read of EVERY step's loss / logits, one step late: the copy into pinned memory is queued behind the step,
+        # the host waits for it only after the next step has been launched (no GPU idle time around a loss.item())
+        pending.append(graphed.read_back_async())
+        if len(pending) > 1:
+            read(*pending.pop(0))
+        if i == (args.steps - 1 if last is None else last):
+            read(*pending.pop(0))                        # the last step of the timed region is read inside it
 
-    e2e_step(0)
+    e2e_step(0, last=0)
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = world * args.steps / (ms_e2e / 1e3)
 

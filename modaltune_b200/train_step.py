@@ -254,7 +254,25 @@ class GraphedStep:
             self._staged_evt.record()
         self._staged_for = packed
 
-    def __call__(self, packed: Optional[Dict] = None):
+    def read_back_async(self):
+        """Queue the device-to-host copy of this step's (loss, logits) into pinned buffers (a ring of two, so the caller
+        may launch the NEXT step before it waits) and return (event, loss_host [1], logits_host): the training loop's
+        ``loss.item()`` without stalling the GPU between steps -- the host reads step i while step i + 1 runs."""
+        if not hasattr(self, "_rb"):
+            mk = lambda t: torch.empty(t.shape, dtype=torch.float32).pin_memory()
+            self._rb = [(mk(self.loss.reshape(1)), mk(self.logits), torch.cuda.Event()) for _ in range(2)]
+            self._rb_i = 0
+        lh, gh, ev = self._rb[self._rb_i]
+        self._rb_i ^= 1
+        lh.copy_(self.loss.reshape(1), non_blocking=True)
+        gh.copy_(self.logits.float(), non_blocking=True)
+        ev.record()
+        return ev, lh, gh
+
+    def __call__(self, packed: Optional[Dict] = None, reduce: bool = True):
+        """``reduce``: all-reduce the flat gradients over the data-parallel ranks after the replay (one slide per rank and
+        step).  ``GraphCache`` passes False: ranks step through different numbers of slides and exchange the accumulated
+        gradients once."""
         if self._frozen_signature() != self._signature:
             # the graph holds pointers to bf16 copies derived from the old frozen weights: capture again
             self._capture()
@@ -263,7 +281,7 @@ class GraphedStep:
         self.graph.replay()
         import torch.distributed as dist
 
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
             self.grads.div_(dist.get_world_size())
         # ``optimizer.zero_grad()`` (set_to_none, the reference's loop) or ``flat.zero()`` drop ``p.grad``; the replay
@@ -313,7 +331,8 @@ class GraphCache:
 
     def __call__(self, packed: Dict):
         """One slide step (packed host or device tensors, ``pack_host_slide``): (loss, logits); the gradients of THIS
-        slide are in ``p.grad`` (views of the captured step's flat buffer, valid until the next call)."""
+        slide are in ``p.grad`` (views of the captured step's flat buffer, valid until the next call).  No collective
+        runs here: a rank's slides of a global step differ in number, the caller accumulates and all-reduces once."""
         L = int(packed["x"].shape[-2])
         step = self.steps.get(L)
         if step is None:
@@ -324,7 +343,7 @@ class GraphCache:
             step = GraphedStep(self.model, self.projector, packed, self.sizes, self.flat,
                                warmup=1 if not self.steps else 0, pool=self.pool, static=self._static_for(packed))
             self.steps[L] = step
-            return step()
+            return step(reduce=False)
         self.hits += 1
         self.steps.move_to_end(L)
-        return step(packed)
+        return step(packed, reduce=False)
