@@ -325,15 +325,15 @@ def extra_records(args, model, proj, flat, dev, world, rank, timed, barrier):
                 for pk in packed:
                     cache(pk[0])
                     accum.add_(cache.steps[int(pk[0]["x"].shape[-2])].grads)   # consumed before the next replay
-                if world > 1:
-                    dist.all_reduce(accum)
 
             ep = []
             for _ in range(2):
                 torch.cuda.synchronize()
                 e0.record()
                 epoch()
-                e1.record()
+                e1.record()                  # this rank's own work: the exchange below would hide the imbalance
+                if world > 1:
+                    dist.all_reduce(accum)
                 torch.cuda.synchronize()
                 own = torch.tensor([e0.elapsed_time(e1)], device=dev)
                 allr = [torch.zeros_like(own) for _ in range(world)]
