@@ -87,6 +87,15 @@ int mt_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, c
                      const float* rstd, const void* residual, int res_dtype, void* dx, int dx_dtype, void* dx_bf16,
                      float* dgamma, float* dbeta, int64_t rows, int64_t cols, void* stream);
 
+/* mt_layernorm_bwd (f32 tensors, cols = 768, residual and bf16 twin required) of the pre-attention LayerNorm of layer
+ * l + 1 that ALSO does mt_ffn_bwd_prep for layer l: its dx IS layer l's dy and its x IS layer l's output y, so the row means
+ * m1, m2 of layer l's ffn_layernorm backward cost one more read (x1_below = the FFN residual input of layer l) instead of a
+ * pass of their own.  rowv [rows, 4] = (mean_f, rstd_f, m1, m2) for MT_EPI_GELU_LN_BWD, dx_bf16 = that GEMM's A operand. */
+int mt_layernorm_bwd_ffn_prep(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                              const float* residual, float* dx, void* dx_bf16, const float* x1_below, const float* c1,
+                              const float* c2, const float* mean_f, const float* rstd_f, float* rowv, int64_t rows,
+                              int64_t cols, int64_t ln_cols, void* stream);
+
 /* residual add fused with the next pre-LN (torchscale/architecture/encoder.py:152-166):
  * x_out = x + D(a [+ abias]) (f32 residual stream, a in a_dtype, abias [cols] f32 or NULL = bias of the GEMM that
  * produced a; D = train-mode dropout + DropPath of the branch, identity when drop is NULL), y = LN(x_out).  cols = 768. */

@@ -616,6 +616,68 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
   }
 }
 
+// LayerNorm(768) backward of the pre-attention LN (+ residual gradient, + bf16 twin) that ALSO prepares the FFN backward of
+// the layer BELOW: its output dx is that layer's dy, and this kernel already holds dx and the layer's input x (= the
+// output y of the layer below) in registers, so the two row means of mt_ffn_bwd_prep cost one more read (x1 of the layer
+// below) instead of a separate pass over three [rows, 768] tensors:  rowv = (mean_f, rstd_f, dx16 . c1 / C,
+// dx16 . (x - x1b - c2) / C) with dx16 = dx rounded to bf16 (the twin written here).
+__global__ void __launch_bounds__(RowCfg<768>::THREADS, RowCfg<768>::MINB)
+ln_bwd_prep_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ residual,
+                   float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_lp, const float* __restrict__ x1b,
+                   const float* __restrict__ c1, const float* __restrict__ c2, const float* __restrict__ mean_f,
+                   const float* __restrict__ rstd_f, float4* __restrict__ rowv, int64_t rows, float inv_ln_cols) {
+  using C = RowCfg<768>;
+  __shared__ float red[C::RPB * (C::TPR / 32) + 1];
+  const int t = threadIdx.x % C::TPR, rib = threadIdx.x / C::TPR;
+  float gam[8], a1[8], a2[8];
+  load8(gamma + t * 8, gam);
+  load8(c1 + t * 8, a1);
+  load8(c2 + t * 8, a2);
+  for (int64_t row0 = (int64_t)blockIdx.x * C::RPB; row0 < rows; row0 += (int64_t)gridDim.x * C::RPB) {
+    const int64_t row = row0 + rib;
+    const bool live = row < rows;
+    float xv[8], xh[8], g[8], xb[8];
+    const float mu = live ? mean[row] : 0.f, rs = live ? rstd[row] : 0.f;
+    float s1 = 0.f, s2 = 0.f;
+    if (live) {
+      float d[8];
+      load8(x + row * 768 + t * 8, xv);
+      load8(dy + row * 768 + t * 8, d);
+      load8(x1b + row * 768 + t * 8, xb);     // requested early: consumed after the two reductions below
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xh[j] = (xv[j] - mu) * rs;
+        g[j] = d[j] * gam[j];
+        s1 += g[j];
+        s2 = fmaf(g[j], xh[j], s2);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xv[j] = xh[j] = g[j] = xb[j] = 0.f;
+    }
+    const float m1 = row_sum<C::TPR>(s1, red, rib, t) * (1.f / 768.f);
+    const float m2 = row_sum<C::TPR>(s2, red, rib, t) * (1.f / 768.f);
+    float p1 = 0.f, p2 = 0.f;
+    if (live) {
+      float o[8], r[8];
+      load8(residual + row * 768 + t * 8, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = rs * (g[j] - m1 - xh[j] * m2) + r[j];
+        const float o16 = __bfloat162float(__float2bfloat16_rn(o[j]));
+        p1 = fmaf(o16, a1[j], p1);
+        p2 = fmaf(o16, (xv[j] - xb[j]) - a2[j], p2);
+      }
+      store8(dx + row * 768 + t * 8, o);
+      store8(dx_lp + row * 768 + t * 8, o);
+    }
+    const float q1 = row_sum<C::TPR>(p1, red, rib, t) * inv_ln_cols;
+    const float q2 = row_sum<C::TPR>(p2, red, rib, t) * inv_ln_cols;
+    if (live && t == 0) rowv[row] = make_float4(mean_f[row], rstd_f[row], q1, q2);
+  }
+}
+
 static inline int grid_for(int64_t work_items, int per_block) {
   int64_t blocks = (work_items + per_block - 1) / per_block;
   int64_t cap = (int64_t)kNumSMs * 8;
@@ -904,6 +966,24 @@ extern "C" int mt_colsum(const float* x, int64_t ld, float* out, int64_t rows, i
   const size_t smem = sizeof(float4) * (size_t)quads * (size_t)(row_lanes > 1 ? row_lanes - 1 : 1);
   colsum_kernel<<<(unsigned)grid, quads * row_lanes, smem, st>>>(x, ld, out, rows, quads, row_lanes);
   return check_launch("colsum_kernel");
+}
+
+extern "C" int mt_layernorm_bwd_ffn_prep(const float* dy, const float* x, const float* gamma, const float* mean,
+                                         const float* rstd, const float* residual, float* dx, void* dx_bf16,
+                                         const float* x1_below, const float* c1, const float* c2, const float* mean_f,
+                                         const float* rstd_f, float* rowv, int64_t rows, int64_t cols, int64_t ln_cols,
+                                         void* stream) {
+  MT_REQUIRE(cols == 768 && ln_cols > 0, "layernorm_bwd_ffn_prep: cols must be 768 (got %lld)", (long long)cols);
+  MT_REQUIRE(dy && x && gamma && mean && rstd && residual && dx && dx_bf16 && x1_below && c1 && c2 && mean_f && rstd_f && rowv,
+             "layernorm_bwd_ffn_prep: NULL argument");
+  MT_REQUIRE(((uintptr_t)rowv & 15) == 0, "layernorm_bwd_ffn_prep: rowv must be 16-byte aligned");
+  if (rows == 0) return 0;
+  using C = RowCfg<768>;
+  const int grid = grid_for(rows, C::RPB);
+  ln_bwd_prep_kernel<<<grid, C::THREADS, 0, (cudaStream_t)stream>>>(dy, x, gamma, mean, rstd, residual, dx,
+                                                                    (__nv_bfloat16*)dx_bf16, x1_below, c1, c2, mean_f, rstd_f,
+                                                                    (float4*)rowv, rows, 1.0f / (float)ln_cols);
+  return check_launch("ln_bwd_prep_kernel");
 }
 
 extern "C" int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream) {

@@ -401,6 +401,22 @@ def ffn_bwd_prep(dy, y, x1, c1, c2, mean, rstd, ln_cols: int):
     return rowv, dy16
 
 
+def layernorm_bwd_ffn_prep(dy, x, gamma, mean, rstd, residual, below):
+    """``layernorm_bwd`` (fp32, 768 columns, residual, bf16 twin) that also forms the FFN-backward row vector of the layer
+    BELOW (``mt_layernorm_bwd_ffn_prep``): ``below`` = (x1, c1, c2, mean_f, rstd_f, ln_cols) of that layer.
+    -> (dx fp32, dx bf16, rowv [rows, 4])."""
+    rows, cols = x.shape
+    x1b, c1, c2, mean_f, rstd_f, ln_cols = below
+    dx = torch.empty((rows, cols), device=x.device, dtype=torch.float32)
+    twin = torch.empty((rows, cols), device=x.device, dtype=torch.bfloat16)
+    rowv = torch.empty((rows, 4), device=x.device, dtype=torch.float32)
+    rc = _lib.load().mt_layernorm_bwd_ffn_prep(_p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(residual), _p(dx), _p(twin),
+                                               _p(x1b), _p(c1), _p(c2), _p(mean_f), _p(rstd_f), _p(rowv), rows, cols,
+                                               int(ln_cols), _stream())
+    _check(rc, "mt_layernorm_bwd_ffn_prep")
+    return dx, twin, rowv
+
+
 def embed_assemble(proj, bias, coords, table, cls, tile_size: float = 256.0):
     """proj [L, E] (GEMM output), coords [L, 2] -> x [L+1, E] fp32 with the sincos positions and the cls row."""
     L, E = proj.shape
@@ -776,6 +792,17 @@ def _use_sm100_gemm(cdt: torch.dtype, rng) -> bool:
     return cdt == torch.bfloat16 and not rng and config.gemm_impl() == "sm100"
 
 
+# hand-over between consecutive frozen layers of one task pass (one slot per CUDA stream: the passes run on their own
+# streams and their autograd nodes interleave).  A slot is consumed by the NEXT layer call on that stream whether it
+# matches or not, so a stale entry can never meet an unrelated tensor that happens to reuse the address later.
+_ffn_fwd_link: Dict[int, tuple] = {}
+_ffn_bwd_link: Dict[int, tuple] = {}
+
+
+def _link_key(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream().cuda_stream if t.is_cuda else 0
+
+
 def _encoder_layer_forward_sm100(x: torch.Tensor, W: FrozenLayerWeights, geom: Geometry, impl):
     """EncoderLayer.forward with every frozen projection on ``mt_linear_sm100`` and its epilogues: bias + bf16 q/k/v into
     the TMA-ready buffer; out_proj + bias + residual -> x1; fc1 + bias + GELU + LayerNorm(3072) statistics; fc2 with the
@@ -783,6 +810,11 @@ def _encoder_layer_forward_sm100(x: torch.Tensor, W: FrozenLayerWeights, geom: G
     and the GELU+LN and residual kernels of the library path do not exist here."""
     N = geom.n_tokens
     cdt = torch.bfloat16
+    # is x the output of the encoder layer that ran right before on this stream?  Then this layer's backward can prepare
+    # that layer's FFN backward in its last kernel (see _encoder_layer_backward_sm100)
+    key = _link_key(x)
+    link = _ffn_fwd_link.pop(key, None)
+    below = link[2] if (link is not None and link[0] == x.data_ptr() and link[1] == tuple(x.shape)) else None
     h1, mean1, rstd1 = layernorm_fwd(x, W.ln1[0], W.ln1[1], cdt)
     qkv = torch.empty((geom.n_alloc, 3 * EMBED), device=x.device, dtype=cdt)
     if geom.n_alloc > N:
@@ -813,18 +845,28 @@ def _encoder_layer_forward_sm100(x: torch.Tensor, W: FrozenLayerWeights, geom: G
     # saved for the backward: f1 = fc1's fp32 output incl. bias (separate GELU'-LN' kernel) or gelu'(h) in bf16 with
     # u = gelu(h) (fused epilogue); y rides along (it is the next layer's saved input anyway: no extra memory)
     saved = (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f, y,
-             u if fused_bwd else None)
+             u if fused_bwd else None) + (tuple(below[:5]) if below is not None else (None,) * 5)
+    if fused_bwd:
+        _ffn_fwd_link[key] = (y.data_ptr(), tuple(y.shape), (x1, W.c1_2, W.c2_2, mean_f, rstd_f, W.w_2g.shape[1]))
     return y, saved
 
 
 def _encoder_layer_backward_sm100(dy: torch.Tensor, saved, W: FrozenLayerWeights, geom: Geometry, impl):
-    (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f, y, u) = saved
+    (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f, y, u) = saved[:17]
+    below = saved[17:22]
     cdt = torch.bfloat16
     dy = dy.contiguous()
+    key = _link_key(dy)
+    hand = _ffn_bwd_link.pop(key, None)
     if u is not None:
         # GELU' . LayerNorm' inside the epilogue of fc2's dX GEMM: the two row means of the LayerNorm backward are dot
-        # products of [N, 768] tensors (mt_ffn_bwd_prep), so the fp32 [N, 3072] gradient is never written or read
-        rowv, d_f2 = ffn_bwd_prep(dy, y, x1, W.c1_2, W.c2_2, mean_f, rstd_f, W.w_2g.shape[1])
+        # products of [N, 768] tensors, so the fp32 [N, 3072] gradient is never written or read.  When dy was produced by
+        # the backward of the layer above on this stream, that layer's last kernel has formed them already (hand-over by
+        # storage identity: autograd passes the gradient on through view nodes, which keep pointer and version)
+        if hand is not None and hand[0] == dy.data_ptr() and hand[1] == dy._version and hand[2] == tuple(dy.shape):
+            rowv, d_f2 = hand[3], hand[4]
+        else:
+            rowv, d_f2 = ffn_bwd_prep(dy, y, x1, W.c1_2, W.c2_2, mean_f, rstd_f, W.w_2g.shape[1])
         _, d_f1 = linear_sm100(d_f2, W.w_2g_t, mode=_lib.MT_EPI_GELU_LN_BWD, in_u=u, in_g=f1, stats=rowv, want_f32=False,
                                want_bf16=True)
     else:
@@ -841,8 +883,12 @@ def _encoder_layer_backward_sm100(dy: torch.Tensor, saved, W: FrozenLayerWeights
     del d_aln
     dqkv = dilated_attn_bwd(geom, qkv, dattn, lse, delta_br, impl[1])             # fp32 [N, 2304]
     dh1, _ = linear_sm100(cast(dqkv, cdt), W.w_qkv_t)
-    # the bf16 twin rides along for the layer below (its first dX GEMM takes it instead of a cast pass over dy)
-    dx, _, _ = layernorm_bwd(dh1, x, W.ln1[0], mean1, rstd1, torch.float32, residual=dx1, bf16_twin=True)
+    if below[0] is not None:
+        # x is the output of the layer below: form ITS FFN-backward row vector and bf16 gradient here (one more read)
+        dx, twin, rowv_b = layernorm_bwd_ffn_prep(dh1, x, W.ln1[0], mean1, rstd1, dx1, tuple(below) + (W.w_2g.shape[1],))
+        _ffn_bwd_link[key] = (dx.data_ptr(), dx._version, tuple(dx.shape), rowv_b, twin)
+    else:
+        dx, _, _ = layernorm_bwd(dh1, x, W.ln1[0], mean1, rstd1, torch.float32, residual=dx1)
     return dx
 
 

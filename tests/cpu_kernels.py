@@ -296,11 +296,18 @@ def ffn_bwd_prep(dy, y, x1, c1, c2, mean, rstd, ln_cols):
     return torch.stack([mean, rstd, m1, m2], 1).contiguous(), d16
 
 
+def layernorm_bwd_ffn_prep(dy, x, gamma, mean, rstd, residual, below):
+    dx, _, _ = layernorm_bwd(dy, x, gamma, mean, rstd, torch.float32, residual=residual)
+    x1b, c1, c2, mean_f, rstd_f, ln_cols = below
+    rowv, twin = ffn_bwd_prep(dx, x, x1b, c1, c2, mean_f, rstd_f, ln_cols)
+    return dx, twin, rowv
+
+
 def colsum(x):
     return x.sum(0)
 
 
-_NAMES = ["linear_sm100", "ffn_bwd_prep", "colsum", "layernorm_fwd", "layernorm_bwd", "add_layernorm_fwd", "gelu_ln_fwd", "gelu_ln_bwd", "dilated_attn_fwd",
+_NAMES = ["linear_sm100", "ffn_bwd_prep", "layernorm_bwd_ffn_prep", "colsum", "layernorm_fwd", "layernorm_bwd", "add_layernorm_fwd", "gelu_ln_fwd", "gelu_ln_bwd", "dilated_attn_fwd",
           "dilated_merge_ln_fwd", "dilated_merge_ln_bwd", "dilated_attn_bwd", "cross_attn_fwd", "cross_attn_bwd",
           "embed_assemble", "cast", "gated_residual_fwd", "gated_residual_bwd", "residual_bias_add"]
 

@@ -189,6 +189,29 @@ def test_cross_attention_tensor_core(lq, lk, packed):
     assert rel(lse, lse0) < 1e-3 and rel(o, o0) < 3e-3
 
 
+@pytest.mark.parametrize("rows", [1, 37, 1200, 10001])
+def test_layernorm_bwd_with_ffn_prep_of_the_layer_below(rows):
+    """mt_layernorm_bwd_ffn_prep = mt_layernorm_bwd (+ residual, + bf16 twin) and mt_ffn_bwd_prep of the layer below in
+    one kernel: against the two separate kernels and against the CPU stand-ins (oracle arithmetic)."""
+    g = torch.Generator().manual_seed(rows)
+    dy, x, res, x1b = (torch.randn(rows, 768, generator=g) for _ in range(4))
+    gamma, c1, c2 = (torch.randn(768, generator=g) for _ in range(3))
+    mean, mean_f = torch.randn(rows, generator=g) * 0.1, torch.randn(rows, generator=g)
+    rstd, rstd_f = torch.rand(rows, generator=g) + 0.5, torch.rand(rows, generator=g) + 0.5
+    d = lambda t: t.to(DEV)
+    dx, twin, rowv = ops.layernorm_bwd_ffn_prep(d(dy), d(x), d(gamma), d(mean), d(rstd), d(res),
+                                                (d(x1b), d(c1), d(c2), d(mean_f), d(rstd_f), 3072))
+    dx_s, _, _ = ops.layernorm_bwd(d(dy), d(x), d(gamma), d(mean), d(rstd), torch.float32, residual=d(res), bf16_twin=True)
+    rowv_s, twin_s = ops.ffn_bwd_prep(dx_s, d(x), d(x1b), d(c1), d(c2), d(mean_f), d(rstd_f), 3072)
+    # the same arithmetic in two kernels: equal up to the order of the fused multiply-adds
+    assert rel(dx, dx_s) < 1e-6 and rel(twin, twin_s) < 1e-2 and torch.equal(twin, dx.to(torch.bfloat16))
+    assert rel(rowv[:, :2], rowv_s[:, :2]) < 1e-6 and rel(rowv[:, 2:], rowv_s[:, 2:]) < 5e-3
+    dx_c, twin_c, rowv_c = C.layernorm_bwd_ffn_prep(dy, x, gamma, mean, rstd, res, (x1b, c1, c2, mean_f, rstd_f, 3072))
+    assert rel(dx, dx_c) < 1e-5 and rel(rowv[:, :2], rowv_c[:, :2]) < 1e-6
+    # m1, m2 are sums of 768 products of bf16-rounded gradients: one element rounding the other way moves them by 2^-9
+    assert rel(rowv[:, 2:], rowv_c[:, 2:]) < 5e-3
+
+
 @pytest.mark.parametrize("rows,cols", [(10000, 384), (10000, 192), (66, 768), (1, 4), (7, 3072), (40001, 768)])
 def test_colsum(rows, cols):
     g = torch.Generator().manual_seed(rows + cols)
