@@ -182,10 +182,16 @@ class GraphedStep:
     all-reduce of the flat gradient buffer runs after it.  Gradients live in ``flat.flat`` / ``p.grad`` views."""
 
     def __init__(self, model, projector, packed_example: Dict, sizes: Sequence[int], flat: FlatGradAllReduce,
-                 warmup: int = 3, pool=None, static: Optional[Dict] = None):
+                 warmup: int = 3, pool=None, static: Optional[Dict] = None, flatten: Optional[bool] = None):
         """``pool``: a ``torch.cuda.graph_pool_handle()`` shared with other captured steps that are never replayed
         concurrently (``GraphCache``); ``static``: pre-allocated device input buffers of the captured shapes (views of a
-        buffer shared by such steps) instead of private copies."""
+        buffer shared by such steps) instead of private copies; ``flatten``: gather the gradients into ONE flat buffer
+        inside the graph (what the all-reduce needs).  Default: only when there is more than one rank -- with a single
+        rank nothing is exchanged and the gather (a 135 MB copy in ~50 launches) would be pure overhead; ``grads`` then
+        concatenates on demand."""
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self._flatten = multi if flatten is None else bool(flatten)
         self.model, self.projector, self.flat, self.sizes = model, projector, flat, list(sizes)
         dev = next(model.parameters()).device
         if static is None:
@@ -219,10 +225,18 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, pool=self._pool):
             self.loss, self.logits = forward_backward(model, projector, slide)
-            self.grads = flat.gather()
+            self._flat_grads = flat.gather() if self._flatten else None
         # views of the captured flat buffer, handed back to ``p.grad`` after every replay
         self._grad_views = [p.grad for p in flat.params]
         self._signature = self._frozen_signature()
+
+    @property
+    def grads(self) -> torch.Tensor:
+        """The flat fp32 gradient vector of the last replay (the captured buffer, or a concatenation made on demand)."""
+        if self._flat_grads is not None:
+            return self._flat_grads
+        return torch.cat([(g if g is not None else torch.zeros_like(p)).reshape(-1)
+                          for p, g in zip(self.flat.params, self._grad_views)])
 
     def load(self, packed: Dict):
         """Copy one packed slide (pinned host or device tensors of the captured shapes) into the static inputs.  A slide
@@ -282,8 +296,9 @@ class GraphedStep:
         import torch.distributed as dist
 
         if reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
-            self.grads.div_(dist.get_world_size())
+            assert self._flat_grads is not None, "a step captured with flatten=False cannot exchange its gradients"
+            dist.all_reduce(self._flat_grads, op=dist.ReduceOp.SUM)
+            self._flat_grads.div_(dist.get_world_size())
         # ``optimizer.zero_grad()`` (set_to_none, the reference's loop) or ``flat.zero()`` drop ``p.grad``; the replay
         # has rewritten the flat buffer, so every parameter gets its view back and ``optimizer.step()`` sees it
         for p, g in zip(self.flat.params, self._grad_views):
@@ -341,7 +356,8 @@ class GraphCache:
                 self.steps.popitem(last=False)
             self.flat.zero()
             step = GraphedStep(self.model, self.projector, packed, self.sizes, self.flat,
-                               warmup=1 if not self.steps else 0, pool=self.pool, static=self._static_for(packed))
+                               warmup=1 if not self.steps else 0, pool=self.pool, static=self._static_for(packed),
+                               flatten=True)   # the caller accumulates the slides of a global step: one flat vector
             self.steps[L] = step
             return step(reduce=False)
         self.hits += 1
