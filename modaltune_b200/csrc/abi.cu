@@ -51,6 +51,10 @@ int make_dilated_geom(const mt_dilated_geometry* g, DilatedGeom* out) {
       return MT_E_UNSUPPORTED;
     }
     bg.hpb = g->n_heads / bg.r;
+    bg.pow2 = ((bg.r & (bg.r - 1)) == 0 && (bg.hpb & (bg.hpb - 1)) == 0 && g->n_tokens < (1 << 24)) ? 1 : 0;
+    bg.log2_hpb = 0;
+    while ((1 << bg.log2_hpb) < bg.hpb) ++bg.log2_hpb;
+    bg.inv_g = 1.0f / (float)bg.g;
     bg.o_off = o_off;
     bg.lse_off = l_off;
     o_off += (int64_t)g->n_tokens * bg.hpb * g->head_dim;

@@ -91,6 +91,9 @@ struct BranchGeom {
   int m;         // sparse slots per (segment, head) = ceil(g / r)
   int n_seg;     // ceil(N / g)
   int hpb;       // heads that own one position = H / r (>= 1)
+  int pow2;      // 1 when r and hpb are powers of two (always with 16 heads): ownership is shifts and masks
+  int log2_hpb;
+  float inv_g;   // 1 / g: p % g by a float reciprocal and one correction step (positions < 2^24)
   int64_t o_off;    // element offset of this branch in o_br   (layout [N][hpb*D])
   int64_t lse_off;  // element offset of this branch in lse_br (layout [N][hpb])
 };
@@ -104,7 +107,18 @@ struct DilatedGeom {
 int make_dilated_geom(const mt_dilated_geometry* g, DilatedGeom* out);
 
 // does head h own position p in branch b?  (p % g) % r == floor(h*r/H); also gives the compact head slot
+// The merge kernels evaluate this for every (position, head, branch): with run-time divisors the three integer
+// divisions were most of their instruction stream, so the common case avoids them.
 __device__ __forceinline__ bool branch_owns(const BranchGeom& bg, int H, int p, int h, int* slot) {
+  if (bg.pow2) {
+    const int q = __float2int_rz(__int2float_rn(p) * bg.inv_g);
+    int local = p - q * bg.g;                       // q is floor(p / g) or one off: one correction step is exact
+    if (local < 0) local += bg.g;
+    else if (local >= bg.g) local -= bg.g;
+    const int o = h >> bg.log2_hpb;                 // (h * r) / H = h / (H / r)
+    *slot = h & (bg.hpb - 1);
+    return (local & (bg.r - 1)) == o;
+  }
   int o = (h * bg.r) / H;
   int local = p % bg.g;
   *slot = h - o * bg.hpb;
