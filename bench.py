@@ -318,13 +318,17 @@ def extra_records(args, model, proj, flat, dev, world, rank, timed, barrier):
             # captures every shape (all misses), epoch 2 revisits the same slides (what training does): all hits.
             packed = [train_step.pack_host_slide(h) for h in hosts]
             cache = train_step.GraphCache(model, proj, flat, packed[0][1], max_tiles=max(counts) + 1)
-            accum = torch.zeros(flat.numel, device=dev)
+            accum = []
 
             def epoch():
-                accum.zero_()
+                for a in accum:
+                    a.zero_()
                 for pk in packed:
                     cache(pk[0])
-                    accum.add_(cache.steps[int(pk[0]["x"].shape[-2])].grads)   # consumed before the next replay
+                    bufs = cache.steps[int(pk[0]["x"].shape[-2])].grad_buffers    # consumed before the next replay
+                    if not accum:
+                        accum.extend(torch.zeros_like(b) for b in bufs)
+                    torch._foreach_add_(accum, bufs)
 
             ep = []
             for _ in range(2):
@@ -333,7 +337,8 @@ def extra_records(args, model, proj, flat, dev, world, rank, timed, barrier):
                 epoch()
                 e1.record()                  # this rank's own work: the exchange below would hide the imbalance
                 if world > 1:
-                    dist.all_reduce(accum)
+                    for a in accum:
+                        dist.all_reduce(a)
                 torch.cuda.synchronize()
                 own = torch.tensor([e0.elapsed_time(e1)], device=dev)
                 allr = [torch.zeros_like(own) for _ in range(world)]
@@ -348,7 +353,8 @@ def extra_records(args, model, proj, flat, dev, world, rank, timed, barrier):
                 "epoch1_capture_ms": max(ep[0]), "epoch2_replay_per_rank_ms": ep[1], "epoch2_makespan_ms": max(ep[1]),
                 "epoch2_measured_imbalance": max(ep[1]) / mean2 - 1.0, "epoch2_slides_per_s": len(counts) / (max(ep[1]) / 1e3),
                 "hits": cache.hits, "misses": cache.misses, "distinct_shapes": len(cache.steps)}
-            del cache, packed, accum
+            del cache, packed
+            accum.clear()
             flat.zero()
             torch.cuda.empty_cache()
         except Exception as e:

@@ -141,6 +141,47 @@ class FlatGradAllReduce:
             off += p.numel()
         return self.flat
 
+    def gather_buffers(self) -> List[torch.Tensor]:
+        """A few contiguous fp32 buffers that together hold every gradient exactly once, WITHOUT copying the gradients
+        that autograd already delivers as views of one tensor: the 1 324 per-pathway SNN parameters of the gene encoder
+        are evaluated as grouped GEMMs over ``cat`` / ``stack``-ed weights, so their gradients are slices (331 of them
+        transposed) of four stacked gradient tensors.  Flattening those one by one cost 331 transposing copies and most
+        of a ~50-launch ``cat`` per step; all-reducing the four bases in place costs nothing and ``p.grad`` keeps
+        aliasing them.  The remaining gradients go into one small flat buffer as before.  The layout is a function of
+        the model only, so every rank builds the same list."""
+        groups: Dict[int, list] = {}
+        order: List[int] = []
+        plain: List[int] = []
+        for i, p in enumerate(self.params):
+            g = p.grad
+            base = g._base if g is not None else None
+            if base is not None and base.dtype == torch.float32 and base.is_contiguous():
+                if id(base) not in groups:
+                    groups[id(base)] = [base, 0, []]
+                    order.append(id(base))
+                groups[id(base)][1] += g.numel()
+                groups[id(base)][2].append(i)
+            else:
+                plain.append(i)
+        bases = []
+        for k in order:
+            base, covered, members = groups[k]
+            if covered == base.numel() and len(members) > 1:
+                bases.append(base)          # the views tile the base: it IS the gradient of these parameters
+            else:
+                plain.extend(members)
+        plain.sort()
+        parts = [(self.params[i].grad if self.params[i].grad is not None else torch.zeros_like(self.params[i])).reshape(-1)
+                 for i in plain]
+        small = torch.cat(parts) if parts else torch.zeros(0, device=self.params[0].device)
+        off = 0
+        for i in plain:
+            p = self.params[i]
+            p.grad = small[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.buffers = [small] + bases
+        return self.buffers
+
     def all_reduce(self):
         import torch.distributed as dist
 
@@ -186,9 +227,9 @@ class GraphedStep:
         """``pool``: a ``torch.cuda.graph_pool_handle()`` shared with other captured steps that are never replayed
         concurrently (``GraphCache``); ``static``: pre-allocated device input buffers of the captured shapes (views of a
         buffer shared by such steps) instead of private copies; ``flatten``: gather the gradients into ONE flat buffer
-        inside the graph (what the all-reduce needs).  Default: only when there is more than one rank -- with a single
-        rank nothing is exchanged and the gather (a 135 MB copy in ~50 launches) would be pure overhead; ``grads`` then
-        concatenates on demand."""
+        inside the graph into the few contiguous buffers the all-reduce runs on (``FlatGradAllReduce.gather_buffers``).
+        Default: only when there is more than one rank -- with a single rank nothing is exchanged; ``grads`` concatenates
+        on demand either way."""
         import torch.distributed as dist
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self._flatten = multi if flatten is None else bool(flatten)
@@ -225,7 +266,7 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, pool=self._pool):
             self.loss, self.logits = forward_backward(model, projector, slide)
-            self._flat_grads = flat.gather() if self._flatten else None
+            self._bufs = flat.gather_buffers() if self._flatten else None
         # views of the captured flat buffer, handed back to ``p.grad`` after every replay
         self._grad_views = [p.grad for p in flat.params]
         self._signature = self._frozen_signature()
@@ -233,10 +274,14 @@ class GraphedStep:
     @property
     def grads(self) -> torch.Tensor:
         """The flat fp32 gradient vector of the last replay (the captured buffer, or a concatenation made on demand)."""
-        if self._flat_grads is not None:
-            return self._flat_grads
         return torch.cat([(g if g is not None else torch.zeros_like(p)).reshape(-1)
                           for p, g in zip(self.flat.params, self._grad_views)])
+
+    @property
+    def grad_buffers(self) -> Optional[List[torch.Tensor]]:
+        """The captured contiguous gradient buffers (``FlatGradAllReduce.gather_buffers``; None when captured with
+        ``flatten=False``): what is exchanged between ranks and what a caller accumulates over the slides of a step."""
+        return self._bufs
 
     def load(self, packed: Dict):
         """Copy one packed slide (pinned host or device tensors of the captured shapes) into the static inputs.  A slide
@@ -296,9 +341,10 @@ class GraphedStep:
         import torch.distributed as dist
 
         if reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            assert self._flat_grads is not None, "a step captured with flatten=False cannot exchange its gradients"
-            dist.all_reduce(self._flat_grads, op=dist.ReduceOp.SUM)
-            self._flat_grads.div_(dist.get_world_size())
+            assert self._bufs is not None, "a step captured with flatten=False cannot exchange its gradients"
+            for b in self._bufs:
+                dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            torch._foreach_div_(self._bufs, float(dist.get_world_size()))
         # ``optimizer.zero_grad()`` (set_to_none, the reference's loop) or ``flat.zero()`` drop ``p.grad``; the replay
         # has rewritten the flat buffer, so every parameter gets its view back and ``optimizer.step()`` sees it
         for p, g in zip(self.flat.params, self._grad_views):

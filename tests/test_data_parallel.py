@@ -64,3 +64,23 @@ def test_zero_drops_grads_and_gather_realiases():
     assert all(float(p.grad.max()) == 2.0 for p in flat.params)   # views of the flat buffer
     flat.zero()
     assert all(p.grad is None for p in flat.params)
+
+
+def test_gather_buffers_exchanges_stacked_gradients_in_place():
+    """``gather_buffers`` (what a captured step all-reduces with more than one rank): the per-pathway SNN gradients stay
+    the slices of the stacked gradient tensors autograd delivers (no copies), everything else goes into one small flat
+    buffer, every gradient is covered exactly once, and ``p.grad`` aliases the buffers (a scaling of the buffers -- the
+    all-reduce -- shows up in every ``p.grad``)."""
+    model, flat = _grads_for(511)
+    want = {id(p): p.grad.clone() for p in flat.params if p.grad is not None}
+    bufs = flat.gather_buffers()
+    assert len(bufs) > 1 and all(b.is_contiguous() and b.dtype == torch.float32 for b in bufs)
+    assert sum(b.numel() for b in bufs) == flat.numel                      # every gradient exactly once
+    n_views = sum(1 for p in flat.params if p.grad is not None and p.grad._base is not None
+                  and any(p.grad._base is b for b in bufs[1:]))
+    assert n_views >= 4 * len(helpers.SMALL_GROUPS)                        # the SNN weights and biases of every pathway
+    for b in bufs:
+        b.mul_(0.5)
+    for p in flat.params:
+        if id(p) in want:
+            assert torch.equal(p.grad, want[id(p)] * 0.5)
