@@ -23,7 +23,8 @@ import torch  # noqa: E402
 def run(tiles: int = 10000, steps: int = 3, warmup: int = 2, dev="cuda"):
     from modaltune_b200 import factory, launcher, synthetic
 
-    ref = launcher.find_reference()
+    staged = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "reference")
+    ref = launcher.find_reference(staged if os.path.isdir(staged) else None)   # measurement tooling: the staged copy
     launcher.install_shims(ref)
     launcher.swap_classes("reference")
     from models.aggregators import Aggregator  # the reference's registry and classes
