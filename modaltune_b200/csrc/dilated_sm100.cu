@@ -399,6 +399,323 @@ dilated_fwd_sm100_kernel(const __grid_constant__ TensorMaps maps, const Sm100Par
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// forward with 48-key score tiles (impl 3): the same pipeline as dilated_fwd_sm100_kernel with S 48 + P 24 + O 48 = 120
+// TMEM columns (a 128-column allocation) and 40 KB of shared memory per CTA, so FOUR CTAs are resident per SM instead of
+// two: sixteen softmax warps (four per scheduler) keep the MUFU pipe fed where two per scheduler leave it idle 23 % of
+// the time.  The Q K^T MMAs are N = 48 (bound by the A read: 3 x 46 cycles per tile), P V is three
+// k-steps; per 128 x 128 score block that is ~560 tensor cycles against the 1 024-cycle MUFU floor.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef MT_K48_KT
+#define MT_K48_KT 48
+#endif
+static constexpr int KT = MT_K48_KT;          // key slots per score tile: 48 (or 32 in experiment builds)
+static constexpr int KT_BYTES = KT * 128;     // [48 key slots][128 B], SWIZZLE_128B: six 1 KB atoms
+static constexpr uint32_t TMEM48_COLS = 128;  // S: [0,48)  P (bf16 pairs): [48,72)  O: [80,128)
+#ifndef MT_K48_STAGES
+#define MT_K48_STAGES 3
+#endif
+#ifndef MT_K48_POLY
+#define MT_K48_POLY 0                        // exponentials per 8 computed on the FMA pipes (ex2_poly)
+#endif
+static constexpr int KS = MT_K48_STAGES;     // K / V ring stages
+struct Fwd48Smem {
+  static constexpr int Q = 0;
+  static constexpr int K = Q + TILE_BYTES;
+  static constexpr int V = K + KS * KT_BYTES;
+  static constexpr int BAR = V + KS * KT_BYTES;
+  // barriers (8 B each): q_full, s_full, s_free, p_full, o_full[2], kv_full[KS], kv_empty[KS]; then the TMEM pointer
+  static constexpr int NBAR = 6 + 2 * KS;
+  static constexpr int TMEM_PTR = BAR + NBAR * 8;
+  static constexpr int TOTAL = TMEM_PTR + 16;
+};
+
+__global__ void __launch_bounds__(FWD_THREADS, 4)
+dilated_fwd_sm100_k48_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ TensorMaps kv_maps,
+                             const Sm100Params P, __nv_bfloat16* __restrict__ o_br,
+                         float* __restrict__ lse_br) {
+  MT_TL_BEGIN
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  // roles by warp id: the scheduler favours high warp ids, so the latency-critical single-thread roles sit last
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int W_TMA = 4, W_MMA = 5;
+  if ((sbase & 1023u) != 0) {  // SWIZZLE_128B tiles need 1024-byte alignment; never expected, but fail loudly
+    __trap();
+  }
+  // ---- which tile -------------------------------------------------------------------------------------------------
+  int oi = 0;
+  while (oi + 1 < P.geo.nb && (int)blockIdx.x >= P.item_prefix[oi + 1]) ++oi;
+  const int b = P.order[oi];
+  const BranchGeom bg = P.geo.b[b];
+  int local = blockIdx.x - P.item_prefix[oi];
+  const int qt = local % P.tiles[b];
+  local /= P.tiles[b];
+  const int h = local % P.geo.H;
+  const int s = local / P.geo.H;
+  const int H = P.geo.H, N = P.geo.N, E = H * DH;
+  const int off = (h * bg.r) / H;                    // residue of the positions this head owns
+  const int jseg = (s * bg.g) / bg.r;                // first slot of the segment in the branch's j axis
+  const int q0 = qt * BT;
+  // Zero padding (positions >= N in the last segment, dilated_attention.py:82-111) in whole tiles is never computed:
+  // a query tile without a real position writes nothing, and key tiles without a real position are all zero keys
+  // (score 0, value 0), whose only effect -- n_zero_tail * exp(0 - max) in the softmax denominator -- is added in
+  // closed form in the epilogue.  At 32k tiles 30 % of the padded tile pairs of the reference disappear this way.
+  const int seg_lo = s * bg.g + off;
+  const int c_real = min(N, (s + 1) * bg.g) > seg_lo ? (min(N, (s + 1) * bg.g) - seg_lo + bg.r - 1) / bg.r : 0;
+  if (q0 >= c_real) return;
+  const int n_kv = min((bg.m + KT - 1) / KT, (c_real + KT - 1) / KT);
+  const int n_zero_tail = max(0, bg.m - n_kv * KT);
+
+  const uint32_t bar_q_full = sbase + Fwd48Smem::BAR + 0;
+  const uint32_t bar_s_full = sbase + Fwd48Smem::BAR + 8;
+  const uint32_t bar_s_free = sbase + Fwd48Smem::BAR + 16;
+  const uint32_t bar_p_full = sbase + Fwd48Smem::BAR + 24;
+  const uint32_t bar_o_full = sbase + Fwd48Smem::BAR + 32;    // [2]
+  const uint32_t bar_kv_full = sbase + Fwd48Smem::BAR + 48;   // [KS]
+  const uint32_t bar_kv_empty = bar_kv_full + 8 * KS;         // [KS]
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Fwd48Smem::TMEM_PTR);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q_full, 1);
+    for (int i = 0; i < KS; ++i) {
+      mbar_init(bar_kv_full + 8 * i, 1);
+      mbar_init(bar_kv_empty + 8 * i, 1);
+    }
+    mbar_init(bar_o_full, 1);
+    mbar_init(bar_o_full + 8, 1);
+    mbar_init(bar_s_full, 1);
+    mbar_init(bar_s_free, 128);
+    mbar_init(bar_p_full, 128);
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.m[b]);
+    tma_prefetch_desc(&kv_maps.m[b]);
+  }
+  if (warp == W_MMA) {
+    tmem_alloc(smem_u32((const void*)tmem_slot), TMEM48_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_s = tmem;
+  const uint32_t tmem_p = tmem + KT;   // P as the A operand of P V: lane = query row, column k/2 holds keys (k, k+1)
+  const uint32_t tmem_o = tmem + 80;
+
+  if (warp == W_TMA) {
+    // ===== TMA producer ===============================================================================================
+    if (lane == 0) {
+      const void* map = &maps.m[b];
+      const void* kmap = &kv_maps.m[b];    // the same view with a 48-slot box
+      mbar_expect_tx(bar_q_full, TILE_BYTES);
+      tma_load_3d(sbase + Fwd48Smem::Q, map, bar_q_full, h * DH, off, jseg + q0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % KS, use = j / KS;
+        mbar_wait(bar_kv_empty + 8 * st, (use & 1) ^ 1);
+        mbar_expect_tx(bar_kv_full + 8 * st, 2 * KT_BYTES);
+        tma_load_3d(sbase + Fwd48Smem::K + st * KT_BYTES, kmap, bar_kv_full + 8 * st, E + h * DH, off, jseg + j * KT);
+        tma_load_3d(sbase + Fwd48Smem::V + st * KT_BYTES, kmap, bar_kv_full + 8 * st, 2 * E + h * DH, off, jseg + j * KT);
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ===== MMA issuer =================================================================================================
+    constexpr uint32_t IDESC_QK = umma_idesc_bf16(BT, KT, 0, 0);
+    constexpr uint32_t IDESC_PV = umma_idesc_bf16(BT, DH, 0, 1);
+    // descriptors are built once; inside the loops an MMA costs one UTCHMMA (+ a constant descriptor advance)
+    const uint64_t q_desc = umma_smem_desc(sbase + Fwd48Smem::Q, 16, 1024);
+    const uint64_t k_desc0 = umma_smem_desc(sbase + Fwd48Smem::K, 16, 1024);
+    const uint64_t v_desc0 = umma_smem_desc(sbase + Fwd48Smem::V, KT_BYTES, 1024);
+    auto issue_qk = [&](int j) {  // S = Q K_j^T : three k-steps of 16 inside the 128-byte swizzle atom
+      if (elect_one()) {
+        const uint64_t kd = umma_desc_adv(k_desc0, (uint32_t)(j % KS) * KT_BYTES);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_ss(tmem_s, umma_desc_adv(q_desc, k * 32), umma_desc_adv(kd, k * 32), IDESC_QK, k > 0);
+        umma_commit(bar_s_full);
+      }
+      __syncwarp();
+    };
+    MT_TRACE_DECL
+    mbar_wait(bar_q_full, 0);
+    mbar_wait(bar_kv_full, 0);
+    tc_fence_after();
+    MT_TRACE(0);
+    issue_qk(0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) {
+        mbar_wait(bar_kv_full + 8 * ((j + 1) % KS), ((j + 1) / KS) & 1);
+        MT_TRACE(100 + j);
+        mbar_wait(bar_s_free, j & 1);  // the softmax threads have read S_j out of TMEM
+        tc_fence_after();
+        MT_TRACE(200 + j);
+        issue_qk(j + 1);
+      }
+      mbar_wait(bar_p_full, j & 1);    // P_j is in TMEM (and the O tile of P_{j-1} V_{j-1} has been folded)
+      tc_fence_after();
+      MT_TRACE(300 + j);
+      if (elect_one()) {
+        // O_tile = P_j V_j : A = P straight from TMEM (16 keys = 8 packed columns per k-step), B = V in place as an
+        // MN-major operand (keys are the rows of the tile: 16 rows = 2048 B per k-step)
+        const uint64_t vd = umma_desc_adv(v_desc0, (uint32_t)(j % KS) * KT_BYTES);
+#pragma unroll
+        for (int k = 0; k < KT / 16; ++k)
+          umma_ts(tmem_o, tmem_p + k * 8, umma_desc_adv(vd, k * 2048), IDESC_PV, (j > 0) || (k > 0));
+        umma_commit(bar_kv_empty + 8 * (j % KS));
+        umma_commit(bar_o_full);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) { MT_TRACE_DUMP("mma"); }
+  } else {
+    // ===== softmax: one query row per thread; O accumulates in TMEM over the whole key loop =========================
+    // The row maximum used for the exponentials is only raised when the new maximum exceeds it by more than 8 in the
+    // log2 domain (P <= 2^8 stays exact enough in bf16, l is fp32): the O accumulator then never needs the per-tile
+    // rescale, and in the rare tile where a row does move, its warp rescales its 32 rows of O in TMEM in place.
+    const int lane_grp = warp & 3;                    // TMEM lanes this warp may touch: [32*lane_grp, +32)
+    constexpr int half = 0;
+    constexpr int NC = KT;                            // score columns per thread
+    constexpr int OC = DH;                            // output columns per thread
+    const int row = lane_grp * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
+    float m_used = -INFINITY, l_run = 0.f;
+    const float scale_log2 = P.scale_log2;
+    MT_TRACE_DECL
+    auto tile = [&](int j, auto mask_tag) {
+      constexpr bool MASK = decltype(mask_tag)::value;
+      const int kvalid = bg.m - j * KT;  // key slots of this tile that belong to the segment (>= 1)
+      MT_TRACE(1000 + j);
+      mbar_wait(bar_s_full, j & 1);
+      tc_fence_after();
+      MT_TRACE(1100 + j);
+      float sv[NC];
+      {
+        float lo[32], hi[16];
+        tmem_ld32(tmem_s + t_lane, lo);
+        if constexpr (KT > 32) tmem_ld16(tmem_s + t_lane + 32, hi);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sv[i] = lo[i];
+        if constexpr (KT > 32) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sv[32 + i] = hi[i];
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_s_free);          // S_j is in registers: the MMA warp may overwrite it with S_{j+1}
+      if (MASK) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) sv[i] = (half * NC + i < kvalid) ? sv[i] : -INFINITY;
+      }
+      float mx = fmax3(sv[0], sv[1], sv[2]);
+#pragma unroll
+      for (int i = 3; i + 1 < NC; i += 2) mx = fmax3(mx, sv[i], sv[i + 1]);
+      mx = fmaxf(mx, sv[NC - 1]);
+      MT_TRACE(1200 + j);
+      bool waited = false;
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool need = (mx - m_used) * scale_log2 > 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(bar_o_full, (j - 1) & 1);   // P V of tile j-1 has completed: O may be touched
+          tc_fence_after();
+          waited = true;
+          const float alpha = need ? ex2((m_used - mx) * scale_log2) : 1.f;
+          float t[8];
+#pragma unroll
+          for (int c = 0; c < OC / 8; ++c) {
+            tmem_ld8(tmem_o + t_lane + half * OC + c * 8, t);
+            tmem_ld_wait();
+            uint32_t u[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u[i] = __float_as_uint(t[i] * alpha);
+            tmem_st8(tmem_o + t_lane + half * OC + c * 8, u);
+          }
+          if (need) {
+            l_run *= alpha;
+            m_used = mx;
+          }
+        }
+      }
+      const float mb = m_used * scale_log2;
+      if (j > 0 && !waited) {             // P_j overwrites P_{j-1}: its P V must have read it
+        mbar_wait(bar_o_full, (j - 1) & 1);
+        tc_fence_after();
+      }
+      MT_TRACE(1300 + j);
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < NC / 16; ++c) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const float x0 = fmaf(sv[c * 16 + i], scale_log2, -mb);
+          const float x1 = fmaf(sv[c * 16 + i + 1], scale_log2, -mb);
+          const float p0 = (!MASK && (i & 7) < MT_K48_POLY) ? ex2_poly(x0) : ex2(x0);
+          const float p1 = (!MASK && ((i + 1) & 7) < MT_K48_POLY) ? ex2_poly(x1) : ex2(x1);
+          rs += p0 + p1;
+          pk[i >> 1] = pack_bf16(p0, p1);
+        }
+        tmem_st8(tmem_p + t_lane + c * 8, pk);   // 16 keys = 8 packed columns
+      }
+      l_run += rs;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_p_full);
+      MT_TRACE(1400 + j);
+    };
+    for (int j = 0; j < n_kv; ++j) {
+      if (bg.m - j * KT >= KT) tile(j, std::false_type{});
+      else tile(j, std::true_type{});
+    }
+    mbar_wait(bar_o_full, (n_kv - 1) & 1);
+    tc_fence_after();
+    if (warp == 0 && lane == 0) { MT_TRACE_DUMP("smx"); }
+    // ---- epilogue: normalise and write the compact per-branch output ---------------------------------------------
+    const int slot = q0 + row;
+    const int pos = s * bg.g + off + slot * bg.r;
+    const int seg_end = min(N, (s + 1) * bg.g);
+    float o_acc[OC];
+#pragma unroll
+    for (int c = 0; c < OC / 8; ++c) {
+      float t[8];
+      tmem_ld8(tmem_o + t_lane + half * OC + c * 8, t);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o_acc[c * 8 + i] = t[i];
+    }
+    if (n_zero_tail > 0) {   // the zero keys of the tiles that were skipped
+      const float m_fin = fmaxf(m_used, 0.f);
+      const float alpha = ex2((m_used - m_fin) * scale_log2);
+      l_run = l_run * alpha + (float)n_zero_tail * ex2(-m_fin * scale_log2);
+#pragma unroll
+      for (int i = 0; i < OC; ++i) o_acc[i] *= alpha;
+      m_used = m_fin;
+    }
+    if (slot < bg.m && pos < seg_end) {
+      const float inv = 1.f / l_run;
+      const int slot_h = h - off * bg.hpb;
+      __nv_bfloat16* dst = o_br + bg.o_off + ((int64_t)pos * bg.hpb + slot_h) * DH + half * OC;
+#pragma unroll
+      for (int c = 0; c < OC / 8; ++c) {
+        uint4 u;
+        u.x = pack_bf16(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
+        u.y = pack_bf16(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
+        u.z = pack_bf16(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv);
+        u.w = pack_bf16(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + c * 8) = u;
+      }
+      if (half == 0) lse_br[bg.lse_off + (int64_t)pos * bg.hpb + slot_h] = m_used * P.scale + logf(l_run);
+    }
+  }
+  // ---- teardown ------------------------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc(tmem, TMEM48_COLS);
+  MT_TL_END(n_kv)
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // forward, persistent (impl 2): the same per-tile pipeline, but the CTAs (2 per SM) stay resident and pull
 // (branch, segment, head, query tile) items from a device counter, longest key loops first.  Measured on B200
 // (tools/attn_timeline.py): a one-shot CTA lives 2 650 cycles per key tile + 4 400 cycles of prologue / epilogue, i.e. a
@@ -798,7 +1115,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 3-D view of a row-major [n_alloc, ld] bf16 matrix for dilation r: (column, residue o, slot j) -> row j*r + o
-static int encode_branch_map(CUtensorMap* map, const void* base, int64_t ld, int64_t n_alloc, int r) {
+static int encode_branch_map(CUtensorMap* map, const void* base, int64_t ld, int64_t n_alloc, int r, int box_rows = BT) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -806,7 +1123,7 @@ static int encode_branch_map(CUtensorMap* map, const void* base, int64_t ld, int
   }
   cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)r, (cuuint64_t)(n_alloc / r)};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)r};
-  cuuint32_t box[3] = {64, 1, (cuuint32_t)BT};
+  cuuint32_t box[3] = {64, 1, (cuuint32_t)box_rows};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -902,6 +1219,22 @@ int dilated_attn_fwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int
   for (int b = 0; b < P.geo.nb; ++b) {
     rc = encode_branch_map(&maps.m[b], qkv, qkv_ld, n_alloc, P.geo.b[b].r);
     if (rc) return rc;
+  }
+  if (impl == 3) {   // 48-key score tiles, four CTAs per SM
+    TensorMaps kv_maps;
+    memset(&kv_maps, 0, sizeof(kv_maps));
+    for (int b = 0; b < P.geo.nb; ++b) {
+      rc = encode_branch_map(&kv_maps.m[b], qkv, qkv_ld, n_alloc, P.geo.b[b].r, KT);
+      if (rc) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+      MT_CUDA(cudaFuncSetAttribute(dilated_fwd_sm100_k48_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd48Smem::TOTAL));
+      attr_set = true;
+    }
+    dilated_fwd_sm100_k48_kernel<<<P.item_prefix[P.geo.nb], FWD_THREADS, Fwd48Smem::TOTAL, st>>>(
+        maps, kv_maps, P, (__nv_bfloat16*)o_br, lse_br);
+    return check_launch("dilated_fwd_sm100_k48_kernel");
   }
   if (impl == 2) {   // persistent CTAs with a device work counter
     int* counter = next_work_counter();

@@ -288,7 +288,7 @@ def test_dilated_attention_linearity_in_v_at_full_size():
 # sizes at which the tcgen05 kernels are held against the ORACLE itself (not only against the SIMT kernels): every small
 # geometry plus the bench geometries of BASELINE configs 2 and 3 (the oracle core needs 2 - 25 s of host time there)
 ORACLE_SIZES = {n for n, _ in GEOMS} | {5793, 10001, 32769}
-FWD_IMPLS = (1, 2)      # tcgen05 variants of mt_dilated_attn_fwd: one CTA per item, persistent CTAs (0 = SIMT cross-check)
+FWD_IMPLS = (1, 2, 3)   # tcgen05 variants of mt_dilated_attn_fwd: one CTA per item, persistent CTAs, 48-key score tiles (0 = SIMT cross-check)
 SM100_GEOMS = GEOMS + [(5793, None), (10001, None), (300, [128, 256, 512, 1024, 2048]),
                        # whole-tile padding skip: last segments with 1 / 128 / 129 real slots, real counts that are
                        # exact multiples of the 128-slot tile, tails of several all-padding tiles in every branch
