@@ -417,6 +417,9 @@ static constexpr uint32_t TMEM48_COLS = 128;  // S: [0,48)  P (bf16 pairs): [48,
 #ifndef MT_K48_POLY
 #define MT_K48_POLY 0                        // exponentials per 8 computed on the FMA pipes (ex2_poly)
 #endif
+#ifndef MT_K48_PACKED
+#define MT_K48_PACKED 1
+#endif
 static constexpr int KS = MT_K48_STAGES;     // K / V ring stages
 struct Fwd48Smem {
   static constexpr int Q = 0;
@@ -644,20 +647,36 @@ dilated_fwd_sm100_k48_kernel(const __grid_constant__ TensorMaps maps, const __gr
       }
       MT_TRACE(1300 + j);
       float rs = 0.f;
+#if MT_K48_PACKED
+      // packed fp32 pairs (FFMA2 / FADD2): the scale-and-shift and the row sum cost one instruction per TWO scores; with
+      // four softmax warps per scheduler the kernel is at 65 % issue-active, so instructions are worth saving
+      const float2 sc2 = make_float2(scale_log2, scale_log2), nb2 = make_float2(-mb, -mb);
+      float2 rs2 = make_float2(0.f, 0.f);
+#endif
 #pragma unroll
       for (int c = 0; c < NC / 16; ++c) {
         uint32_t pk[8];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
+#if MT_K48_PACKED
+          const float2 x = ffma2(make_float2(sv[c * 16 + i], sv[c * 16 + i + 1]), sc2, nb2);
+          const float2 pp = make_float2(ex2(x.x), ex2(x.y));
+          rs2 = fadd2(rs2, pp);
+          pk[i >> 1] = pack_bf16(pp.x, pp.y);
+#else
           const float x0 = fmaf(sv[c * 16 + i], scale_log2, -mb);
           const float x1 = fmaf(sv[c * 16 + i + 1], scale_log2, -mb);
           const float p0 = (!MASK && (i & 7) < MT_K48_POLY) ? ex2_poly(x0) : ex2(x0);
           const float p1 = (!MASK && ((i + 1) & 7) < MT_K48_POLY) ? ex2_poly(x1) : ex2(x1);
           rs += p0 + p1;
           pk[i >> 1] = pack_bf16(p0, p1);
+#endif
         }
         tmem_st8(tmem_p + t_lane + c * 8, pk);   // 16 keys = 8 packed columns
       }
+#if MT_K48_PACKED
+      rs = rs2.x + rs2.y;
+#endif
       l_run += rs;
       tmem_st_wait();
       tc_fence_before();

@@ -312,6 +312,18 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, f, 0x1.fff692p-1f);
   return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));   // p * 2^n through the exponent field
 }
+// two fp32 FMAs / adds in one instruction (FFMA2 / FADD2, sm_100): halves the issue slots of element-wise fp32 loops
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t ra = *reinterpret_cast<uint64_t*>(&a), rb = *reinterpret_cast<uint64_t*>(&b);
+  uint64_t rc = *reinterpret_cast<uint64_t*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  uint64_t ra = *reinterpret_cast<uint64_t*>(&a), rb = *reinterpret_cast<uint64_t*>(&b), rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
