@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import weakref
 from typing import Dict, Optional, Sequence, Tuple
 
 import torch
@@ -794,13 +795,23 @@ def _use_sm100_gemm(cdt: torch.dtype, rng) -> bool:
 
 # hand-over between consecutive frozen layers of one task pass (one slot per CUDA stream: the passes run on their own
 # streams and their autograd nodes interleave).  A slot is consumed by the NEXT layer call on that stream whether it
-# matches or not, so a stale entry can never meet an unrelated tensor that happens to reuse the address later.
+# matches or not, and a match needs the very tensor object (held weakly) or a view of it, with an unchanged version
+# counter: a stale entry can never meet an unrelated tensor that happens to reuse the address later.
 _ffn_fwd_link: Dict[int, tuple] = {}
 _ffn_bwd_link: Dict[int, tuple] = {}
 
 
 def _link_key(t: torch.Tensor) -> int:
     return torch.cuda.current_stream().cuda_stream if t.is_cuda else 0
+
+
+def _is_view_of(t: torch.Tensor, ref) -> bool:
+    """Is ``t`` the tensor ``ref()`` (a weak reference) or a full view of it?  Identity of the OBJECT, not of the address:
+    a tensor of a later step that happens to reuse the memory of a dead one never matches."""
+    src = ref()
+    if src is None:
+        return False
+    return (t is src or t._base is src) and t.data_ptr() == src.data_ptr() and t.numel() == src.numel()
 
 
 def _encoder_layer_forward_sm100(x: torch.Tensor, W: FrozenLayerWeights, geom: Geometry, impl):
@@ -814,7 +825,7 @@ def _encoder_layer_forward_sm100(x: torch.Tensor, W: FrozenLayerWeights, geom: G
     # that layer's FFN backward in its last kernel (see _encoder_layer_backward_sm100)
     key = _link_key(x)
     link = _ffn_fwd_link.pop(key, None)
-    below = link[2] if (link is not None and link[0] == x.data_ptr() and link[1] == tuple(x.shape)) else None
+    below = link[1] if (link is not None and _is_view_of(x, link[0]) and tuple(x.shape) == tuple(link[0]().shape)) else None
     h1, mean1, rstd1 = layernorm_fwd(x, W.ln1[0], W.ln1[1], cdt)
     qkv = torch.empty((geom.n_alloc, 3 * EMBED), device=x.device, dtype=cdt)
     if geom.n_alloc > N:
@@ -847,7 +858,7 @@ def _encoder_layer_forward_sm100(x: torch.Tensor, W: FrozenLayerWeights, geom: G
     saved = (x, mean1, rstd1, qkv, o_br, lse_br, lse, mean_a, rstd_a, x1, mean2, rstd2, f1, mean_f, rstd_f, y,
              u if fused_bwd else None) + (tuple(below[:5]) if below is not None else (None,) * 5)
     if fused_bwd:
-        _ffn_fwd_link[key] = (y.data_ptr(), tuple(y.shape), (x1, W.c1_2, W.c2_2, mean_f, rstd_f, W.w_2g.shape[1]))
+        _ffn_fwd_link[key] = (weakref.ref(y), (x1, W.c1_2, W.c2_2, mean_f, rstd_f, W.w_2g.shape[1]))
     return y, saved
 
 
@@ -863,8 +874,9 @@ def _encoder_layer_backward_sm100(dy: torch.Tensor, saved, W: FrozenLayerWeights
         # products of [N, 768] tensors, so the fp32 [N, 3072] gradient is never written or read.  When dy was produced by
         # the backward of the layer above on this stream, that layer's last kernel has formed them already (hand-over by
         # storage identity: autograd passes the gradient on through view nodes, which keep pointer and version)
-        if hand is not None and hand[0] == dy.data_ptr() and hand[1] == dy._version and hand[2] == tuple(dy.shape):
-            rowv, d_f2 = hand[3], hand[4]
+        if (hand is not None and _is_view_of(dy, hand[0]) and hand[1] == dy._version
+                and tuple(dy.shape) == tuple(hand[0]().shape)):
+            rowv, d_f2 = hand[2], hand[3]
         else:
             rowv, d_f2 = ffn_bwd_prep(dy, y, x1, W.c1_2, W.c2_2, mean_f, rstd_f, W.w_2g.shape[1])
         _, d_f1 = linear_sm100(d_f2, W.w_2g_t, mode=_lib.MT_EPI_GELU_LN_BWD, in_u=u, in_g=f1, stats=rowv, want_f32=False,
@@ -886,7 +898,7 @@ def _encoder_layer_backward_sm100(dy: torch.Tensor, saved, W: FrozenLayerWeights
     if below[0] is not None:
         # x is the output of the layer below: form ITS FFN-backward row vector and bf16 gradient here (one more read)
         dx, twin, rowv_b = layernorm_bwd_ffn_prep(dh1, x, W.ln1[0], mean1, rstd1, dx1, tuple(below) + (W.w_2g.shape[1],))
-        _ffn_bwd_link[key] = (dx.data_ptr(), dx._version, tuple(dx.shape), rowv_b, twin)
+        _ffn_bwd_link[key] = (weakref.ref(dx), dx._version, rowv_b, twin)
     else:
         dx, _, _ = layernorm_bwd(dh1, x, W.ln1[0], mean1, rstd1, torch.float32, residual=dx1)
     return dx
