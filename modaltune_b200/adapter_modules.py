@@ -221,10 +221,33 @@ class Extractor(nn.Module):
             query = query + self.drop_path(self.ffn(query))
         return query
 
-    def forward_full(self, query, xfull, pos=None):
-        """Same as ``forward`` with ``feat`` = the tile rows (1..) of the [1, N, 768] [cls | tiles] buffer ``xfull``."""
+    def kv_weights(self):
+        """The k | v projection of this extractor's memory with ``norm_kq`` folded in: LN(x) Wkv^T + b =
+        xhat (Wkv diag gamma)^T + (Wkv beta + b) for xhat = normalise(x) (``ops.shared_kv_project``)."""
+        cl = self.attn
+        mha = cl.multihead_attn
+        e = mha.embed_dim
+        wkv = torch.cat([mha.k_proj_weight, mha.v_proj_weight], 0)
+        return wkv * cl.norm_kq.weight[None, :], torch.addmv(mha.in_proj_bias[e:], wkv, cl.norm_kq.bias)
+
+    def forward_full(self, query, xfull, pos=None, kv=None):
+        """Same as ``forward`` with ``feat`` = the tile rows (1..) of the [1, N, 768] [cls | tiles] buffer ``xfull``.
+        ``kv``: this extractor's k | v [L, 384] already projected (a column slice of a projection shared with the other
+        extractors of the block); the memory LayerNorm and projection are skipped."""
         c = _rows(query).float()
-        a = self.attn.attend(c, _rows(xfull), None, pos, mem_row0=1)
+        if kv is not None:
+            cl = self.attn
+            mha = cl.multihead_attn
+            e = mha.embed_dim
+            t2 = ops.layer_norm(c, cl.norm.weight, cl.norm.bias, add=_pos_rows(pos, c.shape[0]))
+            qq = _lin(t2, cl.q_proj.weight, cl.q_proj.bias) if cl.with_cffn else t2
+            o = ops.cross_attention_kv(_lin(qq, mha.q_proj_weight, mha.in_proj_bias[:e]), kv, mha.num_heads)
+            a = _lin(o, mha.out_proj.weight, mha.out_proj.bias)
+            if cl.with_cffn:
+                a = _lin(a, cl.output_proj.weight, cl.output_proj.bias)
+            a = cl.dropout(a)
+        else:
+            a = self.attn.attend(c, _rows(xfull), None, pos, mem_row0=1)
         query = (c + (c + a)).unsqueeze(0)
         if self.with_cffn:
             query = query + self.drop_path(self.ffn(query))
@@ -319,6 +342,15 @@ class InteractionBlockWithCls_LongNetViT(InteractionBlockWithCls):
         for idx, blk in enumerate(blocks):
             xfull, _ = blk(xfull, incremental_state=(incremental_state[idx] if incremental_state is not None else None),
                            **layer_configs)
+        if self.extra_extractors is not None and config.shared_extractor_kv():
+            # the three extractors of the last block read the same slide tokens: one normalisation pass and one GEMM
+            # for all their k | v projections (ops.SharedKVProjectFn), each then attends on its column slice
+            exts = [self.extractor, *self.extra_extractors]
+            wb = [e.kv_weights() for e in exts]
+            kv_all = ops.shared_kv_project(_rows(xfull), torch.cat([w for w, _ in wb], 0), torch.cat([b for _, b in wb], 0), 1)
+            for e, kv in zip(exts, torch.split(kv_all, kv_all.shape[1] // len(exts), dim=1)):
+                c = e.forward_full(c, xfull, query_pos, kv=kv)
+            return xfull, c
         c = self.extractor.forward_full(c, xfull, query_pos)
         if self.extra_extractors is not None:
             for extractor in self.extra_extractors:

@@ -27,7 +27,18 @@ _state = {
     # backward of GELU + ffn_layernorm inside the epilogue of fc2's dX GEMM (MT_EPI_GELU_LN_BWD); "0" = the separate
     # GELU'-LN' kernel between two plain dX GEMMs (the path before, kept for comparison)
     "ffn_bwd_fused": os.environ.get("MODALTUNE_B200_FFN_BWD_FUSED", "1") != "0",
+    # one normalisation pass + one GEMM for the k | v projections of the three extractors of the last interaction block
+    # (ops.SharedKVProjectFn); "0" = every extractor normalises and projects the slide tokens itself
+    "shared_extractor_kv": os.environ.get("MODALTUNE_B200_SHARED_KV", "1") != "0",
 }
+
+
+def shared_extractor_kv() -> bool:
+    return _state["shared_extractor_kv"]
+
+
+def set_shared_extractor_kv(on: bool) -> None:
+    _state["shared_extractor_kv"] = bool(on)
 
 
 def ffn_bwd_fused() -> bool:

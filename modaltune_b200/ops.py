@@ -502,7 +502,8 @@ class CrossAttnFn(torch.autograd.Function):
     def forward(ctx, q, k, v, kv, heads):
         q = q.contiguous()
         if kv is not None:
-            kv = kv.contiguous()
+            if not (kv.stride(1) == 1 and kv.stride(0) % 8 == 0 and kv.data_ptr() % 16 == 0):
+                kv = kv.contiguous()      # a column slice of a wider projection buffer is read in place
             e = q.shape[1]
             k, v = kv[:, :e], kv[:, e:]
         else:
@@ -623,6 +624,58 @@ class GatedResidualFn(torch.autograd.Function):
 
 def gated_residual(a, b, gate, row0: int = 0):
     return GatedResidualFn.apply(a, b, gate, row0)
+
+
+class SharedKVProjectFn(torch.autograd.Function):
+    """k | v projections of SEVERAL Extractors that read the same slide tokens (the last interaction block runs three
+    on one ``xfull``, adapter_modules.py:508-516): LayerNorm statistics do not depend on the affine parameters, so with
+    ``xhat = normalise(x)`` every extractor's ``LN_e(x) Wkv_e^T + b_e`` is ``xhat (Wkv_e diag gamma_e)^T + (Wkv_e beta_e +
+    b_e)``: ONE normalisation pass and ONE GEMM against the stacked, composed weights (formed by the caller with
+    differentiable weight-sized ops) instead of three LayerNorms and three GEMMs over [L, 768]; in the backward one
+    dX GEMM, one dW GEMM, one affine-free LayerNorm backward, and the slide-token gradient is written once instead of
+    being summed from three [N, 768] tensors by autograd.
+
+    x [N, 768] fp32 (rows < row0 are skipped), w [n * 384, 768], b [n * 384]  ->  kv [N - row0, n * 384]."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, row0):
+        x = x.contiguous()
+        xv = x[row0:]
+        ones, zeros = _unit_affine(x.device, x.shape[1])
+        xhat, mean, rstd = layernorm_fwd(xv, ones, zeros, torch.float32)
+        kv = _adapter_addmm(b, xhat, w.t())
+        ctx.save_for_backward(x, xhat, w, mean, rstd)
+        ctx.row0 = row0
+        return kv
+
+    @staticmethod
+    def backward(ctx, dkv):
+        x, xhat, w, mean, rstd = ctx.saved_tensors
+        row0 = ctx.row0
+        dkv = dkv.contiguous()
+        db = colsum(dkv)
+        dw = _adapter_mm(dkv.t(), xhat)
+        dxhat = _adapter_mm(dkv, w)
+        ones, _ = _unit_affine(x.device, x.shape[1])
+        dx = torch.empty_like(x)
+        if row0:
+            dx[:row0].zero_()
+        layernorm_bwd(dxhat, x[row0:], ones, mean, rstd, torch.float32, out=dx[row0:])
+        return dx, dw, db, None
+
+
+_unit_affine_cache: Dict[tuple, tuple] = {}
+
+
+def _unit_affine(device, cols: int):
+    key = (str(device), cols)
+    if key not in _unit_affine_cache:
+        _unit_affine_cache[key] = (torch.ones(cols, device=device), torch.zeros(cols, device=device))
+    return _unit_affine_cache[key]
+
+
+def shared_kv_project(x, w, b, row0: int = 0):
+    return SharedKVProjectFn.apply(x, w, b, row0)
 
 
 def _adapter_mm(a, b):
