@@ -292,7 +292,8 @@ class Injector(nn.Module):
 
     def _can_fuse(self):
         cl = self.attn
-        return cl.normalize_before and not (self.training and (cl.dropout.p > 0.0 or cl.multihead_attn.dropout > 0.0))
+        return (config.flag("injector_fused") and cl.normalize_before
+                and not (self.training and (cl.dropout.p > 0.0 or cl.multihead_attn.dropout > 0.0)))
 
     def forward_full(self, xfull, feat, pos=None):
         """Same as ``forward`` on the tile rows (1..) of the [1, N, 768] [cls | tiles] buffer; the cls row passes through."""

@@ -30,7 +30,15 @@ _state = {
     # one normalisation pass + one GEMM for the k | v projections of the three extractors of the last interaction block
     # (ops.SharedKVProjectFn); "0" = every extractor normalises and projects the slide tokens itself
     "shared_extractor_kv": os.environ.get("MODALTUNE_B200_SHARED_KV", "1") != "0",
+    # A / B switches of round-2 host-side restructurings (all default on; "0" = the path before)
+    "injector_fused": os.environ.get("MODALTUNE_B200_INJECTOR_FUSED", "1") != "0",     # ops.InjectorFn
+    "split_param_grads": os.environ.get("MODALTUNE_B200_SPLIT_GRADS", "1") != "0",     # per-pass leaf aliases
+    "cross_tc": os.environ.get("MODALTUNE_B200_CROSS_TC", "1") != "0",                 # TF32 tensor-core cross-attention
 }
+
+
+def flag(name: str) -> bool:
+    return bool(_state[name])
 
 
 def shared_extractor_kv() -> bool:

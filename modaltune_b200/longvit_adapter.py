@@ -155,9 +155,11 @@ class LongNetGeneAdapter(LongNetViT):
         emb = self.embed(x, coords)
         gene = None if self.training else self.gene_encoder(genes)
         self._pass_aliases = None
-        if split_grads and torch.is_grad_enabled() and len(task_tokens) > 1:
-            named = [(n, p) for n, p in self.named_parameters()
-                     if p.requires_grad and (gene is None or not n.startswith("gene_encoder."))]
+        if split_grads and config.flag("split_param_grads") and torch.is_grad_enabled() and len(task_tokens) > 1:
+            # the gene encoder stays on the shared leaves: in eval mode it runs once for all passes, and in train mode its
+            # 1 324 per-pathway gradients are strided slices of stacked tensors, which the multi-tensor add of
+            # forward_backward would handle one tensor at a time (measured: +3.5 ms per train-mode step)
+            named = [(n, p) for n, p in self.named_parameters() if p.requires_grad and not n.startswith("gene_encoder.")]
             self._pass_aliases = [{n: p.detach().requires_grad_(True) for n, p in named} for _ in task_tokens]
 
         def one_pass(t, k=0):

@@ -308,7 +308,7 @@ def _ptr(t: torch.Tensor):
 def cross_impl(t: torch.Tensor) -> int:
     """``impl`` of mt_cross_attn_*: TF32 tensor cores for fp32 tensors in bf16 mode, exact fp32 SIMT math otherwise."""
     from . import config
-    return 1 if (config.mode() == "bf16" and t.dtype == torch.float32) else 0
+    return 1 if (config.mode() == "bf16" and t.dtype == torch.float32 and config.flag("cross_tc")) else 0
 
 
 def cross_attn_fwd(q, k, v, heads: int, impl: Optional[int] = None):

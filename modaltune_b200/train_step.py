@@ -141,14 +141,10 @@ class FlatGradAllReduce:
             off += p.numel()
         return self.flat
 
-    def gather_buffers(self) -> List[torch.Tensor]:
-        """A few contiguous fp32 buffers that together hold every gradient exactly once, WITHOUT copying the gradients
-        that autograd already delivers as views of one tensor: the 1 324 per-pathway SNN parameters of the gene encoder
-        are evaluated as grouped GEMMs over ``cat`` / ``stack``-ed weights, so their gradients are slices (331 of them
-        transposed) of four stacked gradient tensors.  Flattening those one by one cost 331 transposing copies and most
-        of a ~50-launch ``cat`` per step; all-reducing the four bases in place costs nothing and ``p.grad`` keeps
-        aliasing them.  The remaining gradients go into one small flat buffer as before.  The layout is a function of
-        the model only, so every rank builds the same list."""
+    def _stacked_groups(self):
+        """Gradients that autograd delivers as views of one contiguous fp32 tensor which they tile completely (the
+        per-pathway SNN parameters of the gene encoder, evaluated as grouped GEMMs over ``cat`` / ``stack``-ed weights):
+        -> ([(base, [param index, ...]), ...], [indices of all other parameters])."""
         groups: Dict[int, list] = {}
         order: List[int] = []
         plain: List[int] = []
@@ -163,14 +159,69 @@ class FlatGradAllReduce:
                 groups[id(base)][2].append(i)
             else:
                 plain.append(i)
-        bases = []
+        stacked = []
         for k in order:
             base, covered, members = groups[k]
             if covered == base.numel() and len(members) > 1:
-                bases.append(base)          # the views tile the base: it IS the gradient of these parameters
+                stacked.append((base, members))
             else:
                 plain.extend(members)
         plain.sort()
+        return stacked, plain
+
+    def _dense_group(self, base: torch.Tensor, members: List[int]) -> torch.Tensor:
+        """The gradients of one stacked group in PARAMETER layout.  When every view is already laid out like its parameter
+        (slices of a ``stack``) the base itself is returned.  Otherwise (the 331 transposed slices of the ``cat``-ed first
+        SNN layer) ONE gather kernel writes a buffer of consecutive parameter-layout blocks and ``p.grad`` is re-pointed
+        at them: an optimizer's multi-tensor path wants gradients with the strides of their parameters, and producing
+        them one transposing copy per pathway is what the flat gather of round 1 spent most of its time on.  The gather
+        index depends on the model only and is cached."""
+        grads = [self.params[i].grad for i in members]
+        if all(g.is_contiguous() for g in grads):
+            return base
+        key = (tuple(base.shape),) + tuple((g.storage_offset() - base.storage_offset(), tuple(g.shape), tuple(g.stride()))
+                                           for g in grads)
+        cache = self.__dict__.setdefault("_gather_index", {})
+        if key not in cache:
+            idx = []
+            for off, shape, stride in key[1:]:
+                t = torch.full(shape, off, dtype=torch.int64)
+                for d, (n, st) in enumerate(zip(shape, stride)):
+                    view = [1] * len(shape)
+                    view[d] = n
+                    t = t + (torch.arange(n, dtype=torch.int64) * st).view(view)
+                idx.append(t.reshape(-1))
+            cache[key] = torch.cat(idx).to(base.device)
+        dense = base.reshape(-1).index_select(0, cache[key])
+        off = 0
+        for i in members:
+            p = self.params[i]
+            p.grad = dense[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        return dense
+
+    def densify(self) -> None:
+        """Make every ``p.grad`` dense in its parameter's layout (one gather kernel per stacked group that needs it);
+        what a single-rank step does instead of ``gather_buffers``."""
+        stacked, _ = self._stacked_groups()
+        for base, members in stacked:
+            self._dense_group(base, members)
+        # stragglers: strided gradients that are not views any more (train mode: the engine sums the three passes'
+        # transposed slices into a tensor that keeps their strides).  One copy each -- a single gradient without the
+        # strides of its parameter sends an optimizer's WHOLE multi-tensor update down the one-tensor-at-a-time path
+        # (measured: AdamW 5 -> 15 ms per step)
+        for p in self.params:
+            if p.grad is not None and not p.grad.is_contiguous():
+                p.grad = p.grad.contiguous()
+
+    def gather_buffers(self) -> List[torch.Tensor]:
+        """A few contiguous fp32 buffers that together hold every gradient exactly once, WITHOUT flattening the 1 324
+        per-pathway gradients of the gene encoder one by one (331 transposing copies and most of a ~50-launch ``cat``
+        per step in round 1): each stacked group is exchanged as its base tensor, or as one gathered parameter-layout
+        buffer (``_dense_group``), and ``p.grad`` aliases it.  The remaining gradients go into one small flat buffer.
+        The layout is a function of the model only, so every rank builds the same list."""
+        stacked, plain = self._stacked_groups()
+        bufs = [self._dense_group(base, members) for base, members in stacked]
         parts = [(self.params[i].grad if self.params[i].grad is not None else torch.zeros_like(self.params[i])).reshape(-1)
                  for i in plain]
         small = torch.cat(parts) if parts else torch.zeros(0, device=self.params[0].device)
@@ -179,7 +230,7 @@ class FlatGradAllReduce:
             p = self.params[i]
             p.grad = small[off:off + p.numel()].view_as(p)
             off += p.numel()
-        self.buffers = [small] + bases
+        self.buffers = [small] + bufs
         return self.buffers
 
     def all_reduce(self):
@@ -260,13 +311,18 @@ class GraphedStep:
             for _ in range(warmup):
                 flat.zero()
                 forward_backward(model, projector, slide)
+                flat.densify()     # also builds the (cached) gather indices outside the capture
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         flat.zero()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, pool=self._pool):
             self.loss, self.logits = forward_backward(model, projector, slide)
-            self._bufs = flat.gather_buffers() if self._flatten else None
+            if self._flatten:
+                self._bufs = flat.gather_buffers()
+            else:
+                self._bufs = None
+                flat.densify()     # gradients in parameter layout: the optimizer's multi-tensor path
         # views of the captured flat buffer, handed back to ``p.grad`` after every replay
         self._grad_views = [p.grad for p in flat.params]
         self._signature = self._frozen_signature()
