@@ -454,3 +454,32 @@ def test_variable_length_slides_and_pancancer_task_tokens():
     genes = [slide["genes"][i] for i in range(len(helpers.SMALL_GROUPS))]
     want = O.adapter_forward(sd, slide["x"][0], slide["coords"][0], genes, slide["clinical"], torch.eye(4)[3])
     assert helpers.relerr(outs[777][0].float().cpu(), want) < 2e-2
+
+
+@pytest.mark.parametrize("flag", ["injector_fused", "shared_extractor_kv", "split_param_grads", "cross_tc"])
+def test_round2_restructurings_agree_with_the_paths_before(model, flag):
+    """bf16 mode on the B200, 2 000-tile slide: each round-2 restructuring (fused Injector node with composed projections,
+    shared k | v projection of the last block's extractors, per-pass parameter aliases, TF32 tensor-core cross-attention)
+    against the path before it (its ``config`` switch off).  They differ by TF32 / bf16 rounding only."""
+    proj = helpers.build_projector(0, DEV)
+    slide = train_step.slide_to_device(synthetic.synthetic_slide(2000, seed=77, group_sizes=helpers.SMALL_GROUPS), DEV)
+
+    def run():
+        for p in model.parameters():
+            p.grad = None
+        loss, logits = train_step.forward_backward(model, proj, slide)
+        torch.cuda.synchronize()
+        g = torch.cat([p.grad.reshape(-1).double() for p in model.parameters() if p.requires_grad and p.grad is not None])
+        return float(loss), logits.clone(), g
+
+    with config.using(mode="bf16"):
+        on = run()
+        old = config._state[flag]
+        config._state[flag] = False
+        try:
+            off = run()
+        finally:
+            config._state[flag] = old
+    assert helpers.relerr(on[1], off[1]) < 5e-3, flag
+    assert abs(on[0] - off[0]) < 2e-3 * abs(off[0]), flag
+    assert _cos(on[2], off[2]) > 0.9999, flag
