@@ -548,7 +548,7 @@ def main():
         traffic = NCU_TRAFFIC_BWD
         traffic_src = "profiles/r2_ncu_attention.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
     bwd_names = {0: "simt", 1: "tcgen05", 2: "tcgen05-persistent"}
-    fwd_names = {0: "simt", 1: "tcgen05", 2: "tcgen05-persistent", 3: "tcgen05, 48-key tiles, 4 CTAs per SM"}
+    fwd_names = {0: "simt", 1: "tcgen05, 128-key tiles", 3: "tcgen05, 48-key tiles, 4 CTAs per SM"}
     roofline = {
         "bound": "tensor", "kernel": f"dilated_attn_bwd[{bwd_names[config.attn_impl('bwd')]}]", "achieved": ach_bwd,
         "peak": peak, "peak_source": peak_src, "unit": "TFLOP/s", "frac": ach_bwd / peak, "traffic": traffic,

@@ -183,9 +183,9 @@ int mt_ffn_bwd_prep(const float* dy, const float* y, const float* x1, const floa
  *        16/r_b heads that own position p (heads (p%r)*16/r ..), each head_dim wide.           (dtype)
  * lse_br: same compaction, [N][H/r_b] float, natural-log LSE including the zero-slot keys.
  * impl: 0 = SIMT fp32 math (any dtype; also the on-device cross-check of the tensor-core kernels), >= 1 = tcgen05 / TMA /
- * TMEM kernels (bf16 only): 1 = one CTA per work item, 2 = persistent CTAs that pull work items from a device counter
- * (identical arithmetic; the backward hands over between items without draining its pipeline), 3 (forward only) = one
- * CTA per work item with 48-key score tiles, four CTAs per SM (the default forward).  A shared-memory window that is not 1024-byte aligned (never expected) makes the tcgen05
+ * TMEM kernels (bf16 only): 1 = one CTA per work item, 2 (backward only) = persistent CTAs that pull work items from a
+ * device counter (identical arithmetic; hands over between items without draining its pipeline; the default backward),
+ * 3 (forward only) = one CTA per work item with 48-key score tiles, four CTAs per SM (the default forward).  A shared-memory window that is not 1024-byte aligned (never expected) makes the tcgen05
  * kernels trap: the failure surfaces as a CUDA error on the stream, never as silently unwritten outputs. */
 int mt_dilated_attn_fwd(const mt_dilated_geometry* geom, const void* qkv, int64_t qkv_ld, int64_t n_alloc, int dtype,
                         void* o_br, float* lse_br, int impl, void* stream);

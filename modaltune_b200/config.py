@@ -95,12 +95,12 @@ def compute_dtype() -> torch.dtype:
 
 
 # what "auto" resolves to in bf16 mode, per direction: the ``impl`` selector of mt_dilated_attn_{fwd,bwd}
-# (0 = SIMT fp32-math kernels, 1 = tcgen05 / TMA / TMEM kernels with one CTA per work item, 2 = the same pipeline in
-# persistent CTAs that pull items from a device counter, 3 (forward only) = 48-key score tiles: 120 TMEM columns and
-# 52 KB of shared memory per CTA, FOUR CTAs per SM).  Measured on B200 at 10k / 32k tokens: the persistent backward
-# is 7 - 9 % faster than the one-shot one (it runs ONE CTA per SM, so every item hand-over it overlaps is SM time won
-# back); the persistent forward is 4 % SLOWER than the one-shot forward (two CTAs per SM already hide each other's
-# prologue and epilogue); the 48-key forward is 13 % FASTER than impl 1 (0.173 against 0.197 ms at 10k tokens, 0.830
+# (0 = SIMT fp32-math kernels, 1 = tcgen05 / TMA / TMEM kernels with one CTA per work item, 2 (backward only) = the same
+# pipeline in persistent CTAs that pull items from a device counter, 3 (forward only) = 48-key score tiles: 120 TMEM
+# columns and 52 KB of shared memory per CTA, FOUR CTAs per SM).  Measured on B200 at 10k / 32k tokens: the persistent
+# backward is 7 - 9 % faster than the one-shot one (it runs ONE CTA per SM, so every item hand-over it overlaps is SM
+# time won back); a persistent forward was 4 % SLOWER than the one-shot forward (two CTAs per SM already hide each
+# other's prologue and epilogue) and has been removed; the 48-key forward is 13 % FASTER than impl 1 (0.173 against 0.197 ms at 10k tokens, 0.830
 # against 0.937 ms at 32k): sixteen softmax warps per SM keep the MUFU pipe busier than eight.
 AUTO_IMPL = {"fwd": 3, "bwd": 2}
 

@@ -735,385 +735,6 @@ dilated_fwd_sm100_k48_kernel(const __grid_constant__ TensorMaps maps, const __gr
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// forward, persistent (impl 2): the same per-tile pipeline, but the CTAs (2 per SM) stay resident and pull
-// (branch, segment, head, query tile) items from a device counter, longest key loops first.  Measured on B200
-// (tools/attn_timeline.py): a one-shot CTA lives 2 650 cycles per key tile + 4 400 cycles of prologue / epilogue, i.e. a
-// third of an 8-tile CTA's life is spent outside the loop.  Here the barriers, the TMEM allocation and the tensor-map
-// prefetch are paid once per SM, and the producer / MMA warps run ONE ITEM AHEAD: Q of the next item lands in the second
-// Q buffer and its first K / V tiles continue in the same ring while the softmax warps finish the current item, and the
-// first Q K^T of the next item is issued as soon as the last score tile of the current one has left TMEM.  The only
-// serial hand-over is the O accumulator: the first P V of an item waits until the previous item's O has been read out.
-// ---------------------------------------------------------------------------------------------------------------------
-struct FwdPSmem {
-  static constexpr int Q = 0;                                // [2]
-  static constexpr int K = Q + 2 * TILE_BYTES;
-  static constexpr int V = K + KV_STAGES * TILE_BYTES;
-  static constexpr int BAR = V + KV_STAGES * TILE_BYTES;
-  // sched_full[2], sched_empty[2], q_full[2], q_empty[2], kv_full[2], kv_empty[2], s_full, s_free, p_full, o_full, o_free
-  static constexpr int NBAR = 17;
-  static constexpr int QUEUE = BAR + NBAR * 8;               // int[2]: published item ids (-1 = no more work)
-  static constexpr int TMEM_PTR = QUEUE + 8;
-  static constexpr int TOTAL = TMEM_PTR + 16;
-};
-
-struct FwdItem {
-  int b, s, h, off, jseg, q0, n_kv, n_zero_tail;
-};
-
-// item id -> tile coordinates; false for a query tile that holds no real position (whole tiles of zero padding)
-__device__ __forceinline__ bool fwd_decode(const Sm100Params& P, int idx, FwdItem& it) {
-  int oi = 0;
-  while (oi + 1 < P.geo.nb && idx >= P.item_prefix[oi + 1]) ++oi;
-  it.b = P.order[oi];
-  const BranchGeom& bg = P.geo.b[it.b];
-  int local = idx - P.item_prefix[oi];
-  const int qt = local % P.tiles[it.b];
-  local /= P.tiles[it.b];
-  it.h = local % P.geo.H;
-  it.s = local / P.geo.H;
-  it.off = (it.h * bg.r) / P.geo.H;
-  it.jseg = (it.s * bg.g) / bg.r;
-  it.q0 = qt * BT;
-  const int seg_lo = it.s * bg.g + it.off;
-  const int seg_hi = min(P.geo.N, (it.s + 1) * bg.g);
-  const int c_real = seg_hi > seg_lo ? (seg_hi - seg_lo + bg.r - 1) / bg.r : 0;
-  it.n_kv = min(P.tiles[it.b], (c_real + BT - 1) / BT);
-  it.n_zero_tail = max(0, bg.m - it.n_kv * BT);
-  return it.q0 < c_real;
-}
-
-__global__ void __launch_bounds__(FWD_THREADS, 2)
-dilated_fwd_sm100_persistent_kernel(const __grid_constant__ TensorMaps maps, const Sm100Params P,
-                                    __nv_bfloat16* __restrict__ o_br, float* __restrict__ lse_br,
-                                    int* __restrict__ work_counter) {
-  MT_TL_BEGIN
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int W_TMA = 4, W_MMA = 5;
-  if ((sbase & 1023u) != 0) __trap();
-  const int H = P.geo.H, N = P.geo.N, E = H * DH;
-  const int total = P.item_prefix[P.geo.nb];
-
-  const uint32_t bar_sched_full = sbase + FwdPSmem::BAR + 0;     // [2]
-  const uint32_t bar_sched_empty = sbase + FwdPSmem::BAR + 16;   // [2]
-  const uint32_t bar_q_full = sbase + FwdPSmem::BAR + 32;        // [2]
-  const uint32_t bar_q_empty = sbase + FwdPSmem::BAR + 48;       // [2]
-  const uint32_t bar_kv_full = sbase + FwdPSmem::BAR + 64;       // [2]
-  const uint32_t bar_kv_empty = sbase + FwdPSmem::BAR + 80;      // [2]
-  const uint32_t bar_s_full = sbase + FwdPSmem::BAR + 96;
-  const uint32_t bar_s_free = sbase + FwdPSmem::BAR + 104;
-  const uint32_t bar_p_full = sbase + FwdPSmem::BAR + 112;
-  const uint32_t bar_o_full = sbase + FwdPSmem::BAR + 120;
-  const uint32_t bar_o_free = sbase + FwdPSmem::BAR + 128;
-  volatile int* queue = reinterpret_cast<volatile int*>(smem + FwdPSmem::QUEUE);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + FwdPSmem::TMEM_PTR);
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_sched_full + 8 * i, 1);
-      mbar_init(bar_sched_empty + 8 * i, 129);   // 128 softmax threads + the MMA warp
-      mbar_init(bar_q_full + 8 * i, 1);
-      mbar_init(bar_q_empty + 8 * i, 1);
-      mbar_init(bar_kv_full + 8 * i, 1);
-      mbar_init(bar_kv_empty + 8 * i, 1);
-    }
-    mbar_init(bar_s_full, 1);
-    mbar_init(bar_s_free, 128);
-    mbar_init(bar_p_full, 128);
-    mbar_init(bar_o_full, 1);
-    mbar_init(bar_o_free, 128);
-    fence_barrier_init();
-    for (int b = 0; b < P.geo.nb; ++b) tma_prefetch_desc(&maps.m[b]);
-  }
-  if (warp == W_MMA) {
-    tmem_alloc(smem_u32((const void*)tmem_slot), TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_s = tmem;
-  const uint32_t tmem_p = tmem + 128;
-  const uint32_t tmem_o = tmem + 192;
-  int n_tiles_done = 0;   // timeline only
-
-  if (warp == W_TMA) {
-    // ===== scheduler + TMA producer (one thread) ======================================================================
-    if (lane == 0) {
-      int t = 0;                                   // key tiles loaded so far (ring position)
-      int next_idx = atomicAdd(work_counter, 1);   // always one fetch in flight: its latency hides behind the loads
-      for (int n = 0;; ++n) {
-        FwdItem it;
-        int idx = next_idx;
-        while (idx < total && !fwd_decode(P, idx, it)) idx = atomicAdd(work_counter, 1);
-        next_idx = atomicAdd(work_counter, 1);
-        const int slot = n & 1, use = n >> 1;
-        mbar_wait(bar_sched_empty + 8 * slot, (use & 1) ^ 1);
-        queue[slot] = idx < total ? idx : -1;
-        mbar_arrive(bar_sched_full + 8 * slot);
-        if (idx >= total) break;
-        const void* map = &maps.m[it.b];
-        mbar_wait(bar_q_empty + 8 * slot, (use & 1) ^ 1);
-        mbar_expect_tx(bar_q_full + 8 * slot, TILE_BYTES);
-        tma_load_3d(sbase + FwdPSmem::Q + slot * TILE_BYTES, map, bar_q_full + 8 * slot, it.h * DH, it.off,
-                    it.jseg + it.q0);
-        for (int j = 0; j < it.n_kv; ++j, ++t) {
-          const int st = t & 1;
-          mbar_wait(bar_kv_empty + 8 * st, ((t >> 1) & 1) ^ 1);
-          mbar_expect_tx(bar_kv_full + 8 * st, 2 * TILE_BYTES);
-          tma_load_3d(sbase + FwdPSmem::K + st * TILE_BYTES, map, bar_kv_full + 8 * st, E + it.h * DH, it.off,
-                      it.jseg + j * BT);
-          tma_load_3d(sbase + FwdPSmem::V + st * TILE_BYTES, map, bar_kv_full + 8 * st, 2 * E + it.h * DH, it.off,
-                      it.jseg + j * BT);
-        }
-      }
-    }
-  } else if (warp == W_MMA) {
-    // ===== MMA issuer =================================================================================================
-    constexpr uint32_t IDESC_QK = umma_idesc_bf16(BT, BT, 0, 0);
-    constexpr uint32_t IDESC_PV = umma_idesc_bf16(BT, DH, 0, 1);
-    const uint64_t q_desc0 = umma_smem_desc(sbase + FwdPSmem::Q, 16, 1024);
-    const uint64_t k_desc0 = umma_smem_desc(sbase + FwdPSmem::K, 16, 1024);
-    const uint64_t v_desc0 = umma_smem_desc(sbase + FwdPSmem::V, TILE_BYTES, 1024);
-    // S = Q[qslot] K[t & 1]^T; `last` = last Q K^T of its item: the Q buffer is free once it has completed
-    auto issue_qk = [&](int qslot, int t, bool last) {
-      if (elect_one()) {
-        const uint64_t qd = umma_desc_adv(q_desc0, (uint32_t)qslot * TILE_BYTES);
-        const uint64_t kd = umma_desc_adv(k_desc0, (uint32_t)(t & 1) * TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          umma_ss(tmem_s, umma_desc_adv(qd, k * 32), umma_desc_adv(kd, k * 32), IDESC_QK, k > 0);
-        umma_commit(bar_s_full);
-        if (last) umma_commit(bar_q_empty + 8 * qslot);
-      }
-      __syncwarp();
-    };
-    // item n of this CTA -> n_kv (0 = no more work); every lane reads the queue, one lane releases the slot
-    auto get_item = [&](int n) -> int {
-      const int slot = n & 1;
-      mbar_wait(bar_sched_full + 8 * slot, (n >> 1) & 1);
-      const int idx = queue[slot];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_sched_empty + 8 * slot);
-      if (idx < 0) return 0;
-      FwdItem it;
-      fwd_decode(P, idx, it);
-      return it.n_kv;
-    };
-    int t = 0, n = 0;
-    int n_kv = get_item(0);
-    if (n_kv > 0) {
-      mbar_wait(bar_q_full, 0);
-      mbar_wait(bar_kv_full, 0);
-      tc_fence_after();
-      issue_qk(0, 0, n_kv == 1);
-    }
-    while (n_kv > 0) {
-      int n_kv_next = 0;
-      for (int j = 0; j < n_kv; ++j, ++t) {
-        // look one tile ahead: the next key tile of this item, or the first one of the next item
-        bool ahead = true, ahead_last = false;
-        int ahead_slot = n & 1;
-        if (j + 1 < n_kv) {
-          ahead_last = (j + 2 == n_kv);
-        } else {
-          n_kv_next = get_item(n + 1);
-          ahead = n_kv_next > 0;
-          ahead_slot = (n + 1) & 1;
-          ahead_last = (n_kv_next == 1);
-          if (ahead) mbar_wait(bar_q_full + 8 * ahead_slot, ((n + 1) >> 1) & 1);
-        }
-        if (ahead) {
-          mbar_wait(bar_kv_full + 8 * ((t + 1) & 1), ((t + 1) >> 1) & 1);
-          mbar_wait(bar_s_free, t & 1);        // the softmax threads have read S_t out of TMEM
-          tc_fence_after();
-          issue_qk(ahead_slot, t + 1, ahead_last);
-        }
-        mbar_wait(bar_p_full, t & 1);          // P_t is in TMEM
-        if (j == 0 && n > 0) mbar_wait(bar_o_free, (n - 1) & 1);   // the previous item's O has been read out
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t vd = umma_desc_adv(v_desc0, (uint32_t)(t & 1) * TILE_BYTES);
-#pragma unroll
-          for (int k = 0; k < BT / 16; ++k)
-            umma_ts(tmem_o, tmem_p + k * 8, umma_desc_adv(vd, k * 2048), IDESC_PV, (j > 0) || (k > 0));
-          umma_commit(bar_kv_empty + 8 * (t & 1));
-          umma_commit(bar_o_full);
-        }
-        __syncwarp();
-      }
-      n_kv = n_kv_next;
-      ++n;
-    }
-    n_tiles_done = t;
-  } else {
-    // ===== softmax: one query row per thread; O accumulates in TMEM over the key loop of an item ======================
-    const int lane_grp = warp & 3;
-    const int row = lane_grp * 32 + lane;
-    const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
-    const float scale_log2 = P.scale_log2;
-    int t = 0;
-    for (int n = 0;; ++n) {
-      const int slot = n & 1;
-      mbar_wait(bar_sched_full + 8 * slot, (n >> 1) & 1);
-      const int idx = queue[slot];
-      mbar_arrive(bar_sched_empty + 8 * slot);
-      if (idx < 0) break;
-      // only the loop length and the segment's slot count stay live across the key loop (its 128 scores per thread
-      // leave no registers to spare); the epilogue decodes the item again
-      int n_kv, seg_m;
-      {
-        FwdItem it0;
-        fwd_decode(P, idx, it0);
-        n_kv = it0.n_kv;
-        seg_m = P.geo.b[it0.b].m;
-      }
-      float m_used = -INFINITY, l_run = 0.f;
-      auto tile = [&](int j, auto mask_tag) {
-        constexpr bool MASK = decltype(mask_tag)::value;
-        const int kvalid = seg_m - j * BT;
-        mbar_wait(bar_s_full, t & 1);
-        tc_fence_after();
-        float sv[BT];
-        tmem_ld64(tmem_s + t_lane, sv);
-        tmem_ld64(tmem_s + t_lane + 64, sv + 64);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(bar_s_free);
-        if (MASK) {
-#pragma unroll
-          for (int i = 0; i < BT; ++i) sv[i] = (i < kvalid) ? sv[i] : -INFINITY;
-        }
-        float mx = fmax3(sv[0], sv[1], sv[2]);
-#pragma unroll
-        for (int i = 3; i + 1 < BT; i += 2) mx = fmax3(mx, sv[i], sv[i + 1]);
-        mx = fmaxf(mx, sv[BT - 1]);
-        bool waited = false;
-        if (j == 0) {
-          m_used = mx;
-        } else {
-          const bool need = (mx - m_used) * scale_log2 > 8.f;
-          if (__any_sync(0xffffffffu, need)) {
-            mbar_wait(bar_o_full, (t - 1) & 1);
-            tc_fence_after();
-            waited = true;
-            const float alpha = need ? ex2((m_used - mx) * scale_log2) : 1.f;
-            float o8[8];
-#pragma unroll
-            for (int c = 0; c < DH / 8; ++c) {
-              tmem_ld8(tmem_o + t_lane + c * 8, o8);
-              tmem_ld_wait();
-              uint32_t u[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) u[i] = __float_as_uint(o8[i] * alpha);
-              tmem_st8(tmem_o + t_lane + c * 8, u);
-            }
-            if (need) {
-              l_run *= alpha;
-              m_used = mx;
-            }
-          }
-        }
-        const float mb = m_used * scale_log2;
-        // P_t overwrites P_{t-1}: its P V must have read it.  For the first tile of an item that P V belongs to the
-        // previous item, whose epilogue has already waited for it.
-        if (j > 0 && !waited) {
-          mbar_wait(bar_o_full, (t - 1) & 1);
-          tc_fence_after();
-        }
-        float rs = 0.f;
-#pragma unroll
-        for (int c = 0; c < BT / 32; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2(fmaf(sv[c * 32 + i], scale_log2, -mb));
-            const float p1 = ex2(fmaf(sv[c * 32 + i + 1], scale_log2, -mb));
-            rs += p0 + p1;
-            pk[i >> 1] = pack_bf16(p0, p1);
-          }
-          tmem_st16(tmem_p + t_lane + c * 16, pk);
-        }
-        l_run += rs;
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(bar_p_full);
-      };
-      for (int j = 0; j < n_kv; ++j, ++t) {
-        if (seg_m - j * BT >= BT) tile(j, std::false_type{});
-        else tile(j, std::true_type{});
-      }
-      // ---- epilogue of the item: O out of TMEM, then the accumulator is free for the next item ----------------------
-      mbar_wait(bar_o_full, (t - 1) & 1);
-      tc_fence_after();
-      float o_acc[DH];
-#pragma unroll
-      for (int c = 0; c < DH / 16; ++c) {
-        float t16[16];
-        tmem_ld16(tmem_o + t_lane + c * 16, t16);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] = t16[i];
-      }
-      tc_fence_before();
-      mbar_arrive(bar_o_free);
-      int idx2 = idx;
-      asm volatile("" : "+r"(idx2));   // decode again instead of keeping the item's fields live across the loop
-      FwdItem it;
-      fwd_decode(P, idx2, it);
-      const BranchGeom& bg = P.geo.b[it.b];
-      if (it.n_zero_tail > 0) {   // the zero keys of the tiles that were skipped
-        const float m_fin = fmaxf(m_used, 0.f);
-        const float alpha = ex2((m_used - m_fin) * scale_log2);
-        l_run = l_run * alpha + (float)it.n_zero_tail * ex2(-m_fin * scale_log2);
-#pragma unroll
-        for (int i = 0; i < DH; ++i) o_acc[i] *= alpha;
-        m_used = m_fin;
-      }
-      const int slot_q = it.q0 + row;
-      const int pos = it.s * bg.g + it.off + slot_q * bg.r;
-      const int seg_end = min(N, (it.s + 1) * bg.g);
-      if (slot_q < bg.m && pos < seg_end) {
-        const float inv = 1.f / l_run;
-        const int slot_h = it.h - it.off * bg.hpb;
-        __nv_bfloat16* dst = o_br + bg.o_off + ((int64_t)pos * bg.hpb + slot_h) * DH;
-#pragma unroll
-        for (int c = 0; c < DH / 8; ++c) {
-          uint4 u;
-          u.x = pack_bf16(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
-          u.y = pack_bf16(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
-          u.z = pack_bf16(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv);
-          u.w = pack_bf16(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
-          *reinterpret_cast<uint4*>(dst + c * 8) = u;
-        }
-        lse_br[bg.lse_off + (int64_t)pos * bg.hpb + slot_h] = m_used * P.scale + logf(l_run);
-      }
-    }
-  }
-  // ---- teardown: the last CTA to finish re-arms the work counter for the next launch that uses it --------------------
-  tc_fence_before();
-  __syncthreads();
-  if (warp == W_MMA) tmem_dealloc(tmem, TMEM_COLS);
-  if (threadIdx.x == 0) {
-    if (atomicAdd(work_counter + 1, 1) == (int)gridDim.x - 1) {
-      work_counter[1] = 0;
-      __threadfence();
-      work_counter[0] = 0;
-    }
-  }
-#ifdef MT_DEBUG_TIMELINE
-  if (threadIdx.x == W_MMA * 32) {
-    unsigned sm_;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));
-    long long* e_ = mt_timeline + 4 * blockIdx.x;
-    e_[0] = sm_; e_[1] = n_tiles_done; e_[2] = tl_t0_; e_[3] = clock64();
-  }
-#endif
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1255,22 +876,8 @@ int dilated_attn_fwd_sm100(const mt_dilated_geometry* geom, const void* qkv, int
         maps, kv_maps, P, (__nv_bfloat16*)o_br, lse_br);
     return check_launch("dilated_fwd_sm100_k48_kernel");
   }
-  if (impl == 2) {   // persistent CTAs with a device work counter
-    int* counter = next_work_counter();
-    MT_REQUIRE(counter != nullptr, "dilated_attn_fwd: cannot allocate the work counters");
-    const int items = P.item_prefix[P.geo.nb];
-    const int grid = items < 2 * kNumSMs ? items : 2 * kNumSMs;
-    {
-    static bool attr_set = false;   // once per process: the call is not free and never changes
-    if (!attr_set) {
-      MT_CUDA(cudaFuncSetAttribute(dilated_fwd_sm100_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdPSmem::TOTAL));
-      attr_set = true;
-    }
-  }
-    dilated_fwd_sm100_persistent_kernel<<<grid, FWD_THREADS, FwdPSmem::TOTAL, st>>>(maps, P, (__nv_bfloat16*)o_br, lse_br,
-                                                                                   counter);
-    return check_launch("dilated_fwd_sm100_persistent_kernel");
-  }
+  MT_REQUIRE(impl == 1, "dilated_attn_fwd: impl must be 0 (SIMT), 1 (128-key tiles) or 3 (48-key tiles, default); the "
+             "persistent forward of round 2 (impl 2) measured 4 %% slower than impl 1 and was removed");
   {
     static bool attr_set = false;   // once per process: the call is not free and never changes
     if (!attr_set) {

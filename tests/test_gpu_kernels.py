@@ -288,7 +288,7 @@ def test_dilated_attention_linearity_in_v_at_full_size():
 # sizes at which the tcgen05 kernels are held against the ORACLE itself (not only against the SIMT kernels): every small
 # geometry plus the bench geometries of BASELINE configs 2 and 3 (the oracle core needs 2 - 25 s of host time there)
 ORACLE_SIZES = {n for n, _ in GEOMS} | {5793, 10001, 32769}
-FWD_IMPLS = (1, 2, 3)   # tcgen05 variants of mt_dilated_attn_fwd: one CTA per item, persistent CTAs, 48-key score tiles (0 = SIMT cross-check)
+FWD_IMPLS = (1, 3)   # tcgen05 variants of mt_dilated_attn_fwd: 128-key and 48-key (default) score tiles (0 = SIMT cross-check)
 SM100_GEOMS = GEOMS + [(5793, None), (10001, None), (300, [128, 256, 512, 1024, 2048]),
                        # whole-tile padding skip: last segments with 1 / 128 / 129 real slots, real counts that are
                        # exact multiples of the 128-slot tile, tails of several all-padding tiles in every branch
@@ -321,7 +321,7 @@ def test_dilated_attention_tcgen05_forward(N, sl):
 @pytest.mark.parametrize("N", [1025, 5793])
 def test_dilated_attention_tcgen05_forward_rising_maximum(N):
     """Key magnitudes grow along the sequence, so the running row maximum jumps by far more than the lazy-rescale
-    threshold (2^8) in later key tiles: the in-TMEM rescale of the O accumulator (forward impl 2) must kick in."""
+    threshold (2^8) in later key tiles: the in-TMEM rescale of the O accumulator must kick in."""
     geom = ops.Geometry.get(N, optimal_segment_lengths(), DILATED_RATIO)
     g = torch.Generator().manual_seed(7 * N)
     qkv = torch.zeros(geom.n_alloc, 2304)

@@ -7,7 +7,7 @@ from modaltune_b200.slide_encoder import DILATED_RATIO, optimal_segment_lengths
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 10001
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 bwd_impl = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-fwd_impl = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+fwd_impl = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 dev = "cuda"
 geom = ops.Geometry.get(N, optimal_segment_lengths(), DILATED_RATIO)
 g = torch.Generator().manual_seed(0)
